@@ -1,0 +1,127 @@
+/* mpasb.h -- C ABI of the B200-native MPAS-Atmosphere dycore step.
+ *
+ * Drop-in boundary: the reference's time-integration driver
+ *     call atm_timestep(domain, dt, currTime, itimestep, exchange_halo_group)
+ *         src/core_atmosphere/mpas_atm_core.F:1022
+ *         src/core_atmosphere/dynamics/mpas_atm_time_integration.F:739-800 (atm_timestep)
+ *         ... :803-1725 (atm_srk3)
+ * keeps its name and signature in the Fortran host; its body becomes
+ * mpasb_set_field (first call / after a restart read) -> mpasb_step ->
+ * mpasb_get_field (on output/restart alarms).  INTEGRATION.md shows the
+ * ISO_C_BINDING interface block that binds these symbols.
+ *
+ * Conventions (identical to what a Fortran caller holds in its pools):
+ *   - real arrays are RKIND (double in this build), dense, Fortran order,
+ *     outer extent n+1 (the trailing "garbage" element, mpas_block_creator.F:1050-1121)
+ *   - integer arrays are default 4-byte integers, connectivity is 1-BASED with
+ *     out-of-block references equal to n+1 (mpas_block_creator.F:1464-1531)
+ *   - every function returns 0 on success, nonzero on error (the host maps it to
+ *     MPAS_LOG_CRIT, src/framework/mpas_log.F:627-629); mpasb_last_error() gives text.
+ *   - one host thread per handle; one handle per mesh block per GPU.
+ */
+#ifndef MPASB_H
+#define MPASB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double mpasb_real;      /* RKIND, PRECISION=double build */
+
+/* Block dimensions: mesh pool dims + block%dimensions (mpas_atm_time_integration.F:921-962). */
+typedef struct mpasb_dims {
+    int nCells, nEdges, nVertices;                 /* owned + halo, without the garbage slot */
+    int nCellsSolve, nEdgesSolve, nVerticesSolve;  /* owned prefix */
+    int nVertLevels, maxEdges, maxEdges2, vertexDegree;
+    int num_scalars, index_qv, moist_start, moist_end;   /* 1-based scalar indices */
+} mpasb_dims;
+
+/* Namelist options the hot path reads (defaults Registry.xml:63-395)
+ * plus the three mesh scalars cf1..cf3 and sphere_radius. */
+typedef struct mpasb_config {
+    int config_time_integration_order;      /* 2 | 3,          TI:891  */
+    int config_number_of_sub_steps;         /*                 TI:890  */
+    int config_dynamics_split_steps;        /*                 TI:898  */
+    int config_split_dynamics_transport;    /* logical         TI:897  */
+    int config_scalar_advection;            /* logical         TI:892  */
+    int config_monotonic;                   /* logical         TI:894  */
+    int config_positive_definite;           /* logical         TI:893  */
+    int config_horiz_mixing;                /* 0 = "2d_smagorinsky", 1 = "2d_fixed"  TI:5226,5261 */
+    int config_mix_full;                    /* logical         TI:5594 */
+    int config_rayleigh_damp_u;             /* logical         TI:5667 */
+    int config_number_rayleigh_damp_u_levels;
+    int config_number_cam_damping_levels;
+    int config_apply_lbcs;                  /* must be 0: regional path is out of scope */
+    int config_print_global_minmax_vel;     /* logical         TI:7960 */
+    double config_epssm, config_smdiv, config_len_disp, config_coef_3rd_order;
+    double config_visc4_2dsmag, config_smagorinsky_coef, config_del4u_div_factor;
+    double config_h_mom_eddy_visc2, config_h_mom_eddy_visc4, config_v_mom_eddy_visc2;
+    double config_h_theta_eddy_visc2, config_h_theta_eddy_visc4, config_v_theta_eddy_visc2;
+    double config_apvm_upwinding, config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days;
+    double cf1, cf2, cf3, sphere_radius;
+} mpasb_config;
+
+typedef struct mpasb_handle_s* mpasb_handle;
+
+/* mpas_atm_dynamics_init (TI:205) / mpas_atm_dynamics_finalize (TI:479) */
+int  mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int device, mpasb_handle* out);
+int  mpasb_destroy(mpasb_handle h);
+const char* mpasb_last_error(mpasb_handle h);
+
+/* Field import/export by pool key (include/mpasb_fields.def lists every key).
+ * time_level is 1 or 2 for state fields, 1 otherwise.  count = number of
+ * elements of the dense host array (checked).  mpas_pool_get_array equivalents. */
+int  mpasb_set_field(mpasb_handle h, const char* name, int time_level, const mpasb_real* src, long count);
+int  mpasb_get_field(mpasb_handle h, const char* name, int time_level, mpasb_real* dst, long count);
+int  mpasb_set_field_int(mpasb_handle h, const char* name, const int* src, long count);
+int  mpasb_field_count(mpasb_handle h, const char* name, long* count);   /* dense host element count */
+
+/* atm_srk3 (TI:803-1725): advance state level 1 -> level 2 by dt.  Followed by
+ * mpasb_shift_time_levels == mpas_pool_shift_time_levels(state) (mpas_atm_core.F:808). */
+int  mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep);
+int  mpasb_shift_time_levels(mpasb_handle h);
+/* summarize_timestep (TI:7914-8357): out = {min w, max w, min u, max u} of level 2,
+ * reductions start from 0 as in TI:8291-8292. */
+int  mpasb_minmax(mpasb_handle h, mpasb_real out[4]);
+int  mpasb_synchronize(mpasb_handle h);
+
+/* Init-time routines of the path: atm_init_coupled_diagnostics (TI:6776) and
+ * atm_compute_solve_diagnostics without rk_step (mpas_atm_core.F:515-527). */
+int  mpasb_init_coupled_diagnostics(mpasb_handle h);
+int  mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt);
+
+/* Kernel-level entry points, one per *_work routine, operating on the
+ * device-resident fields of the handle (parity tests drive one at a time). */
+int  mpasb_k_rk_integration_setup(mpasb_handle h);                                   /* TI:1930 */
+int  mpasb_k_compute_moist_coefficients(mpasb_handle h);                             /* TI:2042 */
+int  mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts);                 /* TI:2225 */
+int  mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt);           /* TI:4982 */
+int  mpasb_k_set_smlstep_pert_variables(mpasb_handle h);                             /* TI:2427 */
+int  mpasb_k_advance_acoustic_step(mpasb_handle h, mpasb_real dts, int small_step);  /* TI:2646 */
+int  mpasb_k_divergence_damping_3d(mpasb_handle h, mpasb_real dts);                  /* TI:2987 */
+int  mpasb_k_recover_large_step_variables(mpasb_handle h, mpasb_real dt, int ns, int rk_step); /* TI:3189 */
+int  mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, int rk_step);  /* TI:6337 */
+int  mpasb_k_rk_dynamics_substep_finish(mpasb_handle h, int dynamics_substep, int dynamics_split); /* TI:7013 */
+int  mpasb_k_advance_scalars(mpasb_handle h, mpasb_real dt, int rk_step);            /* TI:3575 */
+int  mpasb_k_advance_scalars_mono(mpasb_handle h, mpasb_real dt);                    /* TI:4012 */
+
+/* Halo exchange (mpas_halo_exch_group_full_halo_exch, src/framework/mpas_halo.F:498-846).
+ * Lists are the reference's per-field sendListSrc/recvListDst (1-based local
+ * indices), grouped per neighbour rank and halo layer (mpas_halo_types.inc:22-32). */
+int  mpasb_set_halo_lists(mpasb_handle h, int kind /*0 cell,1 edge,2 vertex*/, int n_neighbors,
+                          const int* neighbor_rank, int n_layers,
+                          const int* n_send /*[n_neighbors*n_layers]*/, const int* send_src,
+                          const int* n_recv /*[n_neighbors*n_layers]*/, const int* recv_dst);
+int  mpasb_comm_init(mpasb_handle h, int rank, int world_size, const void* nccl_unique_id /*128 bytes*/);
+int  mpasb_get_nccl_unique_id(void* out128);
+int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HALOS:90-167 names */
+
+/* Instrumentation */
+long mpasb_kernel_launch_count(mpasb_handle h);      /* kernels launched by this handle so far */
+int  mpasb_set_profile(mpasb_handle h, int on);      /* per-routine CUDA-event timing */
+int  mpasb_get_profile(mpasb_handle h, char* buf, long buflen);  /* "name ms count\n" lines */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPASB_H */

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's time-integration interface.
+
+``Dycore`` binds the C ABI of ``csrc/libmpasb.so`` (include/mpasb.h) with ctypes
+and exposes the reference's entry points under their own names:
+
+  atm_timestep(dt, itimestep)          mpas_atm_time_integration.F:739
+  atm_srk3(dt, itimestep)              ... :803
+  atm_init_coupled_diagnostics()       ... :6776
+  atm_compute_solve_diagnostics(...)   ... :6243
+  mpas_pool_shift_time_levels()        mpas_atm_core.F:808
+  exchange_halo_group(name)            mpas_atm_halos.F:29
+  get_array(name, time_level) / set_array(...)   == mpas_pool_get_array
+
+There is no CPU fallback: constructing a ``Dycore`` without the CUDA library
+(or calling into it without a GPU) raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .fields import FIELDS, host_shape
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpasb.so")
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "nCells", "nEdges", "nVertices", "nCellsSolve", "nEdgesSolve", "nVerticesSolve",
+        "nVertLevels", "maxEdges", "maxEdges2", "vertexDegree",
+        "num_scalars", "index_qv", "moist_start", "moist_end")]
+
+
+_CFG_INT = ("config_time_integration_order", "config_number_of_sub_steps", "config_dynamics_split_steps",
+            "config_split_dynamics_transport", "config_scalar_advection", "config_monotonic",
+            "config_positive_definite", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
+            "config_number_rayleigh_damp_u_levels", "config_number_cam_damping_levels", "config_apply_lbcs",
+            "config_print_global_minmax_vel")
+_CFG_REAL = ("config_epssm", "config_smdiv", "config_len_disp", "config_coef_3rd_order",
+             "config_visc4_2dsmag", "config_smagorinsky_coef", "config_del4u_div_factor",
+             "config_h_mom_eddy_visc2", "config_h_mom_eddy_visc4", "config_v_mom_eddy_visc2",
+             "config_h_theta_eddy_visc2", "config_h_theta_eddy_visc4", "config_v_theta_eddy_visc2",
+             "config_apvm_upwinding", "config_mpas_cam_coef", "config_rayleigh_damp_u_timescale_days",
+             "cf1", "cf2", "cf3", "sphere_radius")
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in _CFG_INT] + [(n, C.c_double) for n in _CFG_REAL]
+
+
+def make_dims(d: dict) -> Dims:
+    """Pool dimensions of a block dict (0-based scalar indices -> 1-based)."""
+    return Dims(
+        nCells=d["nCells"], nEdges=d["nEdges"], nVertices=d["nVertices"],
+        nCellsSolve=d.get("nCellsSolve", d["nCells"]), nEdgesSolve=d.get("nEdgesSolve", d["nEdges"]),
+        nVerticesSolve=d.get("nVerticesSolve", d["nVertices"]),
+        nVertLevels=d["nVertLevels"], maxEdges=d["maxEdges"], maxEdges2=d["maxEdges2"],
+        vertexDegree=d["vertexDegree"], num_scalars=d["num_scalars"], index_qv=d["index_qv"] + 1,
+        moist_start=d["moist_start"] + 1, moist_end=d["moist_end"] + 1)
+
+
+def make_config(cfg: dict, d: dict) -> Config:
+    c = Config()
+    for n in _CFG_INT:
+        v = cfg.get(n, 0)
+        if n == "config_horiz_mixing":
+            v = {"2d_smagorinsky": 0, "2d_fixed": 1}[v]
+        setattr(c, n, int(v))
+    for n in _CFG_REAL:
+        setattr(c, n, float(d[n] if n in ("cf1", "cf2", "cf3", "sphere_radius") else cfg.get(n, 0.0)))
+    c.config_print_global_minmax_vel = 1
+    return c
+
+
+class Backend:
+    """Common host logic of the CUDA library binding and the oracle binding:
+    moving a block dict (numpy, 0-based) through the by-name field ABI."""
+
+    dims: Dims
+
+    # -- to be provided by the concrete binding
+    def _set_real(self, name, lev, arr): raise NotImplementedError
+    def _get_real(self, name, lev, out): raise NotImplementedError
+    def _set_int(self, name, arr): raise NotImplementedError
+
+    def shape(self, name):
+        return host_shape(FIELDS[name], self.dims)
+
+    def set_array(self, name, arr, time_level=1):
+        fd = FIELDS[name]
+        shp = self.shape(name)
+        if fd.type == "INT":
+            a = np.ascontiguousarray(arr, dtype=np.int32).reshape(shp)
+            if fd.target != "NONE":
+                a = a + 1                     # the ABI is 1-based, like the Fortran pools
+            self._set_int(name, np.ascontiguousarray(a))
+        else:
+            a = np.ascontiguousarray(arr, dtype=np.float64).reshape(shp)
+            self._set_real(name, time_level, a)
+
+    def get_array(self, name, time_level=1):
+        out = np.empty(self.shape(name), dtype=np.float64)
+        self._get_real(name, time_level, out)
+        return out
+
+    def load_block(self, d: dict):
+        """Import every table field present in ``d``.  State fields go to time
+        level 1 (and, for ``u``/``w``/..., ``<name>_2`` to level 2 if given)."""
+        for name, fd in FIELDS.items():
+            if name in d and not np.isscalar(d[name]):
+                self.set_array(name, d[name], 1)
+            if fd.levels == 2 and (name + "_2") in d:
+                self.set_array(name, d[name + "_2"], 2)
+
+    def state(self, time_level=1, names=("u", "w", "rho_zz", "theta_m", "scalars")):
+        return {n: self.get_array(n, time_level) for n in names}
+
+
+def _load_lib():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"CUDA library {LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the dycore step)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mpasb_last_error.restype = C.c_char_p
+    lib.mpasb_last_error.argtypes = [C.c_void_p]
+    lib.mpasb_kernel_launch_count.restype = C.c_long
+    lib.mpasb_kernel_launch_count.argtypes = [C.c_void_p]
+    return lib
+
+
+class Dycore(Backend):
+    """One mesh block resident on one GPU."""
+
+    def __init__(self, block: dict, cfg: dict, device: int = 0):
+        self.lib = _load_lib()
+        self.dims = make_dims(block)
+        self.config = make_config(cfg, block)
+        self.cfg = dict(cfg)
+        self._h = C.c_void_p()
+        rc = self.lib.mpasb_create(C.byref(self.dims), C.byref(self.config), C.c_int(device), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"mpasb_create failed ({rc}): no usable CUDA device or bad dimensions")
+        self.load_block(block)
+
+    # -- low level
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.mpasb_last_error(self._h)
+            raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _set_real(self, name, lev, arr):
+        self._check(self.lib.mpasb_set_field(self._h, name.encode(), C.c_int(lev),
+                                             arr.ctypes.data_as(C.c_void_p), C.c_long(arr.size)), f"set_field {name}")
+
+    def _get_real(self, name, lev, out):
+        self._check(self.lib.mpasb_get_field(self._h, name.encode(), C.c_int(lev),
+                                             out.ctypes.data_as(C.c_void_p), C.c_long(out.size)), f"get_field {name}")
+
+    def _set_int(self, name, arr):
+        self._check(self.lib.mpasb_set_field_int(self._h, name.encode(),
+                                                 arr.ctypes.data_as(C.c_void_p), C.c_long(arr.size)), f"set_field_int {name}")
+
+    def close(self):
+        if self._h:
+            self.lib.mpasb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference entry points
+    def atm_init_coupled_diagnostics(self):
+        self._check(self.lib.mpasb_init_coupled_diagnostics(self._h), "init_coupled_diagnostics")
+
+    def atm_init_solve_diagnostics(self, dt):
+        self._check(self.lib.mpasb_init_solve_diagnostics(self._h, C.c_double(dt)), "init_solve_diagnostics")
+
+    def atm_srk3(self, dt, itimestep=1):
+        self._check(self.lib.mpasb_step(self._h, C.c_double(dt), C.c_int(itimestep)), "mpasb_step")
+
+    atm_timestep = atm_srk3      # config_time_integration == 'SRK3' is the only integrator (TI:773-790)
+
+    def mpas_pool_shift_time_levels(self):
+        self._check(self.lib.mpasb_shift_time_levels(self._h), "shift_time_levels")
+
+    def summarize_timestep(self):
+        out = (C.c_double * 4)()
+        self._check(self.lib.mpasb_minmax(self._h, out), "minmax")
+        return tuple(out)
+
+    def synchronize(self):
+        self._check(self.lib.mpasb_synchronize(self._h), "synchronize")
+
+    def exchange_halo_group(self, name):
+        self._check(self.lib.mpasb_exchange_halo_group(self._h, name.encode()), f"exchange {name}")
+
+    def kernel_launch_count(self):
+        return int(self.lib.mpasb_kernel_launch_count(self._h))
+
+    def set_profile(self, on=True):
+        self.lib.mpasb_set_profile(self._h, C.c_int(1 if on else 0))
+
+    def get_profile(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.mpasb_get_profile(self._h, buf, C.c_long(len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            n, ms, cnt = line.split()
+            rows.append((n, float(ms), int(cnt)))
+        return rows
+
+    # -- one *_work routine at a time (parity tests)
+    def k(self, routine, *args):
+        fn = getattr(self.lib, "mpasb_k_" + routine)
+        cargs = [C.c_double(a) if isinstance(a, float) else C.c_int(a) for a in args]
+        self._check(fn(self._h, *cargs), routine)

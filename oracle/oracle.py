@@ -1,0 +1,109 @@
+"""ctypes binding of the CPU parity oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see the header of dycore_oracle.cpp.  Imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never by the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mpas_model_b200.dycore import Backend, make_config, make_dims
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "dycore_oracle.cpp")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.oracle_create.restype = C.c_void_p
+        _lib.oracle_field_count.restype = C.c_long
+    return _lib
+
+
+class OracleDycore(Backend):
+    def __init__(self, block: dict, cfg: dict, rank: int = 0):
+        self.lib = lib()
+        self.dims = make_dims(block)
+        self.config = make_config(cfg, block)
+        self._h = C.c_void_p(self.lib.oracle_create(C.byref(self.dims), C.byref(self.config), C.c_int(rank)))
+        self.load_block(block)
+
+    def _set_real(self, name, lev, arr):
+        rc = self.lib.oracle_set_field(self._h, name.encode(), C.c_int(lev), arr.ctypes.data_as(C.c_void_p), C.c_long(arr.size))
+        assert rc == 0, name
+
+    def _get_real(self, name, lev, out):
+        rc = self.lib.oracle_get_field(self._h, name.encode(), C.c_int(lev), out.ctypes.data_as(C.c_void_p), C.c_long(out.size))
+        assert rc == 0, name
+
+    def _set_int(self, name, arr):
+        rc = self.lib.oracle_set_field_int(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), C.c_long(arr.size))
+        assert rc == 0, name
+
+    def close(self):
+        if self._h:
+            self.lib.oracle_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_halo_lists(self, kind, lists):
+        """lists: {"neighbors": [rank..], "send": [[arr per layer] per nbr], "recv": ...}, 0-based local indices."""
+        nbrs = np.asarray(lists["neighbors"], dtype=np.int32)
+        nl = lists["n_layers"]
+        n_send = np.array([[len(lists["send"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
+        n_recv = np.array([[len(lists["recv"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
+        cat = lambda key: (np.concatenate([np.asarray(a, dtype=np.int32) for per in lists[key] for a in per] + [np.zeros(0, np.int32)]) + 1).astype(np.int32)
+        ss, rr = np.ascontiguousarray(cat("send")), np.ascontiguousarray(cat("recv"))
+        self.lib.oracle_set_halo_lists(self._h, C.c_int(kind), C.c_int(len(nbrs)), nbrs.ctypes.data_as(C.c_void_p), C.c_int(nl),
+                                       n_send.ctypes.data_as(C.c_void_p), ss.ctypes.data_as(C.c_void_p),
+                                       n_recv.ctypes.data_as(C.c_void_p), rr.ctypes.data_as(C.c_void_p))
+
+    # reference entry points
+    def atm_init_coupled_diagnostics(self): self.lib.oracle_init_coupled_diagnostics(self._h)
+    def atm_init_solve_diagnostics(self, dt): self.lib.oracle_init_solve_diagnostics(self._h, C.c_double(dt))
+    def atm_srk3(self, dt, itimestep=1): step([self], dt)
+    atm_timestep = atm_srk3
+    def mpas_pool_shift_time_levels(self): self.lib.oracle_shift_time_levels(self._h)
+
+    def summarize_timestep(self):
+        out = (C.c_double * 4)()
+        self.lib.oracle_minmax(self._h, out)
+        return tuple(out)
+
+    def k(self, routine, *args):
+        fn = getattr(self.lib, "oracle_" + routine)
+        fn(self._h, *[C.c_double(a) if isinstance(a, float) else C.c_int(a) for a in args])
+
+
+def step(blocks, dt):
+    """atm_srk3 over N in-process blocks ("virtual ranks") in lock step."""
+    arr = (C.c_void_p * len(blocks))(*[b._h for b in blocks])
+    lib().oracle_step(arr, C.c_int(len(blocks)), C.c_double(dt))
+
+
+def exchange(blocks, group):
+    arr = (C.c_void_p * len(blocks))(*[b._h for b in blocks])
+    lib().oracle_exchange(arr, C.c_int(len(blocks)), group.encode())
