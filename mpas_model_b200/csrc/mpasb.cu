@@ -1,0 +1,539 @@
+// mpasb.cu -- host side of the B200-native MPAS-A dycore step and its C ABI (include/mpasb.h).
+//
+// atm_srk3 (mpas_atm_time_integration.F:803-1725) is re-expressed as a fixed sequence of
+// kernel launches on one CUDA stream over device-resident, level-contiguous fields; the
+// reference's per-routine host<->device copies (e.g. TI:2739-2749 / 2976-2982) do not exist
+// here.  Halo exchanges are pack-kernel -> NCCL send/recv -> unpack-kernel on the same stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+#include "../../include/mpasb.h"
+#include "kernels_dyn.cuh"
+#include "kernels_acoustic.cuh"
+#include "kernels_diag.cuh"
+#include "kernels_transport.cuh"
+#include "halo.cuh"
+
+enum { T_REAL = 0, T_INT = 1 };
+enum { TG_NONE = 0, TG_LOCAL, TG_CELL, TG_EDGE, TG_VERTEX };
+
+struct FieldRec {
+    const char* name; int loc, inner, levels, type, target;
+    void* d[2];            // device buffers per time level
+    size_t dev_count;      // elements per buffer
+    long host_count;       // dense host elements
+};
+
+struct ProfRec { double ms = 0; long count = 0; };
+
+struct mpasb_handle_s {
+    mpasb_dims dims; mpasb_config cfg; int device = 0;
+    cudaStream_t stream = nullptr;
+    Dev D;
+    std::vector<FieldRec> fields;
+    std::map<std::string, int> index;
+    void* staging = nullptr; size_t staging_bytes = 0;
+    real* d_minmax = nullptr;
+    std::string err;
+    long launches = 0;
+    int cpb = 4;
+    bool profile = false;
+    std::map<std::string, ProfRec> prof;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    HaloState halo;
+};
+typedef mpasb_handle_s H;
+
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+
+static int inner_dense1(const H* h, int in) {
+    const mpasb_dims& d = h->dims;
+    switch (in) {
+        case IN_ONE: return 1; case IN_NL: return d.nVertLevels; case IN_NL1: return d.nVertLevels + 1;
+        case IN_ME: return d.maxEdges; case IN_ME2: return d.maxEdges2; case IN_VD: return d.vertexDegree;
+        case IN_TWO: return 2; case IN_F15: return 15; case IN_NL1_ME: return d.nVertLevels + 1;
+        case IN_S_NL: return d.num_scalars; case IN_NL_TWO: return d.nVertLevels;
+    }
+    return 1;
+}
+static int inner_dense2(const H* h, int in) {
+    switch (in) { case IN_NL1_ME: return h->dims.maxEdges; case IN_S_NL: return h->dims.nVertLevels; case IN_NL_TWO: return 2; default: return 1; }
+}
+static size_t outer_of(const H* h, int loc) {
+    switch (loc) { case LOC_CELL: return (size_t)h->dims.nCells + 1; case LOC_EDGE: return (size_t)h->dims.nEdges + 1;
+                   case LOC_VERTEX: return (size_t)h->dims.nVertices + 1; default: return 1; }
+}
+static size_t dev_count_of(const H* h, int loc, int in) {
+    const size_t o = outer_of(h, loc); const size_t L = h->D.LDK;
+    switch (in) {
+        case IN_NL: case IN_NL1: return o * L;
+        case IN_NL1_ME: return o * h->dims.maxEdges * L;
+        case IN_S_NL: return o * L * h->dims.num_scalars;
+        case IN_NL_TWO: return o * L * 2;
+        default: return o * inner_dense1(h, in);
+    }
+}
+
+static void set_dev_ptr(H* h, const FieldRec& f);
+
+extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int device, mpasb_handle* out) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 2;      // fail loudly: no CPU fallback
+    if (device < 0 || device >= ndev) return 3;
+    if (dims->nVertLevels < 4 || dims->maxEdges < 1 || cfg->config_apply_lbcs) return 4;
+    H* h = new H();
+    h->dims = *dims; h->cfg = *cfg; h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return 5; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    memset(&h->D, 0, sizeof(Dev));
+    Dev& D = h->D;
+    D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
+    D.nCellsSolve = dims->nCellsSolve; D.nEdgesSolve = dims->nEdgesSolve; D.nVerticesSolve = dims->nVerticesSolve;
+    D.nl = dims->nVertLevels; D.LDK = (dims->nVertLevels + 1 + 1) / 2 * 2;
+    D.maxEdges = dims->maxEdges; D.maxEdges2 = dims->maxEdges2; D.num_scalars = dims->num_scalars;
+    D.index_qv = dims->index_qv - 1; D.moist_start = dims->moist_start - 1; D.moist_end = dims->moist_end - 1;
+    D.cellPlane = (size_t)(dims->nCells + 1) * D.LDK; D.edgePlane = (size_t)(dims->nEdges + 1) * D.LDK;
+    h->cpb = std::max(1, 256 / D.LDK);
+#define F(name_, loc_, inner_, lev_, type_, tgt_) { FieldRec f; f.name = #name_; f.loc = LOC_##loc_; f.inner = IN_##inner_; \
+        f.levels = lev_; f.type = T_##type_; f.target = TG_##tgt_; f.d[0] = f.d[1] = nullptr; h->fields.push_back(f); }
+#include "../../include/mpasb_fields.def"
+#undef F
+    size_t max_bytes = 0;
+    for (size_t n = 0; n < h->fields.size(); n++) {
+        FieldRec& f = h->fields[n];
+        h->index[f.name] = (int)n;
+        f.dev_count = dev_count_of(h, f.loc, f.inner);
+        f.host_count = (long)(outer_of(h, f.loc) * inner_dense1(h, f.inner) * inner_dense2(h, f.inner));
+        const size_t esz = f.type == T_REAL ? sizeof(real) : sizeof(int);
+        for (int l = 0; l < f.levels; l++) {
+            if (cudaMalloc(&f.d[l], f.dev_count * esz) != cudaSuccess) { h->err = "cudaMalloc failed"; mpasb_destroy(h); return 7; }
+            cudaMemsetAsync(f.d[l], 0, f.dev_count * esz, h->stream);
+        }
+        max_bytes = std::max(max_bytes, (size_t)f.host_count * esz);
+        set_dev_ptr(h, f);
+    }
+    h->staging_bytes = max_bytes;
+    if (cudaMalloc(&h->staging, max_bytes) != cudaSuccess || cudaMalloc(&h->d_minmax, 4 * sizeof(real)) != cudaSuccess) {
+        mpasb_destroy(h); return 8;
+    }
+    cudaStreamSynchronize(h->stream);
+    *out = h;
+    return 0;
+}
+
+static void set_dev_ptr(H* h, const FieldRec& f) {
+    Dev& D = h->D;
+#define FIELD_REAL(name_) if (!strcmp(f.name, #name_)) { D.name_ = (real*)f.d[0]; D.name_##_2 = (real*)f.d[1]; return; }
+#define FIELD_INT(name_) if (!strcmp(f.name, #name_)) { D.name_ = (int*)f.d[0]; return; }
+#define F(name_, loc_, inner_, lev_, type_, tgt_) FIELD_##type_(name_)
+#include "../../include/mpasb_fields.def"
+#undef F
+#undef FIELD_REAL
+#undef FIELD_INT
+}
+
+extern "C" int mpasb_destroy(mpasb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    halo_destroy(h->halo);
+    for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(f.d[l]);
+    if (h->staging) cudaFree(h->staging);
+    if (h->d_minmax) cudaFree(h->d_minmax);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* mpasb_last_error(mpasb_handle h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" long mpasb_kernel_launch_count(mpasb_handle h) { return h->launches; }
+extern "C" int mpasb_synchronize(mpasb_handle h) { cudaSetDevice(h->device); CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
+
+static FieldRec* find_field(H* h, const char* name) {
+    auto it = h->index.find(name);
+    if (it == h->index.end()) { h->err = std::string("unknown field ") + name; return nullptr; }
+    return &h->fields[it->second];
+}
+extern "C" int mpasb_field_count(mpasb_handle h, const char* name, long* count) {
+    FieldRec* f = find_field(h, name); if (!f) return 1; *count = f->host_count; return 0;
+}
+
+static inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level, const mpasb_real* src, long count) {
+    cudaSetDevice(h->device);
+    FieldRec* f = find_field(h, name); if (!f) return 1;
+    if (f->type != T_REAL || time_level < 1 || time_level > f->levels || count != f->host_count) { h->err = std::string("bad set_field ") + name; return 2; }
+    real* dst = (real*)f->d[time_level - 1];
+    const int LDK = h->D.LDK;
+    const size_t o = outer_of(h, f->loc);
+    const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
+    if (!padded) { CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(real), cudaMemcpyHostToDevice, h->stream)); }
+    else {
+        real* st = (real*)h->staging;
+        CUDA_OK(cudaMemcpyAsync(st, src, count * sizeof(real), cudaMemcpyHostToDevice, h->stream));
+        const int n1 = inner_dense1(h, f->inner);
+        if (f->inner == IN_NL || f->inner == IN_NL1) k_pad<<<nblk(o * LDK), 256, 0, h->stream>>>(dst, st, o, n1, LDK);
+        else if (f->inner == IN_NL1_ME) k_pad<<<nblk(o * h->dims.maxEdges * LDK), 256, 0, h->stream>>>(dst, st, o * h->dims.maxEdges, n1, LDK);
+        else if (f->inner == IN_S_NL) k_pad_planes<<<nblk(f->dev_count), 256, 0, h->stream>>>(dst, st, o, h->dims.nVertLevels, h->dims.num_scalars, LDK);
+        else k_pad_midplanes<<<nblk(f->dev_count), 256, 0, h->stream>>>(dst, st, o, h->dims.nVertLevels, 2, LDK);
+        h->launches++;
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));      // the host buffer and the staging area may be reused on return
+    return 0;
+}
+
+extern "C" int mpasb_get_field(mpasb_handle h, const char* name, int time_level, mpasb_real* dstp, long count) {
+    cudaSetDevice(h->device);
+    FieldRec* f = find_field(h, name); if (!f) return 1;
+    if (f->type != T_REAL || time_level < 1 || time_level > f->levels || count != f->host_count) { h->err = std::string("bad get_field ") + name; return 2; }
+    const real* src = (const real*)f->d[time_level - 1];
+    const int LDK = h->D.LDK;
+    const size_t o = outer_of(h, f->loc);
+    const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
+    if (!padded) { CUDA_OK(cudaMemcpyAsync(dstp, src, count * sizeof(real), cudaMemcpyDeviceToHost, h->stream)); }
+    else {
+        real* st = (real*)h->staging;
+        const int n1 = inner_dense1(h, f->inner);
+        if (f->inner == IN_NL || f->inner == IN_NL1) k_unpad<<<nblk(count), 256, 0, h->stream>>>(st, src, o, n1, LDK);
+        else if (f->inner == IN_NL1_ME) k_unpad<<<nblk(count), 256, 0, h->stream>>>(st, src, o * h->dims.maxEdges, n1, LDK);
+        else if (f->inner == IN_S_NL) k_unpad_planes<<<nblk(count), 256, 0, h->stream>>>(st, src, o, h->dims.nVertLevels, h->dims.num_scalars, LDK);
+        else k_unpad_midplanes<<<nblk(count), 256, 0, h->stream>>>(st, src, o, h->dims.nVertLevels, 2, LDK);
+        h->launches++;
+        CUDA_OK(cudaMemcpyAsync(dstp, st, count * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* src, long count) {
+    cudaSetDevice(h->device);
+    FieldRec* f = find_field(h, name); if (!f) return 1;
+    if (f->type != T_INT || count != f->host_count) { h->err = std::string("bad set_field_int ") + name; return 2; }
+    int* st = (int*)h->staging;
+    CUDA_OK(cudaMemcpyAsync(st, src, count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_int_to_zero_based<<<nblk(count), 256, 0, h->stream>>>((int*)f->d[0], st, (size_t)count, f->target == TG_NONE ? 0 : 1);
+    h->launches++;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpasb_shift_time_levels(mpasb_handle h) {     // mpas_pool_shift_time_levels, shift_time_levs_array.inc:26-33
+    for (FieldRec& f : h->fields) if (f.levels == 2) { std::swap(f.d[0], f.d[1]); set_dev_ptr(h, f); }
+    h->halo.parity ^= 1;        // halo plans cache field pointers per time-level parity
+    return 0;
+}
+
+// ------------------------------------------------------------------ launch helpers
+struct Scope {      // per-routine CUDA-event timing when profiling is on (timer names follow mpas_timer_start, TI:1045...)
+    H* h; const char* name;
+    Scope(H* h_, const char* n) : h(h_), name(n) { if (h->profile) cudaEventRecord(h->ev0, h->stream); }
+    ~Scope() {
+        if (!h->profile) return;
+        cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        ProfRec& p = h->prof[name]; p.ms += ms; p.count++;
+    }
+};
+#define GRID(n) dim3((unsigned)(((n) + h->cpb - 1) / h->cpb)), dim3(h->D.LDK, h->cpb)
+#define LAUNCH(kern, n, smem, ...) do { kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+#define LAUNCH1D(kern, n, ...) do { kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+
+static const real rgas = RGAS, cp = CP_, rv = RV_;
+
+static void copy_cols(H* h, real* dst, const real* src, size_t ncols) {      // [0, ncols) columns, garbage column untouched
+    cudaMemcpyAsync(dst, src, ncols * h->D.LDK * sizeof(real), cudaMemcpyDeviceToDevice, h->stream);
+}
+
+// ------------------------------------------------------------------ routines
+static void rk_integration_setup(H* h) {       // TI:1930-2039
+    Scope sc(h, "atm_rk_integration_setup");
+    Dev& D = h->D; const size_t nC = D.nCells, nE = D.nEdges;
+    copy_cols(h, D.ru_save, D.ru, nE); copy_cols(h, D.u_2, D.u, nE);
+    copy_cols(h, D.rtheta_p_save, D.rtheta_p, nC); copy_cols(h, D.rho_p_save, D.rho_p, nC);
+    copy_cols(h, D.theta_m_2, D.theta_m, nC); copy_cols(h, D.rho_zz_2, D.rho_zz, nC);
+    copy_cols(h, D.rho_zz_old_split, D.rho_zz, nC);
+    copy_cols(h, D.rw_save, D.rw, nC); copy_cols(h, D.w_2, D.w, nC);
+    for (int s = 0; s < D.num_scalars; s++) copy_cols(h, D.scalars_2 + s * D.cellPlane, D.scalars + s * D.cellPlane, nC);
+    cudaMemsetAsync(D.theta_m_2 + nC * D.LDK, 0, D.LDK * sizeof(real), h->stream);          // TI:1987
+}
+static void compute_moist_coefficients(H* h) { // TI:2042-2146
+    Scope sc(h, "atm_compute_moist_coefficients");
+    LAUNCH(k_moist_cell, h->D.nCells, 0, h->D);
+    LAUNCH(k_moist_edge, h->D.nEdges, 0, h->D);
+}
+static void compute_vert_imp_coefs(H* h, real dts) {   // TI:2225-2366
+    Scope sc(h, "atm_compute_vert_imp_coefs");
+    const real dtseps = .5 * dts * (1. + h->cfg.config_epssm);
+    const real rcv = rgas / (cp - rgas);
+    const real c2 = cp * rcv;
+    const size_t smem = (size_t)9 * h->D.LDK * h->cpb * sizeof(real);
+    LAUNCH(k_vert_imp_coefs, h->D.nCellsSolve, smem, h->D, dtseps, c2, rcv);
+}
+static DynTendArgs dyn_tend_args(H* h, int rk_step, real dt) {
+    const mpasb_config& c = h->cfg;
+    DynTendArgs A; memset(&A, 0, sizeof(A));
+    A.rk_step = rk_step; A.smag = c.config_horiz_mixing == 0;
+    A.invDt = 1.0 / dt;
+    const real len = c.config_len_disp;
+    A.cs_len2 = (c.config_smagorinsky_coef * len) * (c.config_smagorinsky_coef * len);
+    A.kdiff_cap = (0.01 * (len * len)) * A.invDt;
+    A.fixed_visc2 = c.config_h_theta_eddy_visc2;
+    if (A.smag) { A.h_mom_eddy_visc4 = c.config_visc4_2dsmag * (len * len * len); A.h_theta_eddy_visc4 = A.h_mom_eddy_visc4; }
+    else { A.h_mom_eddy_visc4 = c.config_h_mom_eddy_visc4; A.h_theta_eddy_visc4 = c.config_h_theta_eddy_visc4; }
+    A.del4u_div_factor = c.config_del4u_div_factor;
+    A.v_mom_eddy_visc2 = c.config_v_mom_eddy_visc2; A.v_theta_eddy_visc2 = c.config_v_theta_eddy_visc2;
+    A.coef_3rd_order = c.config_coef_3rd_order; A.prandtl_inv = 1.0 / PRANDTL; A.mix_full = c.config_mix_full;
+    A.cam_coef = c.config_mpas_cam_coef; A.len_disp = len; A.n_cam_levels = c.config_number_cam_damping_levels;
+    A.rayleigh_damp_u = c.config_rayleigh_damp_u; A.n_rayleigh_levels = c.config_number_rayleigh_damp_u_levels;
+    if (A.rayleigh_damp_u)
+        A.rayleigh_coef_inverse = 1.0 / ((real)A.n_rayleigh_levels * (c.config_rayleigh_damp_u_timescale_days * 86400.0));
+    return A;
+}
+static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
+    Scope sc(h, "atm_compute_dyn_tend");
+    const Dev& D = h->D;
+    const DynTendArgs A = dyn_tend_args(h, rk_step, dt);
+    LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
+    LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
+    if (rk_step == 1) {
+        if (A.h_mom_eddy_visc4 > 0.0) {
+            LAUNCH(k_dt_delsq_vertex, D.nVertices, 0, D);
+            LAUNCH(k_dt_delsq_cell, D.nCells, 0, D);
+        }
+        LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
+        LAUNCH(k_dt_cell_e, D.nCells, 0, D, A);
+    }
+    LAUNCH(k_dt_cell_f, D.nCellsSolve, 0, D, A);
+}
+static void set_smlstep_pert_variables(H* h) {               // TI:2427-2508
+    Scope sc(h, "small_step_prep");
+    LAUNCH(k_smlstep_pert, h->D.nCellsSolve, 0, h->D);
+}
+static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:2646-2984
+    Scope sc(h, "atm_advance_acoustic_step");
+    const real epssm = h->cfg.config_epssm;
+    const real rcv = rgas / (cp - rgas);
+    const real c2 = cp * rcv;
+    const real resm = (1.0 - epssm) / (1.0 + epssm);
+    LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
+    const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
+    LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
+}
+static void divergence_damping_3d(H* h, real dts) {           // TI:2987-3075
+    Scope sc(h, "atm_divergence_damping_3d");
+    const real rdts = 1.0 / dts;
+    const real coef_divdamp = 2.0 * h->cfg.config_smdiv * h->cfg.config_len_disp * rdts;
+    LAUNCH(k_divergence_damping, h->D.nEdges, 0, h->D, coef_divdamp);
+}
+static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {    // TI:3189-3431
+    Scope sc(h, "atm_recover_large_step_variables");
+    const real rcv = rgas / (cp - rgas);
+    const real p0 = 1.0e+05;
+    const real invNs = 1 / (real)ns;
+    LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
+    LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
+    LAUNCH(k_recover_cell2, h->D.nCells, 0, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
+}
+static void compute_solve_diagnostics(H* h, real dt, int time_lev, int rk_step) {  // TI:6337-6773
+    Scope sc(h, "atm_compute_solve_diagnostics");
+    const Dev& D = h->D;
+    const real* u = time_lev == 2 ? D.u_2 : D.u;
+    const real* hh = time_lev == 2 ? D.rho_zz_2 : D.rho_zz;
+    const int apvm = h->cfg.config_apvm_upwinding > 0.0;
+    const int reconstruct_v = (rk_step == 0 || rk_step == 3);
+    LAUNCH(k_diag_vertex, D.nVertices, 0, D, u);
+    LAUNCH(k_diag_cell, D.nCells, 0, D, u, apvm);
+    LAUNCH(k_diag_edge, D.nEdges, 0, D, u, hh, reconstruct_v, apvm, h->cfg.config_apvm_upwinding * dt);
+}
+static void rk_dynamics_substep_finish(H* h, int dynamics_substep, int dynamics_split) {   // TI:7013-7191
+    Scope sc(h, "atm_rk_dynamics_substep_finish");
+    Dev& D = h->D; const size_t nC = D.nCells, nE = D.nEdges, L = D.LDK;
+    cudaMemsetAsync(D.theta_m + nC * L, 0, L * sizeof(real), h->stream);                    // TI:7082
+    const real inv_dynamics_split = 1.0 / (real)dynamics_split;
+    if (dynamics_substep < dynamics_split) {
+        copy_cols(h, D.ru_save, D.ru, nE); copy_cols(h, D.u, D.u_2, nE);
+        copy_cols(h, D.rtheta_p_save, D.rtheta_p, nC); copy_cols(h, D.rho_p_save, D.rho_p, nC);
+        copy_cols(h, D.theta_m, D.theta_m_2, nC); copy_cols(h, D.rho_zz, D.rho_zz_2, nC);
+        copy_cols(h, D.rw_save, D.rw, nC); copy_cols(h, D.w, D.w_2, nC);
+    }
+    if (dynamics_substep == 1) {
+        copy_cols(h, D.ruAvg_split, D.ruAvg, nE); copy_cols(h, D.wwAvg_split, D.wwAvg, nC);
+    } else {
+        LAUNCH1D(k_add_into, nE * L, D.ruAvg_split, D.ruAvg, nE * L);
+        LAUNCH1D(k_add_into, nC * L, D.wwAvg_split, D.wwAvg, nC * L);
+    }
+    if (dynamics_substep == dynamics_split) {
+        LAUNCH1D(k_scale_from, nE * L, D.ruAvg, D.ruAvg_split, inv_dynamics_split, nE * L);
+        LAUNCH1D(k_scale_from, nC * L, D.wwAvg, D.wwAvg_split, inv_dynamics_split, nC * L);
+        copy_cols(h, D.rho_zz, D.rho_zz_old_split, nC);
+    }
+}
+static void advance_scalars(H* h, real dt, int rk_step) {     // TI:3575-3855
+    Scope sc(h, "atm_advance_scalars");
+    const mpasb_config& c = h->cfg;
+    real weight_time_new = 1.;
+    if (c.config_split_dynamics_transport) {
+        if ((rk_step == 1) && c.config_time_integration_order == 3) weight_time_new = 1. / 3;
+        if ((rk_step == 1) && c.config_time_integration_order == 2) weight_time_new = 1. / 2;
+        if (rk_step == 2) weight_time_new = 1. / 2;
+        if (rk_step == 3) weight_time_new = 1.;
+    }
+    const real weight_time_old = 1. - weight_time_new;
+    LAUNCH(k_scalars_edge, h->D.nEdges, 0, h->D);
+    LAUNCH(k_scalars_cell, h->D.nCellsSolve, 0, h->D, dt, weight_time_old, weight_time_new, c.config_coef_3rd_order);
+}
+static int exchange(H* h, const char* group);
+static int advance_scalars_mono(H* h, real dt) {              // TI:4012-4734
+    Scope sc(h, "atm_advance_scalars_mono");
+    const Dev& D = h->D;
+    const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
+    LAUNCH(k_mono_pre, D.nCellsSolve, 0, D, dt);
+    if (exchange(h, "dynamics:scalars_old")) return 1;
+    if (adv_density) LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt);
+    const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
+    for (int s = 0; s < D.num_scalars; s++) {
+        LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+        LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+        LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+        if (exchange(h, "dynamics:scale")) return 1;
+        LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+        LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+    }
+    return 0;
+}
+static void init_coupled_diagnostics(H* h) {                  // TI:6776-7010
+    const real rcv = rgas / (cp - rgas);
+    const real p0 = 1.e5;
+    LAUNCH(k_initcd_cell1, h->D.nCells, 0, h->D, rv / rgas, rcv, rgas / p0);
+    LAUNCH(k_initcd_edge, h->D.nEdges, 0, h->D);
+    LAUNCH(k_initcd_cell2, h->D.nCells, 0, h->D);
+}
+
+// ------------------------------------------------------------------ halo exchange (mpas_halo.F:498-846)
+#include "halo_host.inl"
+
+static int exchange(H* h, const char* group) {
+    if (!h->halo.active) return 0;                // single block: exchange lists are empty (mpas_dmpar.F:2074-2153)
+    Scope sc(h, "exchange_halo_group");
+    return halo_exchange(h, group);
+}
+
+// ------------------------------------------------------------------ atm_srk3  TI:803-1725
+static int srk3(H* h, real dt) {
+    const mpasb_config& c = h->cfg;
+    Dev& D = h->D;
+    cudaSetDevice(h->device);
+    // TI:967-991, 1091-1093: qtot garbage column and the physics tendencies are zero (no physics)
+    cudaMemsetAsync(D.tend_ru_physics, 0, D.edgePlane * sizeof(real), h->stream);
+    cudaMemsetAsync(D.tend_rtheta_physics, 0, D.cellPlane * sizeof(real), h->stream);
+    cudaMemsetAsync(D.tend_rho_physics, 0, D.cellPlane * sizeof(real), h->stream);
+    int dynamics_split = c.config_dynamics_split_steps;
+    real dt_dynamics;
+    if (c.config_split_dynamics_transport) dt_dynamics = dt / (real)dynamics_split;
+    else { dynamics_split = 1; dt_dynamics = dt; }
+    const int number_of_sub_steps = c.config_number_of_sub_steps;
+    real rk_timestep[4], rk_sub_timestep[4];
+    int number_sub_steps[4];
+    if (c.config_time_integration_order == 3) {
+        rk_timestep[1] = dt_dynamics / 3.; rk_timestep[2] = dt_dynamics / 2.; rk_timestep[3] = dt_dynamics;
+        rk_sub_timestep[1] = dt_dynamics / 3.; rk_sub_timestep[2] = dt_dynamics / (real)number_of_sub_steps; rk_sub_timestep[3] = dt_dynamics / (real)number_of_sub_steps;
+        number_sub_steps[1] = 1; number_sub_steps[2] = std::max(1, number_of_sub_steps / 2); number_sub_steps[3] = number_of_sub_steps;
+    } else if (c.config_time_integration_order == 2) {
+        rk_timestep[1] = dt_dynamics / 2.; rk_timestep[2] = dt_dynamics / 2.; rk_timestep[3] = dt_dynamics;
+        rk_sub_timestep[1] = rk_sub_timestep[2] = rk_sub_timestep[3] = dt_dynamics / (real)number_of_sub_steps;
+        number_sub_steps[1] = std::max(1, number_of_sub_steps / 2); number_sub_steps[2] = std::max(1, number_of_sub_steps / 2); number_sub_steps[3] = number_of_sub_steps;
+    } else { h->err = "config_time_integration_order must be 2 or 3"; return 1; }
+    if (c.config_scalar_advection && !c.config_split_dynamics_transport) { h->err = "unsplit scalar transport is not implemented"; return 1; }
+
+    if (exchange(h, "dynamics:theta_m,scalars,pressure_p,rtheta_p")) return 1;
+    rk_integration_setup(h);
+    compute_moist_coefficients(h);
+    for (int dynamics_substep = 1; dynamics_substep <= dynamics_split; dynamics_substep++) {
+        compute_vert_imp_coefs(h, rk_sub_timestep[1]);
+        if (exchange(h, "dynamics:exner")) return 1;
+        for (int rk_step = 1; rk_step <= 3; rk_step++) {
+            if (c.config_time_integration_order == 3 && rk_step == 2) compute_vert_imp_coefs(h, rk_sub_timestep[rk_step]);
+            compute_dyn_tend(h, rk_step, dt);
+            if (exchange(h, "dynamics:tend_u")) return 1;
+            set_smlstep_pert_variables(h);
+            for (int small_step = 1; small_step <= number_sub_steps[rk_step]; small_step++) {
+                if (exchange(h, "dynamics:rho_pp")) return 1;
+                advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step);
+                if (exchange(h, "dynamics:rtheta_pp")) return 1;
+                divergence_damping_3d(h, rk_sub_timestep[rk_step]);
+            }
+            if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
+            recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step);
+            if (exchange(h, "dynamics:u_3")) return 1;
+            compute_solve_diagnostics(h, dt, 2, rk_step);
+            if (exchange(h, "dynamics:w,pv_edge,rho_edge")) return 1;
+        }
+        if (dynamics_substep < dynamics_split)
+            if (exchange(h, "dynamics:theta_m,pressure_p,rtheta_p")) return 1;
+        rk_dynamics_substep_finish(h, dynamics_substep, dynamics_split);
+    }
+    if (c.config_scalar_advection && c.config_split_dynamics_transport) {
+        rk_timestep[1] = dt / 3.; rk_timestep[2] = dt / 2.; rk_timestep[3] = dt;
+        if (c.config_time_integration_order == 2) rk_timestep[1] = dt / 2.;
+        for (int rk_step = 1; rk_step <= 3; rk_step++) {
+            if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) advance_scalars(h, rk_timestep[rk_step], rk_step);
+            else if (advance_scalars_mono(h, rk_timestep[rk_step])) return 1;
+            if (rk_step < 3) if (exchange(h, "dynamics:scalars")) return 1;
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+extern "C" int mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep) { (void)itimestep; return srk3(h, dt); }
+
+extern "C" int mpasb_minmax(mpasb_handle h, mpasb_real out[4]) {
+    cudaSetDevice(h->device);
+    const Dev& D = h->D;
+    CUDA_OK(cudaMemsetAsync(h->d_minmax, 0, 4 * sizeof(real), h->stream));
+    k_minmax<<<296, 256, 0, h->stream>>>(D.w_2, D.nCellsSolve, D.nl, D.LDK, h->d_minmax);
+    k_minmax<<<296, 256, 0, h->stream>>>(D.u_2, D.nEdgesSolve, D.nl, D.LDK, h->d_minmax + 2);
+    h->launches += 2;
+    CUDA_OK(cudaMemcpyAsync(out, h->d_minmax, 4 * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpasb_set_profile(mpasb_handle h, int on) { h->profile = on != 0; if (on) h->prof.clear(); return 0; }
+extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
+    std::string s;
+    for (auto& kv : h->prof) { char line[256]; snprintf(line, sizeof line, "%s %.6f %ld\n", kv.first.c_str(), kv.second.ms, kv.second.count); s += line; }
+    strncpy(buf, s.c_str(), buflen - 1); buf[buflen - 1] = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------ init-time and per-routine entry points
+#define ENTRY(body) { cudaSetDevice(h->device); body; CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
+extern "C" int mpasb_init_coupled_diagnostics(mpasb_handle h) ENTRY(init_coupled_diagnostics(h))
+extern "C" int mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt) ENTRY(compute_solve_diagnostics(h, dt, 1, 0))
+extern "C" int mpasb_k_rk_integration_setup(mpasb_handle h) ENTRY(rk_integration_setup(h))
+extern "C" int mpasb_k_compute_moist_coefficients(mpasb_handle h) ENTRY(compute_moist_coefficients(h))
+extern "C" int mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts) ENTRY(compute_vert_imp_coefs(h, dts))
+extern "C" int mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt) ENTRY(compute_dyn_tend(h, rk_step, dt))
+extern "C" int mpasb_k_set_smlstep_pert_variables(mpasb_handle h) ENTRY(set_smlstep_pert_variables(h))
+extern "C" int mpasb_k_advance_acoustic_step(mpasb_handle h, mpasb_real dts, int small_step) ENTRY(advance_acoustic_step(h, dts, small_step))
+extern "C" int mpasb_k_divergence_damping_3d(mpasb_handle h, mpasb_real dts) ENTRY(divergence_damping_3d(h, dts))
+extern "C" int mpasb_k_recover_large_step_variables(mpasb_handle h, mpasb_real dt, int ns, int rk_step) ENTRY(recover_large_step_variables(h, dt, ns, rk_step))
+extern "C" int mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(compute_solve_diagnostics(h, dt, 2, rk_step))
+extern "C" int mpasb_k_rk_dynamics_substep_finish(mpasb_handle h, int s, int n) ENTRY(rk_dynamics_substep_finish(h, s, n))
+extern "C" int mpasb_k_advance_scalars(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(advance_scalars(h, dt, rk_step))
+extern "C" int mpasb_k_advance_scalars_mono(mpasb_handle h, mpasb_real dt) ENTRY(if (advance_scalars_mono(h, dt)) return 1)

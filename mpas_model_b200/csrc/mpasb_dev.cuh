@@ -1,0 +1,50 @@
+// mpasb_dev.cuh -- device-side view of one mesh block and small device helpers.
+//
+// Layout in HBM: every level-dimensioned field is [n+1][LDK] with the
+// vertical index fastest ("level-contiguous"), LDK = nVertLevels+1 rounded up to an
+// even count, shared by nVertLevels and nVertLevels+1 arrays so that one (k, column)
+// thread index addresses all of them.  Columns are 16-byte aligned.  The trailing
+// column n is the reference's garbage slot n+1 (mpas_block_creator.F:1050-1121).
+// Connectivity is 0-based on the device.
+#pragma once
+#include <cuda_runtime.h>
+
+typedef double real;
+
+enum { LOC_CELL = 0, LOC_EDGE = 1, LOC_VERTEX = 2, LOC_LEVS = 3 };
+enum { IN_ONE, IN_NL, IN_NL1, IN_ME, IN_ME2, IN_VD, IN_TWO, IN_F15, IN_NL1_ME, IN_S_NL, IN_NL_TWO };
+
+#define FIELD_REAL(name) real* name; real* name##_2;
+#define FIELD_INT(name) int* name;
+#define F(name, loc, inner, lev, type, tgt) FIELD_##type(name)
+
+struct Dev {
+#include "../../include/mpasb_fields.def"
+    // dimensions (0-based counts; garbage column index == n)
+    int nCells, nEdges, nVertices, nCellsSolve, nEdgesSolve, nVerticesSolve;
+    int nl;            // nVertLevels
+    int LDK;           // padded level stride
+    int maxEdges, maxEdges2, num_scalars;
+    int index_qv, moist_start, moist_end;      // 0-based
+    size_t cellPlane, edgePlane;               // (n+1)*LDK, stride between scalar planes
+};
+#undef F
+#undef FIELD_REAL
+#undef FIELD_INT
+
+// src/framework/mpas_constants.F:43-56
+#define GRAVITY 9.80616
+#define RGAS 287.0
+#define CP_ (7.0 * 287.0 / 2.0)
+#define RV_ 461.6
+#define PRANDTL 1.0
+
+__device__ __forceinline__ real sign1(real x) { return copysign(1.0, x); }      // Fortran sign(1.0, x)
+
+// statement functions, mpas_atm_time_integration.F:5156-5161
+__device__ __forceinline__ real flux4(real q_im2, real q_im1, real q_i, real q_ip1, real ua) {
+    return ua * (7. * (q_i + q_im1) - (q_ip1 + q_im2)) / 12.0;
+}
+__device__ __forceinline__ real flux3(real q_im2, real q_im1, real q_i, real q_ip1, real ua, real coef3) {
+    return flux4(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * fabs(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;
+}
