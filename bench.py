@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- JW baroclinic-wave dycore step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+
+A "step" is one atm_srk3 call (mpas_atm_time_integration.F:803) over the whole mesh.
+N = 1 workload: BASELINE.json configs[1], JW wave on x1.40962 (120 km), 55 levels, fp64,
+dt = 720 s.  N > 1: the mesh is partitioned with one block per GPU (weak scaling is not
+natural for a fixed global mesh family, so N = 2/4 use x1.163842 and N = 8 uses x1.655362 as
+BASELINE.json names them; "scaling" is reported as "strong-per-config").
+
+Prints ONE JSON line (rank 0).  `value` is device-resident whole-job steps/s; `e2e` is the
+same step driven through the C ABI with HOST buffers (restart-state upload, diagnostics
+recompute, step, state download inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {1: (40962, 55), 2: (163842, 55), 4: (163842, 55), 8: (655362, 55)}
+# restart-stream state that a host keeps between steps (Registry.xml stream "restart")
+E2E_FIELDS = (("u", 1), ("w", 1), ("rho_zz", 1), ("theta_m", 1), ("scalars", 1), ("ru", 1), ("rw", 1),
+              ("rtheta_p", 1), ("rho_p", 1), ("exner", 1), ("pressure_p", 1))
+E2E_OUT = (("u", 2), ("w", 2), ("rho_zz", 2), ("theta_m", 2), ("scalars", 2), ("ru", 1), ("rw", 1),
+           ("rtheta_p", 1), ("rho_p", 1), ("exner", 1), ("pressure_p", 1))
+
+
+def model_bytes_per_step(n_cells, n_levels, n_scalars, real_bytes=8):
+    """B_step = (2197 + 107 S) * nVertLevels * nCells * sizeof(real)."""
+    return (2197 + 107 * n_scalars) * n_levels * n_cells * real_bytes
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu=0):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic bytes per launch of the kernels worth a roofline line, in units of
+# C = nVertLevels * nCells * 8 B (SURVEY.md §8a per-routine model; DESIGN.md §4 per kernel)
+KERNEL_MODEL_C = {
+    "k:k_acoustic_cell": 29.0,       # 1 E + 21 C read, 5 C written (non-first small step)
+    "k:k_dt_cell_f": 22.0,           # w, theta_m (+save), ru/ru_save (E), rw(+save), rho_zz, tendencies
+    "k:k_dt_edge_b": 24.0,
+    "k:k_recover_cell2": 19.0,       # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
+}
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path.  The Fortran build is
+    impossible in this image (no Fortran compiler/MPI/NetCDF), so this times the C++ restatement
+    (oracle/, OpenMP over the same cell/edge ranges) on the box's host cores."""
+    if rank != 0:
+        return
+    from mpas_model_b200.case import make_case
+    from oracle.oracle import OracleDycore
+    n_cells, n_lev = WORKLOADS[1]
+    d, cfg = make_case(n_cells, n_lev)
+    dt = cfg["config_dt"]
+    o = OracleDycore(d, cfg)
+    o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+    t0 = time.time(); o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); t1 = time.time() - t0
+    warm = max(0, min(args.warmup - 1, int(30.0 / max(t1, 1e-3))))
+    for _ in range(warm):
+        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+    steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
+    t0 = time.time()
+    for _ in range(steps):
+        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+    el = time.time() - t0
+    v = steps / el
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+    print(json.dumps({
+        "impl": "reference", "metric": "JW wave dycore steps/sec", "value": v, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * el / steps,
+        "higher_is_better": True, "scaling": "strong-per-config", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
+        "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s, restated CPU dycore (C++/OpenMP), not the Fortran build"},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full atm_srk3 steps of the same workload"},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sdpd": dt * v, "cell_columns_per_s": n_cells * v,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cells", type=int, default=0, help="override the mesh (10*4^n+2 cells)")
+    ap.add_argument("--levels", type=int, default=0)
+    ap.add_argument("--scalars", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    from mpas_model_b200.case import make_case
+    from mpas_model_b200.dycore import Dycore
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dycore step has no CPU path")
+    n_cells, n_lev = WORKLOADS.get(args.gpus, WORKLOADS[1])
+    if args.cells:
+        n_cells = args.cells
+    if args.levels:
+        n_lev = args.levels
+    if world > 1:
+        from mpas_model_b200 import multigpu
+        return multigpu.bench_main(args, rank, world, local_rank, n_cells, n_lev)
+
+    torch.cuda.set_device(0)
+    d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
+    dt = cfg["config_dt"]
+    g = Dycore(d, cfg, device=0)
+    g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
+
+    # ---------------- device-resident throughput
+    for _ in range(args.warmup):
+        g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
+    g.synchronize(); torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    l0 = g.kernel_launch_count()
+    g.timer_start()
+    for _ in range(args.steps):
+        g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
+    ms = g.timer_stop()
+    g.synchronize(); torch.cuda.synchronize()
+    launches = g.kernel_launch_count() - l0
+    minmax = g.summarize_timestep()
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---------------- end to end through the C ABI with pinned host buffers
+    host = {}
+    for name, lev in set(E2E_FIELDS) | set(E2E_OUT):
+        t = torch.empty(tuple(g.shape(name)), dtype=torch.float64).pin_memory()
+        host[(name, lev)] = t.numpy()
+    for (name, lev) in E2E_FIELDS:
+        g._get_real(name, lev, host[(name, lev)])
+    h2d = sum(host[k].nbytes for k in E2E_FIELDS)
+    d2h = sum(host[k].nbytes for k in E2E_OUT) + 32
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        for (name, lev) in E2E_FIELDS:                 # host pools -> device (pinned)
+            g._set_real(name, lev, host[(name, lev)])
+        g.atm_init_solve_diagnostics(dt)                # what a restart read is followed by (mpas_atm_core.F:524)
+        g.atm_srk3(dt)
+        for (name, lev) in E2E_OUT:                     # device -> host pools
+            g._get_real(name, lev, host[(name, lev)])
+        mm = g.summarize_timestep()                     # the step's logged result (TI:8304,8319)
+        for name in ("u", "w", "rho_zz", "theta_m", "scalars"):     # mpas_pool_shift_time_levels on the host: swap pointers
+            host[(name, 1)], host[(name, 2)] = host[(name, 2)], host[(name, 1)]
+        return mm
+
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    g.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()
+
+    # ---------------- per-kernel timing (CUDA events on the launching stream) for the roofline object
+    g.set_profile(True)
+    nprof = 3
+    for _ in range(nprof):
+        g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
+    rows = g.get_profile(); g.set_profile(False)
+    krows = {n: (m, c) for n, m, c in rows if n.startswith("k:")}
+    ksum = sum(m for m, _ in krows.values())
+    dom = max(krows.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms, dom_cnt) = dom
+    peak, peak_src = measured_peak_gbs()
+    C = n_lev * n_cells * 8
+    model_c = KERNEL_MODEL_C.get(dom_name)
+    dom_us = 1e3 * dom_ms / dom_cnt
+    achieved = (model_c * C / (dom_us * 1e-6) / 1e9) if model_c else None
+    roofline = {"bound": "hbm", "kernel": dom_name[2:], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum, "algorithmic_bytes_per_launch": (model_c * C) if model_c else None,
+                "peak_source": peak_src}
+    B_step = model_bytes_per_step(n_cells, n_lev, args.scalars)
+    step_gbs = B_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- CPU baseline: the oracle on the host cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.oracle import OracleDycore
+        o = OracleDycore(d, cfg)
+        o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+        t0 = time.time(); n = 0
+        while n < 3 or (time.time() - t0 < 10.0 and n < 20):
+            o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); n += 1
+        el = time.time() - t0
+        cpu = {"value": n / el, "unit": "steps/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())),
+               "kind": "port", "sample": f"{n} full atm_srk3 steps of the same workload (C++/OpenMP restatement, not the Fortran build)"}
+
+    line = {
+        "metric": "JW wave dycore steps/sec", "value": value, "unit": "steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong-per-config", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
+        "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s S={args.scalars}",
+                   "l2": "no flush: ~3.5 GB of fields are streamed per step, >> 126 MB L2",
+                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"},
+        "e2e": {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline,
+        "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs, "frac_of_measured_peak": step_gbs / peak,
+                          "frac_of_nominal_8TBs": step_gbs / 8000.0},
+        "cpu_baseline": cpu,
+        "sdpd": dt * value, "cell_columns_per_s": n_cells * value,
+        "minmax_w_u": list(minmax),
+        "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:12]},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

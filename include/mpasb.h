@@ -118,7 +118,9 @@ int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HAL
 
 /* Instrumentation */
 long mpasb_kernel_launch_count(mpasb_handle h);      /* kernels launched by this handle so far */
-int  mpasb_set_profile(mpasb_handle h, int on);      /* per-routine CUDA-event timing */
+int  mpasb_timer_start(mpasb_handle h);              /* CUDA event on the compute stream */
+int  mpasb_timer_stop(mpasb_handle h, double* ms);   /* second event + elapsed time between the two */
+int  mpasb_set_profile(mpasb_handle h, int on);      /* per-routine and per-kernel CUDA-event timing */
 int  mpasb_get_profile(mpasb_handle h, char* buf, long buflen);  /* "name ms count\n" lines */
 
 #ifdef __cplusplus

@@ -46,7 +46,7 @@ struct mpasb_handle_s {
     int cpb = 4;
     bool profile = false;
     std::map<std::string, ProfRec> prof;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     HaloState halo;
 };
 typedef mpasb_handle_s H;
@@ -94,7 +94,8 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->dims = *dims; h->cfg = *cfg; h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return 5; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
-    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->kev0); cudaEventCreate(&h->kev1);
+    cudaEventCreate(&h->tev0); cudaEventCreate(&h->tev1);
     memset(&h->D, 0, sizeof(Dev));
     Dev& D = h->D;
     D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
@@ -152,6 +153,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->d_minmax) cudaFree(h->d_minmax);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : {h->kev0, h->kev1, h->tev0, h->tev1}) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -248,8 +250,20 @@ struct Scope {      // per-routine CUDA-event timing when profiling is on (timer
     }
 };
 #define GRID(n) dim3((unsigned)(((n) + h->cpb - 1) / h->cpb)), dim3(h->D.LDK, h->cpb)
-#define LAUNCH(kern, n, smem, ...) do { kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
-#define LAUNCH1D(kern, n, ...) do { kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+// In profile mode every launch is bracketed by CUDA events on the launching stream and
+// accounted under the kernel's name ("k:<kernel>"); otherwise launches are fully asynchronous.
+struct KScope {
+    H* h; const char* name;
+    KScope(H* h_, const char* n) : h(h_), name(n) { if (h->profile) cudaEventRecord(h->kev0, h->stream); }
+    ~KScope() {
+        if (!h->profile) return;
+        cudaEventRecord(h->kev1, h->stream); cudaEventSynchronize(h->kev1);
+        float ms = 0; cudaEventElapsedTime(&ms, h->kev0, h->kev1);
+        ProfRec& p = h->prof[name]; p.ms += ms; p.count++;
+    }
+};
+#define LAUNCH(kern, n, smem, ...) do { KScope ks_(h, "k:" #kern); kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+#define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
 
@@ -513,6 +527,13 @@ extern "C" int mpasb_minmax(mpasb_handle h, mpasb_real out[4]) {
     return 0;
 }
 
+// CUDA-event timer on the stream the kernels are launched on (bench.py's timed region)
+extern "C" int mpasb_timer_start(mpasb_handle h) { cudaSetDevice(h->device); CUDA_OK(cudaEventRecord(h->tev0, h->stream)); return 0; }
+extern "C" int mpasb_timer_stop(mpasb_handle h, double* ms) {
+    cudaSetDevice(h->device);
+    CUDA_OK(cudaEventRecord(h->tev1, h->stream)); CUDA_OK(cudaEventSynchronize(h->tev1));
+    float f = 0; CUDA_OK(cudaEventElapsedTime(&f, h->tev0, h->tev1)); *ms = f; return 0;
+}
 extern "C" int mpasb_set_profile(mpasb_handle h, int on) { h->profile = on != 0; if (on) h->prof.clear(); return 0; }
 extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
     std::string s;

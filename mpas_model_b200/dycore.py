@@ -201,6 +201,14 @@ class Dycore(Backend):
     def exchange_halo_group(self, name):
         self._check(self.lib.mpasb_exchange_halo_group(self._h, name.encode()), f"exchange {name}")
 
+    def timer_start(self):
+        self._check(self.lib.mpasb_timer_start(self._h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.mpasb_timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return ms.value
+
     def kernel_launch_count(self):
         return int(self.lib.mpasb_kernel_launch_count(self._h))
 
