@@ -115,6 +115,19 @@ class Backend:
             if fd.levels == 2 and (name + "_2") in d:
                 self.set_array(name, d[name + "_2"], 2)
 
+    @staticmethod
+    def _flatten_halo_lists(lists):
+        """decomp.exchange_lists()[rank][kind] -> the flat 1-based arrays of mpasb_set_halo_lists."""
+        nbrs = np.asarray(lists["neighbors"], dtype=np.int32)
+        nl = lists["n_layers"]
+        n_send = np.array([[len(lists["send"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
+        n_recv = np.array([[len(lists["recv"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
+
+        def cat(key):
+            parts = [np.asarray(a, dtype=np.int32) for per in lists[key] for a in per] + [np.zeros(0, np.int32)]
+            return np.ascontiguousarray(np.concatenate(parts) + 1, dtype=np.int32)
+        return nbrs, nl, np.ascontiguousarray(n_send), cat("send"), np.ascontiguousarray(n_recv), cat("recv")
+
     def state(self, time_level=1, names=("u", "w", "rho_zz", "theta_m", "scalars")):
         return {n: self.get_array(n, time_level) for n in names}
 
@@ -200,6 +213,23 @@ class Dycore(Backend):
 
     def exchange_halo_group(self, name):
         self._check(self.lib.mpasb_exchange_halo_group(self._h, name.encode()), f"exchange {name}")
+
+    def set_halo_lists(self, kind, lists):
+        """kind: 0 cells, 1 edges, 2 vertices; lists: decomp.exchange_lists()[rank][kind name]."""
+        nbrs, nl, n_send, ss, n_recv, rr = self._flatten_halo_lists(lists)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.mpasb_set_halo_lists(self._h, C.c_int(kind), C.c_int(len(nbrs)), p(nbrs), C.c_int(nl),
+                                                  p(n_send), p(ss), p(n_recv), p(rr)), "set_halo_lists")
+
+    def comm_init(self, rank, world_size, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.lib.mpasb_comm_init(self._h, C.c_int(rank), C.c_int(world_size), buf), "comm_init")
+
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.mpasb_get_nccl_unique_id(buf) != 0:
+            raise RuntimeError("mpasb_get_nccl_unique_id failed (libnccl.so.2 not found?)")
+        return buf.raw
 
     def timer_start(self):
         self._check(self.lib.mpasb_timer_start(self._h), "timer_start")

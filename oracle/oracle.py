@@ -70,16 +70,10 @@ class OracleDycore(Backend):
             pass
 
     def set_halo_lists(self, kind, lists):
-        """lists: {"neighbors": [rank..], "send": [[arr per layer] per nbr], "recv": ...}, 0-based local indices."""
-        nbrs = np.asarray(lists["neighbors"], dtype=np.int32)
-        nl = lists["n_layers"]
-        n_send = np.array([[len(lists["send"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
-        n_recv = np.array([[len(lists["recv"][i][l]) for l in range(nl)] for i in range(len(nbrs))], dtype=np.int32).reshape(-1)
-        cat = lambda key: (np.concatenate([np.asarray(a, dtype=np.int32) for per in lists[key] for a in per] + [np.zeros(0, np.int32)]) + 1).astype(np.int32)
-        ss, rr = np.ascontiguousarray(cat("send")), np.ascontiguousarray(cat("recv"))
-        self.lib.oracle_set_halo_lists(self._h, C.c_int(kind), C.c_int(len(nbrs)), nbrs.ctypes.data_as(C.c_void_p), C.c_int(nl),
-                                       n_send.ctypes.data_as(C.c_void_p), ss.ctypes.data_as(C.c_void_p),
-                                       n_recv.ctypes.data_as(C.c_void_p), rr.ctypes.data_as(C.c_void_p))
+        nbrs, nl, n_send, ss, n_recv, rr = self._flatten_halo_lists(lists)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.lib.oracle_set_halo_lists(self._h, C.c_int(kind), C.c_int(len(nbrs)), p(nbrs), C.c_int(nl),
+                                       p(n_send), p(ss), p(n_recv), p(rr))
 
     # reference entry points
     def atm_init_coupled_diagnostics(self): self.lib.oracle_init_coupled_diagnostics(self._h)
