@@ -8,7 +8,8 @@ A "step" is one atm_srk3 call (mpas_atm_time_integration.F:803) over the whole m
 N = 1 workload: BASELINE.json configs[1], JW wave on x1.40962 (120 km), 55 levels, fp64,
 dt = 720 s.  N > 1: the mesh is partitioned with one block per GPU (weak scaling is not
 natural for a fixed global mesh family, so N = 2/4 use x1.163842 and N = 8 uses x1.655362 as
-BASELINE.json names them; "scaling" is reported as "strong-per-config").
+BASELINE.json names them: per-GPU work is 40962 / 81921 / 40961 / 81920 columns, i.e. weak scaling
+within a factor of two; cell_columns_per_s is the figure comparable across N).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident whole-job steps/s; `e2e` is the
 same step driven through the C ABI with HOST buffers (restart-state upload, diagnostics
@@ -87,43 +88,76 @@ KERNEL_MODEL_C = {
     "k:k_dt_edge_b": 24.0,
     "k:k_recover_cell2": 19.0,       # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/), x1.40962 x 55 levels; None = not captured for the current kernel version
+KERNEL_TRAFFIC = {}
 
 
-def reference_arm(args, rank):
+def workload_for(args):
+    n_cells, n_lev = WORKLOADS.get(args.gpus, WORKLOADS[1])
+    return (args.cells or n_cells), (args.levels or n_lev)
+
+
+def line_common(args, n_cells, n_lev, dt, world):
+    return {
+        "metric": "JW wave dycore steps/sec", "unit": "steps/s", "n_gpus": world, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
+        "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s S={args.scalars}",
+                   "cells_per_gpu": n_cells // world,
+                   "decomposition": "single block" if world == 1 else f"{world} blocks (recursive coordinate bisection), one per GPU, reference halo lists",
+                   "scaling_note": "BASELINE.json names one mesh per GPU count (x1.40962 @1, x1.163842 @2/4, x1.655362 @8); "
+                                   "compare cell_columns_per_s across N, steps/s only within one mesh",
+                   "l2": "no flush: every step streams the block's fields (>= 3.5 GB at 40962 cells x 55 levels), >> 126 MB L2",
+                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"},
+    }
+
+
+def reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The Fortran build is
     impossible in this image (no Fortran compiler/MPI/NetCDF), so this times the C++ restatement
-    (oracle/, OpenMP over the same cell/edge ranges) on the box's host cores."""
+    (oracle/, OpenMP over the same cell/edge ranges) on the box's host cores.  For N > 1 workloads
+    the sample is ONE block of the N-block decomposition (1/N of the mesh plus its halo); the
+    whole-mesh rate on the same cores is the block rate / N."""
     if rank != 0:
         return
-    from mpas_model_b200.case import make_case
     from oracle.oracle import OracleDycore
-    n_cells, n_lev = WORKLOADS[1]
-    d, cfg = make_case(n_cells, n_lev)
+    n_cells, n_lev = workload_for(args)
+    if args.gpus > 1:
+        from mpas_model_b200 import multigpu as mg
+        rec = mg.load_block(mg.prepare_blocks(n_cells, n_lev, args.scalars, args.gpus), 0)
+        d, cfg = rec["block"], rec["cfg"]
+        frac = 1.0 / args.gpus
+        sample_what = f"block 0 of {args.gpus} ({d['nCellsSolve']} owned cells + halo; halo values frozen), rate scaled by 1/{args.gpus}"
+    else:
+        from mpas_model_b200.case import make_case
+        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
+        frac = 1.0
+        sample_what = "the whole mesh"
     dt = cfg["config_dt"]
     o = OracleDycore(d, cfg)
     o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
     t0 = time.time(); o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); t1 = time.time() - t0
-    warm = max(0, min(args.warmup - 1, int(30.0 / max(t1, 1e-3))))
+    warm = max(0, min(args.warmup - 1, int(20.0 / max(t1, 1e-3))))
     for _ in range(warm):
         o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
-    steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
+    steps = max(1, min(args.steps, int(100.0 / max(t1, 1e-3))))
     t0 = time.time()
     for _ in range(steps):
         o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
     el = time.time() - t0
-    v = steps / el
+    v = frac * steps / el
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
-    print(json.dumps({
-        "impl": "reference", "metric": "JW wave dycore steps/sec", "value": v, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * el / steps,
-        "higher_is_better": True, "scaling": "strong-per-config", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
-        "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s, restated CPU dycore (C++/OpenMP), not the Fortran build"},
+    line = line_common(args, n_cells, n_lev, dt, args.gpus)
+    line["config"]["implementation"] = "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build"
+    line.update({
+        "impl": "reference", "value": v, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 / v,
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full atm_srk3 steps of the same workload"},
+                         "sample": f"{steps} full atm_srk3 steps on {sample_what}"},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sdpd": dt * v, "cell_columns_per_s": n_cells * v,
-    }))
+    })
+    print(json.dumps(line))
 
 
 def main():
@@ -136,6 +170,7 @@ def main():
     ap.add_argument("--levels", type=int, default=0)
     ap.add_argument("--scalars", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -143,102 +178,136 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, world)
         return
 
     import torch
-    from mpas_model_b200.case import make_case
     from mpas_model_b200.dycore import Dycore
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the dycore step has no CPU path")
-    n_cells, n_lev = WORKLOADS.get(args.gpus, WORKLOADS[1])
-    if args.cells:
-        n_cells = args.cells
-    if args.levels:
-        n_lev = args.levels
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} needs {args.gpus} ranks (torch.distributed.run), got WORLD_SIZE={world}")
+    n_cells, n_lev = workload_for(args)
+    torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
-        from mpas_model_b200 import multigpu
-        return multigpu.bench_main(args, rank, world, local_rank, n_cells, n_lev)
+        from mpas_model_b200 import multigpu as mg
+        dist = mg.init_distributed("gloo")
+        g, d, cfg, _ex, _ = mg.setup_rank(n_cells, n_lev, args.scalars, rank, world, local_rank)
+        dt = cfg["config_dt"]
+    else:
+        from mpas_model_b200.case import make_case
+        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
+        dt = cfg["config_dt"]
+        g = Dycore(d, cfg, device=0)
+        g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
 
-    torch.cuda.set_device(0)
-    d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
-    dt = cfg["config_dt"]
-    g = Dycore(d, cfg, device=0)
-    g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
+    def barrier():
+        g.synchronize(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
 
     # ---------------- device-resident throughput
     for _ in range(args.warmup):
         g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
-    g.synchronize(); torch.cuda.synchronize()
-    sampler = ClockSampler(0); sampler.start()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
     l0 = g.kernel_launch_count()
     g.timer_start()
     for _ in range(args.steps):
         g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
     ms = g.timer_stop()
-    g.synchronize(); torch.cuda.synchronize()
-    launches = g.kernel_launch_count() - l0
-    minmax = g.summarize_timestep()
-    ms_per_step = ms / args.steps
+    barrier()
+    launches = int(sum_over_ranks(g.kernel_launch_count() - l0))
+    ms_per_step = max_over_ranks(ms) / args.steps
     value = 1e3 / ms_per_step
+    mm = g.summarize_timestep()
+    if dist is not None:
+        t = torch.tensor([-mm[0], mm[1], -mm[2], mm[3]], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)              # the reference's mpas_dmpar_min/max_real (TI:8300-8318)
+        mm = (-float(t[0]), float(t[1]), -float(t[2]), float(t[3]))
+    minmax = mm
 
-    # ---------------- end to end through the C ABI with pinned host buffers
-    host = {}
-    for name, lev in set(E2E_FIELDS) | set(E2E_OUT):
-        t = torch.empty(tuple(g.shape(name)), dtype=torch.float64).pin_memory()
-        host[(name, lev)] = t.numpy()
-    for (name, lev) in E2E_FIELDS:
-        g._get_real(name, lev, host[(name, lev)])
-    h2d = sum(host[k].nbytes for k in E2E_FIELDS)
-    d2h = sum(host[k].nbytes for k in E2E_OUT) + 32
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def e2e_step():
-        for (name, lev) in E2E_FIELDS:                 # host pools -> device (pinned)
-            g._set_real(name, lev, host[(name, lev)])
-        g.atm_init_solve_diagnostics(dt)                # what a restart read is followed by (mpas_atm_core.F:524)
-        g.atm_srk3(dt)
-        for (name, lev) in E2E_OUT:                     # device -> host pools
+    # ---------------- end to end through the C ABI with pinned host buffers (every rank moves its own block)
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for name, lev in set(E2E_FIELDS) | set(E2E_OUT):
+            t = torch.empty(tuple(g.shape(name)), dtype=torch.float64).pin_memory()
+            host[(name, lev)] = t.numpy()
+        for (name, lev) in E2E_FIELDS:
             g._get_real(name, lev, host[(name, lev)])
-        mm = g.summarize_timestep()                     # the step's logged result (TI:8304,8319)
-        for name in ("u", "w", "rho_zz", "theta_m", "scalars"):     # mpas_pool_shift_time_levels on the host: swap pointers
-            host[(name, 1)], host[(name, 2)] = host[(name, 2)], host[(name, 1)]
-        return mm
+        h2d = sum(host[k].nbytes for k in E2E_FIELDS)
+        d2h = sum(host[k].nbytes for k in E2E_OUT) + 32
+        e2e_steps = max(3, min(args.steps, 10))
 
-    e2e_step()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+        def e2e_step():
+            for (name, lev) in E2E_FIELDS:                 # host pools -> device (pinned)
+                g._set_real(name, lev, host[(name, lev)])
+            g.atm_init_solve_diagnostics(dt)                # what a restart read is followed by (mpas_atm_core.F:524)
+            if dist is not None:
+                g.exchange_halo_group("initialization:pv_edge,ru,rw")      # mpas_atm_core.F:288
+            g.atm_srk3(dt)
+            for (name, lev) in E2E_OUT:                     # device -> host pools
+                g._get_real(name, lev, host[(name, lev)])
+            out = g.summarize_timestep()                    # the step's logged result (TI:8304,8319)
+            for name in ("u", "w", "rho_zz", "theta_m", "scalars"):     # mpas_pool_shift_time_levels on the host: swap pointers
+                host[(name, 1)], host[(name, 2)] = host[(name, 2)], host[(name, 1)]
+            return out
+
         e2e_step()
-    g.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e = {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": 1e3 * e2e_s}
     clocks = sampler.stop()
 
     # ---------------- per-kernel timing (CUDA events on the launching stream) for the roofline object
+    barrier()
     g.set_profile(True)
     nprof = 3
     for _ in range(nprof):
         g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
     rows = g.get_profile(); g.set_profile(False)
+    barrier()
     krows = {n: (m, c) for n, m, c in rows if n.startswith("k:")}
     ksum = sum(m for m, _ in krows.values())
     dom = max(krows.items(), key=lambda kv: kv[1][0])
     dom_name, (dom_ms, dom_cnt) = dom
     peak, peak_src = measured_peak_gbs()
-    C = n_lev * n_cells * 8
+    C = n_lev * d["nCells"] * 8                       # this rank's block (owned + halo columns)
     model_c = KERNEL_MODEL_C.get(dom_name)
     dom_us = 1e3 * dom_ms / dom_cnt
     achieved = (model_c * C / (dom_us * 1e-6) / 1e9) if model_c else None
     roofline = {"bound": "hbm", "kernel": dom_name[2:], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum, "algorithmic_bytes_per_launch": (model_c * C) if model_c else None,
-                "peak_source": peak_src}
+                "frac": (achieved / peak) if achieved else None, "traffic": KERNEL_TRAFFIC.get(dom_name),
+                "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum,
+                "algorithmic_bytes_per_launch": (model_c * C) if model_c else None, "peak_source": peak_src}
     B_step = model_bytes_per_step(n_cells, n_lev, args.scalars)
     step_gbs = B_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---------------- CPU baseline: the oracle on the host cores, bounded sample
+    # ---------------- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle.oracle import OracleDycore
         o = OracleDycore(d, cfg)
         o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
@@ -250,25 +319,19 @@ def main():
         cpu = {"value": n / el, "unit": "steps/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())),
                "kind": "port", "sample": f"{n} full atm_srk3 steps of the same workload (C++/OpenMP restatement, not the Fortran build)"}
 
-    line = {
-        "metric": "JW wave dycore steps/sec", "value": value, "unit": "steps/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong-per-config", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
-        "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s S={args.scalars}",
-                   "l2": "no flush: ~3.5 GB of fields are streamed per step, >> 126 MB L2",
-                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"},
-        "e2e": {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * e2e_s},
-        "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline,
-        "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs, "frac_of_measured_peak": step_gbs / peak,
-                          "frac_of_nominal_8TBs": step_gbs / 8000.0},
+    if rank != 0:
+        return
+    line = line_common(args, n_cells, n_lev, dt, world)
+    line.update({
+        "value": value, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs,
+                          "frac_of_measured_peak": step_gbs / (peak * world), "frac_of_nominal_8TBs": step_gbs / (8000.0 * world)},
         "cpu_baseline": cpu,
         "sdpd": dt * value, "cell_columns_per_s": n_cells * value,
         "minmax_w_u": list(minmax),
-        "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:12]},
-    }
+        "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:14]},
+    })
     print(json.dumps(line))
 
 

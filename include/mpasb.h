@@ -104,6 +104,11 @@ int  mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, int rk_ste
 int  mpasb_k_rk_dynamics_substep_finish(mpasb_handle h, int dynamics_substep, int dynamics_split); /* TI:7013 */
 int  mpasb_k_advance_scalars(mpasb_handle h, mpasb_real dt, int rk_step);            /* TI:3575 */
 int  mpasb_k_advance_scalars_mono(mpasb_handle h, mpasb_real dt);                    /* TI:4012 */
+/* ... and split at its two exchange points (TI:4155 scalars_old, TI:4568 scale) for hosts that
+ * keep calling the reference's own exchange_halo_group between the pieces; s is 0-based */
+int  mpasb_k_advance_scalars_mono_pre(mpasb_handle h, mpasb_real dt);                /* TI:4129-4143 */
+int  mpasb_k_advance_scalars_mono_a(mpasb_handle h, mpasb_real dt, int s);           /* TI:4177-4553 */
+int  mpasb_k_advance_scalars_mono_b(mpasb_handle h, mpasb_real dt, int s);           /* TI:4579-4715 */
 
 /* Halo exchange (mpas_halo_exch_group_full_halo_exch, src/framework/mpas_halo.F:498-846).
  * Lists are the reference's per-field sendListSrc/recvListDst (1-based local

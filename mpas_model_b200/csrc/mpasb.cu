@@ -428,6 +428,23 @@ static int advance_scalars_mono(H* h, real dt) {              // TI:4012-4734
     }
     return 0;
 }
+// the same routine split at its two exchange points, for hosts that exchange halos themselves
+static void mono_pre(H* h, real dt) { LAUNCH(k_mono_pre, h->D.nCellsSolve, 0, h->D, dt); }
+static void mono_a(H* h, real dt, int s) {
+    const Dev& D = h->D;
+    const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
+    if (s == 0 && adv_density) LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt);
+    const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
+    LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+    LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+    LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+}
+static void mono_b(H* h, int s) {
+    const Dev& D = h->D;
+    const real* rho = h->cfg.config_split_dynamics_transport ? D.rho_zz_int : D.rho_zz_2;
+    LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+    LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+}
 static void init_coupled_diagnostics(H* h) {                  // TI:6776-7010
     const real rcv = rgas / (cp - rgas);
     const real p0 = 1.e5;
@@ -558,3 +575,6 @@ extern "C" int mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, 
 extern "C" int mpasb_k_rk_dynamics_substep_finish(mpasb_handle h, int s, int n) ENTRY(rk_dynamics_substep_finish(h, s, n))
 extern "C" int mpasb_k_advance_scalars(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(advance_scalars(h, dt, rk_step))
 extern "C" int mpasb_k_advance_scalars_mono(mpasb_handle h, mpasb_real dt) ENTRY(if (advance_scalars_mono(h, dt)) return 1)
+extern "C" int mpasb_k_advance_scalars_mono_pre(mpasb_handle h, mpasb_real dt) ENTRY(mono_pre(h, dt))
+extern "C" int mpasb_k_advance_scalars_mono_a(mpasb_handle h, mpasb_real dt, int s) ENTRY(mono_a(h, dt, s))
+extern "C" int mpasb_k_advance_scalars_mono_b(mpasb_handle h, mpasb_real dt, int s) ENTRY(mono_b(h, s); (void)dt)

@@ -15,6 +15,8 @@ ship with the reference); it is host-side setup, as it is in the reference.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # src/framework/mpas_constants.F:43-56
@@ -202,24 +204,52 @@ def _recompute_geostrophic_wind(u_2d, rho_2d, pp_2d, qv_2d, lat_2d, zz_2d, zx_2d
     return out
 
 
-def _jw_columns(lat, zgrid, zz, dzw, dzu, fzm, fzp, qv):
+def _jw_columns(lat, zgrid, zz, dzw, dzu, fzm, fzp, qv, chunk=2048):
     """Iterative hydrostatic balance of the JW temperature profile on columns.
     lat [n]; zgrid [n, nz]; zz [n, nz1]; returns dict of [n, nz1] arrays.
-    (mpas_init_atm_cases.F:803-886 for the (lat,z) slice and :912-1021 per cell.)"""
+    (mpas_init_atm_cases.F:803-886 for the (lat,z) slice and :912-1021 per cell.)
+    Columns are independent: they are processed in cache-sized chunks on a thread pool
+    (numpy releases the GIL inside its loops); the arithmetic per column is unchanged."""
+    n = zgrid.shape[0]
+    keys = ("ppb", "pb", "rb", "tb", "pp", "rr", "tt")
+    if n <= chunk:
+        return _jw_columns_chunk(lat, zgrid, zz, dzw, dzu, fzm, fzp, qv)
+    out = {k: np.empty_like(zz) for k in keys}
+
+    def work(s):
+        e = slice(s, min(n, s + chunk))
+        r = _jw_columns_chunk(lat[e], zgrid[e], zz[e], dzw, dzu, fzm, fzp, qv[e])
+        for k in keys:
+            out[k][e] = r[k]
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(work, range(0, n, chunk)))
+    return out
+
+
+def _jw_columns_chunk(lat, zgrid, zz, dzw, dzu, fzm, fzp, qv):
+    # level-major [nz1, n] work arrays: every level slice is contiguous
     u0, t0b, t0, delta_t, dtdz, znut = 35.0, 250.0, 288.0, 4.8e5, 0.005, 0.2
     n, nz = zgrid.shape
     nz1 = nz - 1
-    ztemp = 0.5 * (zgrid[:, 1:] + zgrid[:, :-1])
+    zgrid = np.ascontiguousarray(zgrid.T)
+    zz = np.ascontiguousarray(zz.T)
+    qv = np.ascontiguousarray(qv.T)
+    ztemp = 0.5 * (zgrid[1:] + zgrid[:-1])
     ppb = P0 * np.exp(-GRAVITY * ztemp / (RGAS * t0b))
     pb = (ppb / P0) ** (RGAS / CP)
     rb = ppb / (RGAS * t0b * zz)
     tb = t0b / pb
     pp = np.zeros_like(ppb)
     rr = np.zeros_like(ppb)
-    phi = lat[:, None]
+    phi = lat[None, :]
     lat_term_a = (-2.0 * np.sin(phi) ** 6 * (np.cos(phi) ** 2 + 1.0 / 3.0) + 10.0 / 63.0)
     lat_term_b = (1.6 * np.cos(phi) ** 3 * (np.sin(phi) ** 2 + 2.0 / 3.0) - PII / 4.0) * A_EARTH * OMEGA
     tt = None
+    ppi = np.empty_like(pp)
+    cz = (dzu[1:nz1] * GRAVITY)[:, None]
+    fp_, fm_ = fzp[1:nz1][:, None], fzm[1:nz1][:, None]
     for _itr in range(10):
         eta = (ppb + pp) / P0
         etav = (eta - 0.252) * PII / 2.0
@@ -230,15 +260,16 @@ def _jw_columns(lat, zgrid, zz, dzw, dzu, fzm, fzp, qv):
         tt = temperature * (1.0 + 1.61 * qv)
         for _itrp in range(25):
             rr = (pp / (RGAS * zz) - rb * (tt - t0b)) / tt
-            ppi = np.empty_like(pp)
-            ppi[:, 0] = P0 - 0.5 * dzw[0] * GRAVITY * (1.25 * (rr[:, 0] + rb[:, 0]) * (1.0 + qv[:, 0])
-                                                        - 0.25 * (rr[:, 1] + rb[:, 1]) * (1.0 + qv[:, 1]))
-            ppi[:, 0] = ppi[:, 0] - ppb[:, 0]
+            ppi[0] = P0 - 0.5 * dzw[0] * GRAVITY * (1.25 * (rr[0] + rb[0]) * (1.0 + qv[0])
+                                                    - 0.25 * (rr[1] + rb[1]) * (1.0 + qv[1]))
+            ppi[0] = ppi[0] - ppb[0]
             rq = rr + (rr + rb) * qv
+            term = cz * (rq[:-1] * fp_ + rq[1:] * fm_)
             for k in range(nz1 - 1):
-                ppi[:, k + 1] = ppi[:, k] - dzu[k + 1] * GRAVITY * (rq[:, k] * fzp[k + 1] + rq[:, k + 1] * fzm[k + 1])
+                np.subtract(ppi[k], term[k], out=ppi[k + 1])
             pp = 0.2 * ppi + 0.8 * pp
-    return dict(ppb=ppb, pb=pb, rb=rb, tb=tb, pp=pp, rr=rr, tt=tt)
+    return {k: np.ascontiguousarray(v.T) for k, v in
+            dict(ppb=ppb, pb=pb, rb=rb, tb=tb, pp=pp, rr=rr, tt=tt).items()}
 
 
 def _flux_zonal(u_2d, lat_2d, lat1_in, lat2_in, dvEdge, a, u0, nz1, nlat, chunk=65536):

@@ -1693,6 +1693,15 @@ void oracle_recover_large_step_variables(void* h, double dt, int ns, int rk_step
 void oracle_compute_solve_diagnostics(void* h, double dt, int rk_step) { atm_compute_solve_diagnostics(*(Block*)h, dt, 2, rk_step); }
 void oracle_rk_dynamics_substep_finish(void* h, int s, int n) { atm_rk_dynamics_substep_finish(*(Block*)h, s, n); }
 void oracle_advance_scalars(void* h, double dt, int rk_step) { atm_advance_scalars(*(Block*)h, dt, rk_step); }
+// the monotonic transport split at its two exchange points (TI:4155, TI:4568), for drivers that
+// perform the halo exchanges themselves (mpas_model_b200/multigpu.py: srk3_host_exchange)
+void oracle_advance_scalars_mono_pre(void* h, double dt) { mono_pre_update(*(Block*)h, dt); }
+void oracle_advance_scalars_mono_a(void* h, double dt, int s) {
+    Block& b = *(Block*)h;
+    if (s == 0) mono_rho_zz_int(b, dt);
+    mono_scalar_phase1(b, dt, s + 1);
+}
+void oracle_advance_scalars_mono_b(void* h, double dt, int s) { mono_scalar_phase2(*(Block*)h, dt, s + 1); }
 void oracle_advance_scalars_mono(void* h, double dt) {
     Block& b = *(Block*)h;
     mono_pre_update(b, dt); mono_rho_zz_int(b, dt);

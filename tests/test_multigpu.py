@@ -1,0 +1,87 @@
+"""N > 1: one block per rank, real processes.
+
+CPU (gloo, world_size 2): each rank runs the oracle on its block and exchanges halos on host arrays
+with the message layout of mpas_halo.F:671,695; the owned results must equal the single-block run
+bit for bit (the decomposition keeps the reference's redundant owned-edge computation, TI:2757-2759).
+GPU (-m gpu, needs >= 2 devices): the same through the library's pack -> NCCL -> unpack path."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STATE = ("u", "w", "rho_zz", "theta_m", "scalars")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _launch(mode, world, n_cells, n_lev, n_scal, n_steps, out, tmp_path):
+    env = dict(os.environ, MPASB_CACHE=str(tmp_path), OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "mp_worker.py"), mode, str(n_cells), str(n_lev), str(n_scal), str(n_steps), out]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _single_block_oracle(n_cells, n_lev, n_scal, n_steps):
+    from mpas_model_b200.case import make_case
+    from oracle.oracle import OracleDycore
+    d, cfg = make_case(n_cells, n_lev, num_scalars=n_scal)
+    o = OracleDycore(d, cfg)
+    dt = cfg["config_dt"]
+    o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+    for _ in range(n_steps):
+        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+    return d, {n: o.get_array(n) for n in STATE}
+
+
+def test_two_ranks_gloo_equal_one_block_bit_for_bit(tmp_path):
+    out = str(tmp_path / "gloo2.npz")
+    _launch("oracle", 2, 642, 10, 2, 2, out, tmp_path)
+    d, ref = _single_block_oracle(642, 10, 2, 2)
+    got = np.load(out)
+    for n in STATE:
+        cnt = got[n].shape[0]
+        assert cnt == (d["nEdges"] if n == "u" else d["nCells"])
+        assert np.array_equal(got[n], ref[n][:cnt]), n
+
+
+def test_group_tables_agree():
+    """multigpu.GROUPS (host exchange) and the library's table (csrc/halo_host.inl) list the same
+    fields, time levels and halo layers for every group."""
+    import re
+    from mpas_model_b200 import multigpu as mg
+    src = open(os.path.join(ROOT, "mpas_model_b200", "csrc", "halo_host.inl")).read()
+    kinds = {0: "cells", 1: "edges", 2: "vertices"}
+    found = {}
+    for name, body in re.findall(r'\{"((?:dynamics|initialization):[^"]+)",\s*\{(.*?)\}\},', src):
+        fields = []
+        for f, lev, kind, mask in re.findall(r'\{"(\w+)",\s*(\d),\s*(\d),\s*(\d)\}', body):
+            layers = tuple(l + 1 for l in range(3) if int(mask) & (1 << l))
+            fields.append((f, int(lev), kinds[int(kind)], layers))
+        found[name] = tuple(fields)
+    assert found == mg.GROUPS
+
+
+@pytest.mark.gpu
+def test_two_gpus_nccl_equal_one_block(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path / "nccl2.npz")
+    _launch("gpu", 2, 2562, 26, 2, 2, out, tmp_path)
+    d, ref = _single_block_oracle(2562, 26, 2, 2)
+    got = np.load(out)
+    for n in STATE:
+        cnt = got[n].shape[0]
+        a, b = got[n], ref[n][:cnt]
+        rel = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+        assert rel <= 1e-10, (n, rel)
