@@ -121,6 +121,10 @@ int  mpasb_comm_init(mpasb_handle h, int rank, int world_size, const void* nccl_
 int  mpasb_get_nccl_unique_id(void* out128);
 int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HALOS:90-167 names */
 
+/* 1 if every kernel keeps the reference's operation order without FMA contraction (results bit-identical to
+ * the fp64 CPU arithmetic; the only build at present), 0 for a relaxed build */
+int  mpasb_strict_arithmetic(void);
+
 /* Instrumentation */
 long mpasb_kernel_launch_count(mpasb_handle h);      /* kernels launched by this handle so far */
 int  mpasb_timer_start(mpasb_handle h);              /* CUDA event on the compute stream */

@@ -205,7 +205,7 @@ __global__ void k_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     const int ne = D.nEdgesOnCell[i];
     real w = AT(D.w_2, i, k);
     const real fm = D.fzm[k], fp = D.fzp[k];
-    for (int e = 0; e < ne; e++) {
+    if (D.zb_any[i]) for (int e = 0; e < ne; e++) {
         const int iEdge = D.edgesOnCell[(size_t)i * D.maxEdges + e];
         real flux;
         if (k == 0) flux = (cf1 * AT(D.ru, iEdge, 0) + cf2 * AT(D.ru, iEdge, 1) + cf3 * AT(D.ru, iEdge, 2));

@@ -1,0 +1,495 @@
+// kernels_col.cuh -- "column-warp" versions of the hot kernels of the dycore step.
+//
+// Mapping: one warp per mesh column (cell or edge), lane l owns the level pair
+// (2l, 2l+1), so every field access is a 16-byte vector load of a level-contiguous
+// column (LDK <= 64 levels; taller columns use the generic (k, column) kernels of
+// kernels_dyn.cuh / kernels_acoustic.cuh).  Vertical neighbours (k-2 .. k+1) come from
+// warp shuffles, the per-column connectivity and weights are loaded once per warp
+// (one entry per lane) and broadcast, advection lists are staged in shared memory, and
+// the column tridiagonal solve runs out of shared memory.
+//
+// Every expression keeps the operand order of the generic kernels (and therefore of
+// mpas_atm_time_integration.F, "TI"), so results stay bit-identical to the fp64 CPU
+// arithmetic when built --fmad=false.
+//
+// Latency structure: these kernels are chains of gathers whose addresses come from other loads, so
+// what bounds them is the number of EXPOSED memory latencies per warp, not bytes.  Each kernel
+// therefore (1) loads its connectivity once, with lanes beyond the list length duplicating the last
+// valid entry so that every later gather is unconditional, (2) runs its gather loops fully unrolled
+// over a fixed trip count (CW_NE edges, CW_NADV stencil cells; longer lists take a tail loop) with
+// the accumulation -- not the load -- predicated, so all loads of a loop are in flight together,
+// and (3) issues every store at the very end: a store in the middle would pin all later loads
+// behind it (the compiler must assume the Dev pointers alias).
+#pragma once
+#include "kernels_dyn.cuh"
+
+#define CW_FULL 0xffffffffu
+#define CW_WARPS 8                      // warps (= columns) per block
+#define CW_THREADS (CW_WARPS * 32)
+#ifndef CW_MINB
+#define CW_MINB 2                       // resident blocks per SM the register allocation aims for
+#endif
+
+struct __align__(2 * sizeof(real)) r2 { real x, y; };
+struct b2 { bool x, y; };
+
+__device__ __forceinline__ r2 mk2(real a, real b) { r2 r; r.x = a; r.y = b; return r; }
+__device__ __forceinline__ r2 splat(real a) { return mk2(a, a); }
+__device__ __forceinline__ r2 operator+(r2 a, r2 b) { return mk2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ r2 operator-(r2 a, r2 b) { return mk2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ r2 operator*(r2 a, r2 b) { return mk2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ r2 operator/(r2 a, r2 b) { return mk2(a.x / b.x, a.y / b.y); }
+__device__ __forceinline__ r2 operator+(r2 a, real b) { return mk2(a.x + b, a.y + b); }
+__device__ __forceinline__ r2 operator-(r2 a, real b) { return mk2(a.x - b, a.y - b); }
+__device__ __forceinline__ r2 operator*(r2 a, real b) { return mk2(a.x * b, a.y * b); }
+__device__ __forceinline__ r2 operator/(r2 a, real b) { return mk2(a.x / b, a.y / b); }
+__device__ __forceinline__ r2 operator+(real a, r2 b) { return mk2(a + b.x, a + b.y); }
+__device__ __forceinline__ r2 operator-(real a, r2 b) { return mk2(a - b.x, a - b.y); }
+__device__ __forceinline__ r2 operator*(real a, r2 b) { return mk2(a * b.x, a * b.y); }
+__device__ __forceinline__ r2 operator/(real a, r2 b) { return mk2(a / b.x, a / b.y); }
+__device__ __forceinline__ r2 operator-(r2 a) { return mk2(-a.x, -a.y); }
+__device__ __forceinline__ r2 sel(b2 m, r2 a, r2 b) { return mk2(m.x ? a.x : b.x, m.y ? a.y : b.y); }
+__device__ __forceinline__ r2 sel(b2 m, r2 a, real b) { return mk2(m.x ? a.x : b, m.y ? a.y : b); }
+__device__ __forceinline__ r2 selb(bool on, r2 a, r2 b) { return mk2(on ? a.x : b.x, on ? a.y : b.y); }   // warp-uniform condition
+__device__ __forceinline__ r2 abs2(r2 a) { return mk2(fabs(a.x), fabs(a.y)); }
+__device__ __forceinline__ b2 operator&&(b2 a, b2 b) { b2 r; r.x = a.x && b.x; r.y = a.y && b.y; return r; }
+__device__ __forceinline__ b2 operator||(b2 a, b2 b) { b2 r; r.x = a.x || b.x; r.y = a.y || b.y; return r; }
+__device__ __forceinline__ b2 operator!(b2 a) { b2 r; r.x = !a.x; r.y = !a.y; return r; }
+// Fortran sign(1.0, x) > 0  <=>  sign bit clear (so +0 -> +1, -0 -> -1, TI:5744, 5978)
+__device__ __forceinline__ b2 nonneg_sign(r2 a) { b2 r; r.x = !signbit(a.x); r.y = !signbit(a.y); return r; }
+
+// per-lane level predicates for the pair (k0, k0 + 1)
+struct Lv {
+    int k0;
+    __device__ __forceinline__ b2 lt(int n) const { b2 r; r.x = k0 < n; r.y = k0 + 1 < n; return r; }
+    __device__ __forceinline__ b2 ge(int n) const { b2 r; r.x = k0 >= n; r.y = k0 + 1 >= n; return r; }
+    __device__ __forceinline__ b2 eq(int n) const { b2 r; r.x = k0 == n; r.y = k0 + 1 == n; return r; }
+    __device__ __forceinline__ b2 in(int lo, int hi) const { b2 r; r.x = k0 >= lo && k0 <= hi; r.y = k0 + 1 >= lo && k0 + 1 <= hi; return r; }
+};
+
+// column pair load/store.  Element offsets are 32-bit (a block holds < 2^32 reals per field), so an
+// address costs one IMAD + one IMAD.WIDE; lanes beyond the padded column re-read its last pair
+// (kc = min(k0, LDK-2)) instead of being predicated off -- their results are never stored.
+__device__ __forceinline__ r2 ld2(const real* __restrict__ p, unsigned off) {
+    return *reinterpret_cast<const r2*>(p + off);
+}
+__device__ __forceinline__ void st2(real* p, unsigned off, bool act, r2 v) {
+    if (act) *reinterpret_cast<r2*>(p + off) = v;
+}
+// vertical shifts inside the warp: result[k] = v[k-1], v[k+1], v[k-2]
+__device__ __forceinline__ r2 up1(r2 v) { return mk2(__shfl_up_sync(CW_FULL, v.y, 1), v.x); }
+__device__ __forceinline__ r2 dn1(r2 v) { return mk2(v.y, __shfl_down_sync(CW_FULL, v.x, 1)); }
+__device__ __forceinline__ r2 up2(r2 v) { return mk2(__shfl_up_sync(CW_FULL, v.x, 1), __shfl_up_sync(CW_FULL, v.y, 1)); }
+__device__ __forceinline__ r2 dn2(r2 v) { return mk2(__shfl_down_sync(CW_FULL, v.x, 1), __shfl_down_sync(CW_FULL, v.y, 1)); }
+
+__device__ __forceinline__ r2 flux4_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 ua) {
+    return ua * (7. * (q_i + q_im1) - (q_ip1 + q_im2)) / 12.0;
+}
+__device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 ua, real coef3) {
+    return flux4_2(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * abs2(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;
+}
+
+#define CW_SETUP(ncols)                                                                       \
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
+    const int i = blockIdx.x * CW_WARPS + wib;                                                \
+    const int LDK = D.LDK, nl = D.nl;                                                         \
+    if (i >= (ncols)) return;                                                                 \
+    Lv lv; lv.k0 = 2 * lane;                                                                  \
+    const int k0 = lv.k0; const bool act = k0 < LDK; (void)nl;                                \
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+#define LD(p, col) ld2((p), (unsigned)(col) * uLDK + kc)
+#define ST(p, col, v) st2((p), (unsigned)(col) * uLDK + kc, act, (v))
+#define BC(v, src) __shfl_sync(CW_FULL, (v), (src))
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f)
+// The reference computes the 3rd/4th-order horizontal flux of w and theta_m inside the cell loop, i.e. every
+// edge flux twice -- once from each adjacent cell (TI:5713-5757, 5956-5991) -- through a 10-cell stencil.  That
+// loop is bound by the L1 data pipe (120 gathered columns per cell).  Here the flux is computed ONCE per edge
+// (k2_dt_edge_flux: 20 gathered columns per edge = 60 per cell) into two edge scratch arrays, and the cell kernel
+// only sums its <= CW_MAXNE edge fluxes.  The result is bit-identical: the reference's cell-side expression
+// (sign * ru_edge) * flux and sign * (ru_edge * flux) differ by an exact sign flip only (sign = +/-1).
+#define CW_MAXNE 8                      // most edges per cell these kernels handle (host checks nEdgesOnCell)
+#define CW_NE 6                         // edges per cell covered by the unrolled loops
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;           // only edges of owned cells are consumed
+    const int nadv = D.nAdvCellsForEdge[i];
+    // one stencil entry per lane: cell index and the two possible weights adv_coefs +/- adv_coefs_3rd
+    // (TI:5744-5750: coef + sign(ru) * coef_3rd with sign = +/-1)
+    int my_c = 0; real my_wp = 0.0, my_wm = 0.0;
+    if (lane < nadv) {
+        my_c = D.advCellsForEdge[(unsigned)i * 15 + lane];
+        const real a = D.adv_coefs[(unsigned)i * 15 + lane], b = D.adv_coefs_3rd[(unsigned)i * 15 + lane];
+        my_wp = a + b; my_wm = a - b;
+    }
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const r2 ruk = LD(D.ru, i);
+    const r2 ruw = fm * ruk + fp * up1(ruk);               // ru_edge_w (levels k >= 1)
+    const b2 pw = nonneg_sign(ruw), pt = nonneg_sign(ruk);
+    r2 fw = mk2(0.0, 0.0), ft = mk2(0.0, 0.0);
+#pragma unroll 5
+    for (int j = 0; j < nadv; j++) {
+        const int c = BC(my_c, j);
+        const real wp = BC(my_wp, j), wm = BC(my_wm, j);
+        const r2 w2 = LD(D.w_2, c), t2 = LD(D.theta_m_2, c);
+        fw.x = fw.x + (pw.x ? wp : wm) * w2.x;
+        fw.y = fw.y + (pw.y ? wp : wm) * w2.y;
+        ft.x = ft.x + (pt.x ? wp : wm) * t2.x;
+        ft.y = ft.y + (pt.y ? wp : wm) * t2.y;
+    }
+    ST(D.adv_flux_w, i, sel(lv.ge(1) && lv.lt(nl), ruw * fw, 0.0));
+    ST(D.adv_flux_theta, i, sel(lv.lt(nl), ruk * ft, 0.0));
+}
+
+// owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
+// Restrictions (the host falls back to k_dt_cell_f otherwise): v_mom_eddy_visc2 == v_theta_eddy_visc2 == 0.
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    // one edge of the cell per lane (lanes >= ne repeat the last edge): id, sign, mixing metadata
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    const real my_dv = D.dvEdge[my_e];
+    real my_d4 = 0.0, my_idc = 0.0;
+    if (A.rk_step == 1) { my_d4 = D.meshScalingDel4[my_e]; my_idc = D.invDcEdge[my_e]; }
+    const real invArea = D.invAreaCell[i];
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
+    // horizontal flux divergence of w and theta_m from the per-edge fluxes
+#define CELL_F_EDGE(E)                                                                                      \
+    {                                                                                                       \
+        const int iEdge = BC(my_e, (E));                                                                    \
+        const real sg = BC(my_sgn, (E));                                                                    \
+        const r2 fxw = LD(D.adv_flux_w, iEdge), fxt = LD(D.adv_flux_theta, iEdge);                          \
+        tw = selb((E) < ne, tw - sg * fxw, tw);                                                             \
+        tt = selb((E) < ne, tt - sg * fxt, tt);                                                             \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) CELL_F_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) CELL_F_EDGE(e)
+#undef CELL_F_EDGE
+    // own-column operands of the vertical terms: issued here so that they travel while the loops below run
+    const r2 rdzu = LD(D.rdzu, 0), rdzw = LD(D.rdzw, 0);
+    const r2 rw = LD(D.rw, i), w = LD(D.w_2, i), t = LD(D.theta_m_2, i), ts = LD(D.theta_m, i), rws = LD(D.rw_save, i);
+    const r2 rho = LD(D.rho_zz_2, i), tend_rho = LD(D.tend_rho, i), rtdiab = LD(D.rt_diabatic_tend, i);
+    const r2 trp = LD(D.tend_rtheta_physics, i);
+    r2 twe = LD(D.tend_w_euler, i), tte = LD(D.tend_theta_euler, i);
+    const r2 twe_in = twe;
+    r2 pp = mk2(0.0, 0.0), dpdz = mk2(0.0, 0.0), cqw = mk2(0.0, 0.0);
+    if (A.rk_step == 1) { pp = LD(D.pressure_p, i); dpdz = LD(D.dpdz, i); cqw = LD(D.cqw, i); }
+    if (A.rk_step > 1) {          // perturbation flux for the rtheta_pp equation, TI:5995-6016
+#define CELL_F_PERT(E)                                                                                      \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                \
+            const real sg = BC(my_sgn, (E)), dv = BC(my_dv, (E));                                           \
+            const r2 flux = sg * dv * (LD(D.ru_save, iEdge) - LD(D.ru, iEdge)) * 0.5 * (LD(D.theta_m, cell2) + LD(D.theta_m, cell1)); \
+            tt = selb((E) < ne, tt - flux, tt);                                                             \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) CELL_F_PERT(e)
+        for (int e = CW_NE; e < ne; e++) CELL_F_PERT(e)
+#undef CELL_F_PERT
+    }
+    const b2 k_ge1 = lv.ge(1), k_lt_nl = lv.lt(nl);
+    if (A.rk_step == 1) {
+#define CELL_F_DEL4(E, ACC, FIELD, RAREA)                                                                   \
+        {                                                                                                   \
+            const int cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                                       \
+            const real edge_sign = BC(my_d4, (E)) * (RAREA) * BC(my_dv, (E)) * BC(my_sgn, (E)) * BC(my_idc, (E)); \
+            const r2 d = LD(FIELD, cell2) - LD(FIELD, cell1);                                               \
+            ACC = selb((E) < ne, ACC - edge_sign * d, ACC);                                                 \
+        }
+        if (A.h_mom_eddy_visc4 > 0.0) {
+            const real r_areaCell = A.h_mom_eddy_visc4 * invArea;
+#pragma unroll
+            for (int e = 0; e < CW_NE; e++) CELL_F_DEL4(e, twe, D.delsq_w, r_areaCell)
+            for (int e = CW_NE; e < ne; e++) CELL_F_DEL4(e, twe, D.delsq_w, r_areaCell)
+        }
+        if (A.h_theta_eddy_visc4 > 0.0) {
+            const real r_areaCell = A.h_theta_eddy_visc4 * A.prandtl_inv * invArea;
+#pragma unroll
+            for (int e = 0; e < CW_NE; e++) CELL_F_DEL4(e, tte, D.delsq_theta, r_areaCell)
+            for (int e = CW_NE; e < ne; e++) CELL_F_DEL4(e, tte, D.delsq_theta, r_areaCell)
+        }
+#undef CELL_F_DEL4
+    }
+    const r2 rwm1 = up1(rw);
+    const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
+    const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
+    // ---- w: vertical advection (TI:5878-5891), pressure gradient, buoyancy
+    {
+        const r2 wm1 = up1(w), wm2 = up2(w), wp1 = dn1(w);
+        const r2 f2 = 0.25 * (rw + rwm1) * (w + wm1);
+        const r2 f3 = flux3_2(wm2, wm1, w, wp1, 0.5 * (rw + rwm1), 1.0);
+        const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(kk_edge, f2, f3));     // flux at interface k
+        const r2 f1 = dn1(fz);
+        tw = tw * invArea - rdzu * (f1 - fz);
+        if (A.rk_step == 1) {
+            const r2 twe_new = twe - cqw * (rdzu * (pp - up1(pp)) - (fm * dpdz + fp * up1(dpdz)));
+            twe = sel(k_ge1 && k_lt_nl, twe_new, twe_in);    // rows 0 and nl keep what they held
+        }
+    }
+    const r2 out_tend_w = sel(k_ge1 && k_lt_nl, tw + twe, 0.0);
+    // ---- theta_m: vertical advection (TI:6101-6116), mixing
+    r2 out_rthdynten;
+    {
+        const r2 tm1 = up1(t), tm2 = up2(t), tp1 = dn1(t), tsm1 = up1(ts);
+        const r2 ftop = rws * (fm * t + fp * tm1);                                   // kk == nl-1
+        const r2 flow = rw * (fm * t + fp * tm1);                                    // kk == 1
+        const r2 f3 = flux3_2(tm2, tm1, t, tp1, rw, A.coef_3rd_order);
+        const r2 fpert = sel(lv.eq(1), flow, f3) + (rws - rw) * (fm * ts + fp * tsm1);
+        const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(lv.eq(nl - 1), ftop, fpert));
+        const r2 f1 = dn1(fz);
+        tt = tt * invArea - rdzw * (f1 - fz);
+        out_rthdynten = sel(k_lt_nl, (tt - tend_rho * t) / rho, 0.0);
+        tt = tt + rho * rtdiab;
+    }
+    if (A.rk_step == 1) {
+        ST(D.tend_w_euler, i, twe);
+        ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
+    }
+    ST(D.tend_w, i, out_tend_w);
+    ST(D.rthdynten, i, out_rthdynten);
+    ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (b)
+// edge-all: [rk 1] PGF (5379-5387), delsq_u + del2 mixing (5467-5503); [owned edges] vertical transport,
+// nonlinear Coriolis, KE gradient (5391-5447); [rk > 1] final sum with tend_u_euler (5694-5701).
+// Restriction (host falls back to k_dt_edge_b otherwise): config_rayleigh_damp_u off.
+// This kernel is bound by the L1 data pipe (46 gathered columns per edge), not by latency: it is kept at
+// ~64 registers for 32 resident warps per SM rather than unrolled for more loads in flight (measured).
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    const bool solve = i < D.nEdgesSolve;
+    const real invDc = D.invDcEdge[i];
+    const b2 k_lt_nl = lv.lt(nl);
+    const r2 rho_e = LD(D.rho_edge, i);
+    if (A.rk_step == 1) {
+        r2 tue = mk2(0.0, 0.0);
+        if (solve)
+            tue = -LD(D.cqu, i) * ((LD(D.pressure_p, cell2) - LD(D.pressure_p, cell1)) * invDc / (.5 * (LD(D.zz, cell2) + LD(D.zz, cell1)))
+                                   - 0.5 * LD(D.zxu, i) * (LD(D.dpdz, cell1) + LD(D.dpdz, cell2)));
+        const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
+        const real r_dc = invDc;
+        const real r_dv = fmin(D.invDvEdge[i], 4 * invDc);
+        const r2 u_diffusion = (LD(D.divergence, cell2) - LD(D.divergence, cell1)) * r_dc
+                               - (LD(D.vorticity, vertex2) - LD(D.vorticity, vertex1)) * r_dv;
+        ST(D.delsq_u, i, sel(k_lt_nl, 0.0 + u_diffusion, 0.0));
+        const r2 kdiffu = 0.5 * (LD(D.kdiff, cell1) + LD(D.kdiff, cell2));
+        tue = tue + rho_e * kdiffu * u_diffusion * D.meshScalingDel2[i];
+        ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
+    }
+    if (!solve) return;
+    const r2 u = LD(D.u_2, i);
+    r2 tu;
+    {   // vertical transport of u, TI:5391-5408
+        const r2 rwf = LD(D.rw, cell1) + LD(D.rw, cell2);
+        const r2 um1 = up1(u), um2 = up2(u), up = dn1(u);
+        const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+        const r2 f2 = 0.5 * (rwf) * (fm * u + fp * um1);
+        const r2 f3 = flux3_2(um2, um1, u, up, 0.5 * (rwf), 1.0);
+        const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);
+        const b2 kk_zero = lv.lt(1) || lv.ge(nl);
+        const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(kk_edge, f2, f3));
+        const r2 f1 = dn1(fz);
+        tu = -LD(D.rdzw, 0) * (f1 - fz);
+    }
+    r2 q = mk2(0.0, 0.0);
+    const int neoe = D.nEdgesOnEdge[i];
+    int my_eoe = 0; real my_woe = 0.0;
+    if (lane < neoe) { my_eoe = D.edgesOnEdge[(unsigned)i * D.maxEdges2 + lane]; my_woe = D.weightsOnEdge[(unsigned)i * D.maxEdges2 + lane]; }
+    const r2 pv_e = LD(D.pv_edge, i);
+#pragma unroll 5
+    for (int j = 0; j < neoe; j++) {
+        const int eoe = BC(my_eoe, j);
+        const real woe = BC(my_woe, j);
+        const r2 workpv = 0.5 * (pv_e + LD(D.pv_edge, eoe));
+        q = q + woe * LD(D.u_2, eoe) * workpv;
+    }
+    tu = tu + rho_e * (q - (LD(D.ke, cell2) - LD(D.ke, cell1)) * invDc)
+         - u * 0.5 * (LD(D.h_divergence, cell1) + LD(D.h_divergence, cell2));
+    if (A.rk_step != 1) tu = tu + LD(D.tend_u_euler, i) + LD(D.tend_ru_physics, i);
+    ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_advance_acoustic_step_work, cell part  TI:2824-2973
+// One warp per cell.  Right-hand sides are assembled by all lanes; lane 0 then runs the two
+// tridiagonal sweeps (TI:2922-2930) out of the warp's shared-memory slab in the reference's order,
+// while the operands of the post-solve damping step are already in flight.
+#define AC_STRIDE 66
+__global__ void __launch_bounds__(CW_THREADS, CW_MINB) k2_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    __shared__ __align__(16) real s_rw[CW_WARPS][AC_STRIDE], s_a[CW_WARPS][AC_STRIDE], s_al[CW_WARPS][AC_STRIDE], s_ga[CW_WARPS][AC_STRIDE];
+    CW_SETUP(D.nCells)
+    const bool first = small_step == 1;
+    const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
+    // old values of the perturbation variables (zero on the first small step, TI:2850-2860)
+    r2 rtheta_pp = mk2(0.0, 0.0);
+    if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
+    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); return; }
+    const int ne = D.nEdgesOnCell[i];
+    const real invArea = D.invAreaCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
+    r2 rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
+    if (!first) {
+        rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
+        wwAvg = sel(k_le_nl, LD(D.wwAvg, i), 0.0);
+        rho_pp = sel(k_lt_nl, LD(D.rho_pp, i), 0.0);
+    }
+    const r2 tend_rho = LD(D.tend_rho, i), tend_theta = LD(D.tend_theta, i), tend_w = LD(D.tend_w, i);
+    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
+    const r2 zz = LD(D.zz, i);
+    const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
+    r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
+#define AC_EDGE(E)                                                                                          \
+    {                                                                                                       \
+        const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                    \
+        const r2 flux = BC(my_f, (E)) * LD(D.ru_p, iEdge) * invArea;                                        \
+        const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                          \
+        rs = selb((E) < ne, rs - flux, rs);                                                                 \
+        ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                      \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) AC_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) AC_EDGE(e)
+#undef AC_EDGE
+    // operands of the implicit Rayleigh damping step (TI:2936-2942): requested before the solve
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
+    const r2 rw_p1 = dn1(rw_p);
+    const r2 coftz1 = dn1(coftz);
+    rs = rho_pp + dts * tend_rho + rs
+         - cofrz * resm * (rw_p1 - rw_p);
+    ts = rtheta_pp + dts * tend_theta + ts
+         - resm * rdzw * (coftz1 * rw_p1
+                          - coftz * rw_p);
+    rs = sel(k_lt_nl, rs, 0.0); ts = sel(k_lt_nl, ts, 0.0);
+    wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 - epssm) * rw_p, wwAvg);
+    const r2 zzm = up1(zz);
+    {
+        const r2 tsm = up1(ts), rsm = up1(rs), rtm = up1(rtheta_pp), rhm = up1(rho_pp), cofwtm = up1(cofwt);
+        const r2 r = rw_p + dts * tend_w
+                     - cofwz * ((zz * ts
+                                 - zzm * tsm)
+                                + resm * (zz * rtheta_pp
+                                          - zzm * rtm))
+                     - cofwr * ((rs + rsm)
+                                + resm * (rho_pp + rhm))
+                     + cofwt * (ts + resm * rtheta_pp)
+                     + cofwtm * (tsm + resm * rtm);
+        const r2 rhs = sel(k_mid, r, rw_p);
+        if (act) {
+            *reinterpret_cast<r2*>(&s_rw[wib][k0]) = rhs; *reinterpret_cast<r2*>(&s_a[wib][k0]) = a_tri;
+            *reinterpret_cast<r2*>(&s_al[wib][k0]) = al_tri; *reinterpret_cast<r2*>(&s_ga[wib][k0]) = ga_tri;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        real* rwv = s_rw[wib];
+        const real* av = s_a[wib]; const real* alv = s_al[wib]; const real* gav = s_ga[wib];
+        real prev = rwv[0];
+#pragma unroll 4
+        for (int kk = 1; kk < nl; kk++) {
+            prev = (rwv[kk] - av[kk] * prev) * alv[kk];
+            rwv[kk] = prev;
+        }
+        real next = rwv[nl];
+#pragma unroll 4
+        for (int kk = nl - 1; kk >= 0; kk--) {
+            next = rwv[kk] - gav[kk] * next;
+            rwv[kk] = next;
+        }
+    }
+    __syncwarp();
+    r2 r = *reinterpret_cast<const r2*>(&s_rw[wib][kc]);
+    {   // implicit Rayleigh damping on w, TI:2936-2942
+        const r2 dw = rw_save - rw_now;
+        const r2 rd = (r + dw - dts * dss *
+                       (fm * zz + fp * zzm)
+                       * (fm * rho + fp * up1(rho))
+                       * w_now) / (1.0 + dts * dss)
+                      - dw;
+        r = sel(k_mid, rd, r);
+        wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 + epssm) * r, wwAvg);
+    }
+    r = sel(k_le_nl, r, 0.0);
+    const r2 r1 = dn1(r);
+    ST(D.rtheta_pp_old, i, rtheta_pp);
+    ST(D.rw_p, i, r);
+    ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
+    ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
+    ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1
+                                                  - coftz * r), 0.0));
+}
+
+// ------------------------------------------------------------------ atm_set_smlstep_pert_variables_work  TI:2427-2508
+// zb_cell/zb3_cell are [cell][edge slot][LDK]; requires maxEdges >= CW_NE (slots beyond nEdgesOnCell exist and are skipped)
+#define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
+__global__ void __launch_bounds__(CW_THREADS) k2_smlstep_pert(const Dev D) {
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const r2 wt_in = LD(D.tend_w, i);
+    const r2 zz = LD(D.zz, i);
+    r2 wt = wt_in;
+    if (D.zb_any[i]) {
+#define SML_EDGE(E)                                                                                         \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E));                                                                \
+            const real sg = BC(my_sgn, (E));                                                                \
+            const r2 tu = LD(D.tend_u, iEdge);                                                              \
+            const r2 zb = LDZ(D.zb_cell, (E)), zb3 = LDZ(D.zb3_cell, (E));                                  \
+            const r2 flux = sg * (fm * tu + fp * up1(tu));                                                  \
+            const r2 szb3 = mk2(signbit(tu.x) ? -zb3.x : zb3.x, signbit(tu.y) ? -zb3.y : zb3.y);   /* sign(1,tend_u) * zb3 */ \
+            wt = selb((E) < ne, wt - (zb + szb3) * flux, wt);                                               \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) SML_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) SML_EDGE(e)
+#undef SML_EDGE
+    }
+    ST(D.tend_w, i, sel(lv.ge(1) && lv.lt(nl), (fm * zz + fp * up1(zz)) * wt, wt_in));
+}
+
+// ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
+__global__ void __launch_bounds__(CW_THREADS) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const r2 w_in = LD(D.w_2, i);
+    const r2 rho = LD(D.rho_zz_2, i);
+    const b2 k_eq0 = lv.eq(0);
+    r2 w = w_in;
+    if (D.zb_any[i]) {
+#define REC_EDGE(E)                                                                                         \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E));                                                                \
+            const real sg = BC(my_sgn, (E));                                                                \
+            const r2 ru = LD(D.ru, iEdge);                                                                  \
+            const r2 zb = LDZ(D.zb_cell, (E)), zb3 = LDZ(D.zb3_cell, (E));                                  \
+            const r2 flux = sel(k_eq0, cf1 * ru + cf2 * dn1(ru) + cf3 * dn2(ru), fm * ru + fp * up1(ru));   \
+            const r2 szb3 = mk2(signbit(flux.x) ? -zb3.x : zb3.x, signbit(flux.y) ? -zb3.y : zb3.y);        \
+            w = selb((E) < ne, w + sg * (zb + szb3) * flux, w);                                             \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) REC_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) REC_EDGE(e)
+#undef REC_EDGE
+    }
+    const r2 den = sel(k_eq0, cf1 * rho + cf2 * dn1(rho) + cf3 * dn2(rho), fm * rho + fp * up1(rho));
+    ST(D.w_2, i, sel(lv.lt(nl), w / den, w_in));
+}

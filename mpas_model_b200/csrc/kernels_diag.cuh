@@ -143,6 +143,16 @@ __global__ void k_initcd_cell2(const Dev D) {
 }
 
 // ------------------------------------------------------------------ element-wise helpers (atm_rk_dynamics_substep_finish TI:7121-7172)
+// zb_any(i) = any non-zero zb_cell / zb3_cell entry of cell i (derived once per upload of those fields)
+__global__ void k_zb_flags(const Dev D) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > (size_t)D.nCells) return;
+    const size_t n = (size_t)D.maxEdges * D.LDK;
+    const real* a = D.zb_cell + i * n; const real* b = D.zb3_cell + i * n;
+    int any = 0;
+    for (size_t j = 0; j < n; j++) any |= (a[j] != 0.0) | (b[j] != 0.0);
+    D.zb_any[i] = any;
+}
 __global__ void k_add_into(real* __restrict__ y, const real* __restrict__ x, size_t n) {       // y = x + y
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) y[t] = x[t] + y[t];

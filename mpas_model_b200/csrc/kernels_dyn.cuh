@@ -7,7 +7,8 @@
 
 #define KI const int k = threadIdx.x; const int i = blockIdx.x * blockDim.y + threadIdx.y; \
            const int LDK = D.LDK; const int nl = D.nl; (void)LDK; (void)nl;
-#define AT(p, i, k) (p)[(size_t)(i) * LDK + (k)]
+// 32-bit element offsets: a block holds < 2^32 reals per field, and unsigned wrap-around keeps k-1, k-2 exact
+#define AT(p, i, k) (p)[(unsigned)((unsigned)(i) * (unsigned)LDK + (unsigned)(k))]
 #define RP const real* __restrict__
 #define IP const int* __restrict__
 
@@ -470,7 +471,7 @@ __global__ void k_smlstep_pert(const Dev D) {
     const int ne = D.nEdgesOnCell[i];
     const real fm = D.fzm[k], fp = D.fzp[k];
     real wt = AT(D.tend_w, i, k);
-    for (int e = 0; e < ne; e++) {
+    if (D.zb_any[i]) for (int e = 0; e < ne; e++) {
         const int iEdge = D.edgesOnCell[(size_t)i * D.maxEdges + e];
         const real tuk = AT(D.tend_u, iEdge, k);
         const real flux = D.edgesOnCell_sign[(size_t)i * D.maxEdges + e] * (fm * tuk + fp * AT(D.tend_u, iEdge, k - 1));

@@ -19,6 +19,7 @@
 #include "kernels_acoustic.cuh"
 #include "kernels_diag.cuh"
 #include "kernels_transport.cuh"
+#include "kernels_col.cuh"
 #include "halo.cuh"
 
 enum { T_REAL = 0, T_INT = 1 };
@@ -44,6 +45,9 @@ struct mpasb_handle_s {
     std::string err;
     long launches = 0;
     int cpb = 4;
+    bool colwarp = false;          // LDK <= 64 and <= CW_MAXNE edges per cell: the column-warp kernels apply
+    int max_ne = 0;                // max(nEdgesOnCell), known once the mesh is uploaded
+    bool zb_dirty = true;          // zb_any must be recomputed before the next step
     bool profile = false;
     std::map<std::string, ProfRec> prof;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -124,7 +128,10 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
         set_dev_ptr(h, f);
     }
     h->staging_bytes = max_bytes;
-    if (cudaMalloc(&h->staging, max_bytes) != cudaSuccess || cudaMalloc(&h->d_minmax, 4 * sizeof(real)) != cudaSuccess) {
+    if (cudaMalloc(&h->staging, max_bytes) != cudaSuccess || cudaMalloc(&h->d_minmax, 4 * sizeof(real)) != cudaSuccess ||
+        cudaMalloc(&h->D.zb_any, ((size_t)dims->nCells + 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->D.adv_flux_w, h->D.edgePlane * sizeof(real)) != cudaSuccess ||
+        cudaMalloc(&h->D.adv_flux_theta, h->D.edgePlane * sizeof(real)) != cudaSuccess) {
         mpasb_destroy(h); return 8;
     }
     cudaStreamSynchronize(h->stream);
@@ -151,6 +158,9 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(f.d[l]);
     if (h->staging) cudaFree(h->staging);
     if (h->d_minmax) cudaFree(h->d_minmax);
+    if (h->D.zb_any) cudaFree(h->D.zb_any);
+    if (h->D.adv_flux_w) cudaFree(h->D.adv_flux_w);
+    if (h->D.adv_flux_theta) cudaFree(h->D.adv_flux_theta);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : {h->kev0, h->kev1, h->tev0, h->tev1}) if (e) cudaEventDestroy(e);
@@ -161,6 +171,9 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
 
 extern "C" const char* mpasb_last_error(mpasb_handle h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" long mpasb_kernel_launch_count(mpasb_handle h) { return h->launches; }
+// 1: every kernel keeps the reference's operation order and is built without FMA contraction, so results are
+// bit-identical to the fp64 CPU arithmetic (the only build at present; a relaxed build would return 0)
+extern "C" int mpasb_strict_arithmetic(void) { return 1; }
 extern "C" int mpasb_synchronize(mpasb_handle h) { cudaSetDevice(h->device); CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
 
 static FieldRec* find_field(H* h, const char* name) {
@@ -182,6 +195,7 @@ extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level,
     const int LDK = h->D.LDK;
     const size_t o = outer_of(h, f->loc);
     const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
+    if (f->inner == IN_NL1_ME) h->zb_dirty = true;
     if (!padded) { CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(real), cudaMemcpyHostToDevice, h->stream)); }
     else {
         real* st = (real*)h->staging;
@@ -225,6 +239,11 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
     FieldRec* f = find_field(h, name); if (!f) return 1;
     if (f->type != T_INT || count != f->host_count) { h->err = std::string("bad set_field_int ") + name; return 2; }
     int* st = (int*)h->staging;
+    if (!strcmp(name, "nEdgesOnCell")) {
+        h->max_ne = 0;
+        for (long n = 0; n < count; n++) h->max_ne = std::max(h->max_ne, src[n]);
+        h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS");
+    }
     CUDA_OK(cudaMemcpyAsync(st, src, count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     k_int_to_zero_based<<<nblk(count), 256, 0, h->stream>>>((int*)f->d[0], st, (size_t)count, f->target == TG_NONE ? 0 : 1);
     h->launches++;
@@ -263,6 +282,7 @@ struct KScope {
     }
 };
 #define LAUNCH(kern, n, smem, ...) do { KScope ks_(h, "k:" #kern); kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<(unsigned)(((n) + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -321,7 +341,8 @@ static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
     const Dev& D = h->D;
     const DynTendArgs A = dyn_tend_args(h, rk_step, dt);
     LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
-    LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
+    if (h->colwarp && !A.rayleigh_damp_u) LAUNCHW(k2_dt_edge_b, D.nEdges, D, A);
+    else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
         if (A.h_mom_eddy_visc4 > 0.0) {
             LAUNCH(k_dt_delsq_vertex, D.nVertices, 0, D);
@@ -330,11 +351,22 @@ static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
         LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
         LAUNCH(k_dt_cell_e, D.nCells, 0, D, A);
     }
-    LAUNCH(k_dt_cell_f, D.nCellsSolve, 0, D, A);
+    if (h->colwarp && !(A.v_mom_eddy_visc2 > 0.0) && !(A.v_theta_eddy_visc2 > 0.0)) {
+        LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
+        LAUNCHW(k2_dt_cell_f, D.nCellsSolve, D, A);
+    }
+    else LAUNCH(k_dt_cell_f, D.nCellsSolve, 0, D, A);
+}
+static void refresh_zb_flags(H* h) {
+    if (!h->zb_dirty) return;
+    k_zb_flags<<<nblk((size_t)h->D.nCells + 1), 256, 0, h->stream>>>(h->D);
+    h->launches++; h->zb_dirty = false;
 }
 static void set_smlstep_pert_variables(H* h) {               // TI:2427-2508
     Scope sc(h, "small_step_prep");
-    LAUNCH(k_smlstep_pert, h->D.nCellsSolve, 0, h->D);
+    refresh_zb_flags(h);
+    if (h->colwarp) LAUNCHW(k2_smlstep_pert, h->D.nCellsSolve, h->D);
+    else LAUNCH(k_smlstep_pert, h->D.nCellsSolve, 0, h->D);
 }
 static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:2646-2984
     Scope sc(h, "atm_advance_acoustic_step");
@@ -343,6 +375,7 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
     const real c2 = cp * rcv;
     const real resm = (1.0 - epssm) / (1.0 + epssm);
     LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
+    if (h->colwarp) { LAUNCHW(k2_acoustic_cell, h->D.nCells, h->D, dts, small_step, epssm, resm); return; }
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
 }
@@ -357,9 +390,11 @@ static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {  
     const real rcv = rgas / (cp - rgas);
     const real p0 = 1.0e+05;
     const real invNs = 1 / (real)ns;
+    refresh_zb_flags(h);
     LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
     LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
-    LAUNCH(k_recover_cell2, h->D.nCells, 0, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
+    if (h->colwarp) LAUNCHW(k2_recover_cell2, h->D.nCells, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
+    else LAUNCH(k_recover_cell2, h->D.nCells, 0, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
 }
 static void compute_solve_diagnostics(H* h, real dt, int time_lev, int rk_step) {  // TI:6337-6773
     Scope sc(h, "atm_compute_solve_diagnostics");

@@ -27,6 +27,11 @@ struct Dev {
     int maxEdges, maxEdges2, num_scalars;
     int index_qv, moist_start, moist_end;      // 0-based
     size_t cellPlane, edgePlane;               // (n+1)*LDK, stride between scalar planes
+    // derived, library-internal: 1 where any zb_cell/zb3_cell entry of the cell is non-zero (terrain slope);
+    // cells with 0 skip the 2 x maxEdges x nVertLevels metric reads of TI:2480-2500 and TI:3379-3414
+    int* zb_any;
+    // per-edge 3rd/4th-order advective fluxes of w and theta_m (kernels_col.cuh: k2_dt_edge_flux -> k2_dt_cell_f)
+    real* adv_flux_w; real* adv_flux_theta;
 };
 #undef F
 #undef FIELD_REAL

@@ -24,7 +24,7 @@ import numpy as np
 from .fields import FIELDS, host_shape
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpasb.so")
+LIB_PATH = os.environ.get("MPASB_LIB") or os.path.join(_HERE, "csrc", "libmpasb.so")
 
 
 class Dims(C.Structure):
@@ -238,6 +238,10 @@ class Dycore(Backend):
         ms = C.c_double()
         self._check(self.lib.mpasb_timer_stop(self._h, C.byref(ms)), "timer_stop")
         return ms.value
+
+    def strict_arithmetic(self) -> bool:
+        """True if the library keeps the reference's operation order everywhere (bit-exact build)."""
+        return bool(self.lib.mpasb_strict_arithmetic())
 
     def kernel_launch_count(self):
         return int(self.lib.mpasb_kernel_launch_count(self._h))

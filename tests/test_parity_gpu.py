@@ -13,7 +13,8 @@ from tests.util import STATE, compare_all, rel_l2, srk3_stepwise, sync_all
 pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-11          # north star, one RK3 step
-TOL_ROUTINE = 1e-13       # a single routine on identical inputs
+TOL_ROUTINE = 1e-13       # a single routine on identical inputs (pow() in the strict build)
+TOL_ROUTINE_FAST = 5e-12  # fast build: FMA / re-associated stencil sums, incl. cancellation in the tendencies
 
 
 @pytest.fixture(scope="module")
@@ -68,7 +69,9 @@ def test_every_routine_in_sequence(pair):
         worst = max(diffs.items(), key=lambda kv: kv[1])
         report.append((label, worst))
         uses_pow = label.startswith("recover_large_step_variables") and label.endswith("3)")
-        if uses_pow:
+        if not g.strict_arithmetic():
+            assert worst[1] <= TOL_ROUTINE_FAST, (label, worst)
+        elif uses_pow:
             assert worst[1] <= TOL_ROUTINE, (label, worst)
         else:
             assert worst[1] == 0.0, (label, worst)          # bit for bit
@@ -76,7 +79,9 @@ def test_every_routine_in_sequence(pair):
 
     srk3_stepwise([o, g], cfg, cfg["config_dt"], after)
     exact = sum(1 for _, w in report if w[1] == 0.0)
-    print(f"routines bit-exact: {exact}/{len(report)}; worst {max(report, key=lambda r: r[1][1])}")
+    print(f"strict={g.strict_arithmetic()} routines bit-exact: {exact}/{len(report)}; worst {max(report, key=lambda r: r[1][1])}")
+    inexact = sorted({(lab.split("(")[0], w[0], float(f"{w[1]:.2e}")) for lab, w in report if w[1] > 0.0}, key=lambda t: -t[2])
+    print("inexact routines:", inexact[:12])
 
 
 def test_one_step(pair):
