@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
 
 // owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
 // Restrictions (the host falls back to k_dt_cell_f otherwise): v_mom_eddy_visc2 == v_theta_eddy_visc2 == 0.
-__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
+__global__ void __launch_bounds__(CW_THREADS, 3) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     // one edge of the cell per lane (lanes >= ne repeat the last edge): id, sign, mixing metadata
@@ -171,15 +171,8 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_f(const Dev D, const Dy
     for (int e = 0; e < CW_NE; e++) CELL_F_EDGE(e)
     for (int e = CW_NE; e < ne; e++) CELL_F_EDGE(e)
 #undef CELL_F_EDGE
-    // own-column operands of the vertical terms: issued here so that they travel while the loops below run
-    const r2 rdzu = LD(D.rdzu, 0), rdzw = LD(D.rdzw, 0);
-    const r2 rw = LD(D.rw, i), w = LD(D.w_2, i), t = LD(D.theta_m_2, i), ts = LD(D.theta_m, i), rws = LD(D.rw_save, i);
-    const r2 rho = LD(D.rho_zz_2, i), tend_rho = LD(D.tend_rho, i), rtdiab = LD(D.rt_diabatic_tend, i);
-    const r2 trp = LD(D.tend_rtheta_physics, i);
     r2 twe = LD(D.tend_w_euler, i), tte = LD(D.tend_theta_euler, i);
     const r2 twe_in = twe;
-    r2 pp = mk2(0.0, 0.0), dpdz = mk2(0.0, 0.0), cqw = mk2(0.0, 0.0);
-    if (A.rk_step == 1) { pp = LD(D.pressure_p, i); dpdz = LD(D.dpdz, i); cqw = LD(D.cqw, i); }
     if (A.rk_step > 1) {          // perturbation flux for the rtheta_pp equation, TI:5995-6016
 #define CELL_F_PERT(E)                                                                                      \
         {                                                                                                   \
@@ -188,7 +181,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_f(const Dev D, const Dy
             const r2 flux = sg * dv * (LD(D.ru_save, iEdge) - LD(D.ru, iEdge)) * 0.5 * (LD(D.theta_m, cell2) + LD(D.theta_m, cell1)); \
             tt = selb((E) < ne, tt - flux, tt);                                                             \
         }
-#pragma unroll
+#pragma unroll 3
         for (int e = 0; e < CW_NE; e++) CELL_F_PERT(e)
         for (int e = CW_NE; e < ne; e++) CELL_F_PERT(e)
 #undef CELL_F_PERT
@@ -216,6 +209,14 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_f(const Dev D, const Dy
         }
 #undef CELL_F_DEL4
     }
+    // own-column operands of the vertical terms (loaded after the edge loops: keeps the kernel at <= 80
+    // registers, i.e. 24 resident warps per SM, which matters more here than one extra exposed latency)
+    const r2 rdzu = LD(D.rdzu, 0), rdzw = LD(D.rdzw, 0);
+    const r2 rw = LD(D.rw, i), w = LD(D.w_2, i), t = LD(D.theta_m_2, i), ts = LD(D.theta_m, i), rws = LD(D.rw_save, i);
+    const r2 rho = LD(D.rho_zz_2, i), tend_rho = LD(D.tend_rho, i), rtdiab = LD(D.rt_diabatic_tend, i);
+    const r2 trp = LD(D.tend_rtheta_physics, i);
+    r2 pp = mk2(0.0, 0.0), dpdz = mk2(0.0, 0.0), cqw = mk2(0.0, 0.0);
+    if (A.rk_step == 1) { pp = LD(D.pressure_p, i); dpdz = LD(D.dpdz, i); cqw = LD(D.cqw, i); }
     const r2 rwm1 = up1(rw);
     const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
     const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
@@ -492,4 +493,204 @@ __global__ void __launch_bounds__(CW_THREADS) k2_recover_cell2(const Dev D, real
     }
     const r2 den = sel(k_eq0, cf1 * rho + cf2 * dn1(rho) + cf3 * dn2(rho), fm * rho + fp * up1(rho));
     ST(D.w_2, i, sel(lv.lt(nl), w / den, w_in));
+}
+
+// ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
+// (1) vertex-all: vorticity (6452-6472), ke_vertex (6548-6561, ke_edge recomputed inline), pv_vertex (6647-6659)
+__global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const real* __restrict__ u) {
+    CW_SETUP(D.nVertices)
+    int my_e = 0; real my_s = 0.0, my_efac = 0.0;
+    {
+        const int l3 = min(lane, 2);
+        my_e = D.edgesOnVertex[3 * i + l3];
+        const real dc = D.dcEdge[my_e];
+        my_s = D.edgesOnVertex_sign[3 * i + l3] * dc;
+        my_efac = dc * D.dvEdge[my_e];
+    }
+    const r2 u0 = LD(u, BC(my_e, 0)), u1 = LD(u, BC(my_e, 1)), u2 = LD(u, BC(my_e, 2));
+    r2 vort = mk2(0.0, 0.0);
+    vort = vort + BC(my_s, 0) * u0;
+    vort = vort + BC(my_s, 1) * u1;
+    vort = vort + BC(my_s, 2) * u2;
+    const r2 ke0 = BC(my_efac, 0) * (u0 * u0), ke1 = BC(my_efac, 1) * (u1 * u1), ke2 = BC(my_efac, 2) * (u2 * u2);
+    const real iat = D.invAreaTriangle[i];
+    vort = vort * iat;
+    const b2 k_lt_nl = lv.lt(nl);
+    const real r = 0.25 * iat;
+    ST(D.vorticity, i, sel(k_lt_nl, vort, 0.0));
+    ST(D.ke_vertex, i, sel(k_lt_nl, (ke0 + ke1 + ke2) * r, 0.0));
+    ST(D.pv_vertex, i, sel(k_lt_nl, D.fVertex[i] + vort, 0.0));
+}
+// (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
+__global__ void __launch_bounds__(CW_THREADS) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const real r = D.invAreaCell[i];
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_dv = D.dvEdge[my_e];
+    const real my_s = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * my_dv;
+    const real my_efac = D.dcEdge[my_e] * my_dv;
+    const int my_v = D.verticesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_kite = D.kiteAreasOnVertex[3 * my_v + D.kiteForCell[(unsigned)i * D.maxEdges + le]];
+    r2 div = mk2(0.0, 0.0), ke = mk2(0.0, 0.0);
+#define DIAG_C_EDGE(E)                                                                                      \
+    {                                                                                                       \
+        const r2 uu = LD(u, BC(my_e, (E)));                                                                 \
+        div = selb((E) < ne, div + BC(my_s, (E)) * uu, div);                                                \
+        ke = selb((E) < ne, ke + 0.25 * (BC(my_efac, (E)) * (uu * uu)), ke);                                \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) DIAG_C_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) DIAG_C_EDGE(e)
+#undef DIAG_C_EDGE
+    ke = ke * r;
+    const real ke_fact = 1.0 - .375;
+    ke = ke_fact * ke;
+    r2 pvc = mk2(0.0, 0.0);
+#define DIAG_C_VTX(E)                                                                                       \
+    {                                                                                                       \
+        const int iVertex = BC(my_v, (E));                                                                  \
+        const real kite = BC(my_kite, (E));                                                                 \
+        const r2 kev = LD(D.ke_vertex, iVertex);                                                            \
+        ke = selb((E) < ne, ke + (1. - ke_fact) * kite * kev * r, ke);                                      \
+        if (apvm) pvc = selb((E) < ne, pvc + kite * LD(D.pv_vertex, iVertex) * r, pvc);                     \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) DIAG_C_VTX(e)
+    for (int e = CW_NE; e < ne; e++) DIAG_C_VTX(e)
+#undef DIAG_C_VTX
+    const b2 k_lt_nl = lv.lt(nl);
+    ST(D.divergence, i, sel(k_lt_nl, div * r, 0.0));
+    ST(D.ke, i, sel(k_lt_nl, ke, 0.0));
+    if (apvm) ST(D.pv_cell, i, sel(k_lt_nl, pvc, 0.0));
+}
+// (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
+__global__ void __launch_bounds__(CW_THREADS) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
+                                                           int reconstruct_v, int apvm, real apvm_dt) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
+    const b2 k_lt_nl = lv.lt(nl);
+    const r2 rho_edge = 0.5 * (LD(h, cell1) + LD(h, cell2));
+    const r2 pv1 = LD(D.pv_vertex, vertex1), pv2 = LD(D.pv_vertex, vertex2);
+    r2 vv;
+    if (reconstruct_v) {
+        vv = mk2(0.0, 0.0);
+        const int neoe = D.nEdgesOnEdge[i];
+        int my_eoe = 0; real my_woe = 0.0;
+        if (lane < neoe) { my_eoe = D.edgesOnEdge[(unsigned)i * D.maxEdges2 + lane]; my_woe = D.weightsOnEdge[(unsigned)i * D.maxEdges2 + lane]; }
+#pragma unroll 5
+        for (int j = 0; j < neoe; j++) vv = vv + BC(my_woe, j) * LD(u, BC(my_eoe, j));
+    } else {
+        vv = LD(D.v, i);
+    }
+    r2 pve = 0.5 * (pv1 + pv2);
+    r2 gt = mk2(0.0, 0.0), gn = mk2(0.0, 0.0);
+    if (apvm) {
+        const real r1 = 1.0 * D.invDvEdge[i];
+        const real r2_ = 1.0 * D.invDcEdge[i];
+        gt = (pv2 - pv1) * r1;
+        gn = (LD(D.pv_cell, cell2) - LD(D.pv_cell, cell1)) * r2_;
+        pve = pve - apvm_dt * (vv * gt + LD(u, i) * gn);
+    }
+    ST(D.rho_edge, i, sel(k_lt_nl, rho_edge, 0.0));
+    if (reconstruct_v) ST(D.v, i, sel(k_lt_nl, vv, 0.0));
+    if (apvm) { ST(D.gradPVt, i, sel(k_lt_nl, gt, 0.0)); ST(D.gradPVn, i, sel(k_lt_nl, gn, 0.0)); }
+    ST(D.pv_edge, i, sel(k_lt_nl, pve, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (a)
+// cell-all: Smagorinsky kdiff (rk 1, TI:5226-5296), h_divergence (5307-5338), tend_rho + dpdz (rk 1, 5345-5362).
+// Restriction (host falls back to k_dt_cell_a otherwise): config_mpas_cam_coef == 0.
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_es = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * D.dvEdge[my_e];
+    const b2 k_lt_nl = lv.lt(nl);
+    r2 kd = mk2(A.fixed_visc2, A.fixed_visc2);
+    if (A.rk_step == 1 && A.smag) {
+        const real my_da = D.defc_a[(unsigned)i * D.maxEdges + le], my_db = D.defc_b[(unsigned)i * D.maxEdges + le];
+        r2 d_diag = mk2(0.0, 0.0), d_off_diag = mk2(0.0, 0.0);
+#define CELL_A_DEF(E)                                                                                       \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E));                                                                \
+            const real da = BC(my_da, (E)), db = BC(my_db, (E));                                            \
+            const r2 uu = LD(D.u_2, iEdge), vv = LD(D.v, iEdge);                                            \
+            d_diag = selb((E) < ne, d_diag + da * uu - db * vv, d_diag);                                    \
+            d_off_diag = selb((E) < ne, d_off_diag + db * uu + da * vv, d_off_diag);                        \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) CELL_A_DEF(e)
+        for (int e = CW_NE; e < ne; e++) CELL_A_DEF(e)
+#undef CELL_A_DEF
+        const r2 dd = d_diag * d_diag + d_off_diag * d_off_diag;
+        kd = mk2(fmin(A.cs_len2 * sqrt(dd.x), A.kdiff_cap), fmin(A.cs_len2 * sqrt(dd.y), A.kdiff_cap));
+    }
+    r2 hd = mk2(0.0, 0.0);
+#define CELL_A_DIV(E) { const r2 ru = LD(D.ru, BC(my_e, (E))); hd = selb((E) < ne, hd + BC(my_es, (E)) * ru, hd); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) CELL_A_DIV(e)
+    for (int e = CW_NE; e < ne; e++) CELL_A_DIV(e)
+#undef CELL_A_DIV
+    hd = hd * D.invAreaCell[i];
+    if (A.rk_step == 1) {
+        const r2 rw = LD(D.rw, i), qt = LD(D.qtot, i);
+        const r2 tend_rho = -hd - LD(D.rdzw, 0) * (dn1(rw) - rw) + LD(D.tend_rho_physics, i);
+        const r2 dpdz = -GRAVITY * (LD(D.rho_base, i) * (qt) + LD(D.rho_p_save, i) * (1. + qt));
+        ST(D.kdiff, i, sel(k_lt_nl, kd, 0.0));
+        ST(D.tend_rho, i, sel(k_lt_nl, tend_rho, 0.0));
+        ST(D.dpdz, i, sel(k_lt_nl, dpdz, 0.0));
+    }
+    ST(D.h_divergence, i, sel(k_lt_nl, hd, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
+// rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    const real my_dv = D.dvEdge[my_e], my_idc = D.invDcEdge[my_e], my_msd2 = D.meshScalingDel2[my_e];
+    const real r_areaCell = D.invAreaCell[i];
+    r2 dsw = mk2(0.0, 0.0), twe = mk2(0.0, 0.0), dst = mk2(0.0, 0.0), tte = mk2(0.0, 0.0);
+#define CELL_E_EDGE(E)                                                                                      \
+    {                                                                                                       \
+        const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                    \
+        const real sg = BC(my_sgn, (E)), dv = BC(my_dv, (E)), idc = BC(my_idc, (E)), msd2 = BC(my_msd2, (E)); \
+        const r2 rho_e = LD(D.rho_edge, iEdge);                                                             \
+        const r2 kd1 = LD(D.kdiff, cell1), kd2 = LD(D.kdiff, cell2);                                        \
+        const r2 dw = LD(D.w_2, cell2) - LD(D.w_2, cell1);                                                  \
+        const r2 dth = LD(D.theta_m_2, cell2) - LD(D.theta_m_2, cell1);                                     \
+        {                                                                                                   \
+            const real edge_sign = 0.5 * r_areaCell * sg * dv * idc;                                        \
+            r2 w_turb_flux = edge_sign * (rho_e + up1(rho_e)) * dw;                                         \
+            dsw = selb((E) < ne, dsw + w_turb_flux, dsw);                                                   \
+            w_turb_flux = w_turb_flux * msd2 * 0.25 *                                                       \
+                          (kd1 + kd2 + up1(kd1) + up1(kd2));                                                \
+            twe = selb((E) < ne, twe + w_turb_flux, twe);                                                   \
+        }                                                                                                   \
+        {                                                                                                   \
+            const real edge_sign = r_areaCell * sg * dv * idc;                                              \
+            const real pr_scale = A.prandtl_inv * msd2;                                                     \
+            r2 theta_turb_flux = edge_sign * dth * rho_e;                                                   \
+            dst = selb((E) < ne, dst + theta_turb_flux, dst);                                               \
+            theta_turb_flux = theta_turb_flux * 0.5 * (kd1 + kd2) * pr_scale;                               \
+            tte = selb((E) < ne, tte + theta_turb_flux, tte);                                               \
+        }                                                                                                   \
+    }
+#pragma unroll 3
+    for (int e = 0; e < CW_NE; e++) CELL_E_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) CELL_E_EDGE(e)
+#undef CELL_E_EDGE
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
+    ST(D.delsq_w, i, sel(k_mid, dsw, 0.0));
+    ST(D.tend_w_euler, i, sel(k_mid, twe, 0.0));
+    ST(D.delsq_theta, i, sel(k_lt_nl, dst, 0.0));
+    ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
 }

@@ -340,7 +340,8 @@ static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
     Scope sc(h, "atm_compute_dyn_tend");
     const Dev& D = h->D;
     const DynTendArgs A = dyn_tend_args(h, rk_step, dt);
-    LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
+    if (h->colwarp && !(A.cam_coef > 0.0)) LAUNCHW(k2_dt_cell_a, D.nCells, D, A);
+    else LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
     if (h->colwarp && !A.rayleigh_damp_u) LAUNCHW(k2_dt_edge_b, D.nEdges, D, A);
     else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
@@ -349,7 +350,8 @@ static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
             LAUNCH(k_dt_delsq_cell, D.nCells, 0, D);
         }
         LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
-        LAUNCH(k_dt_cell_e, D.nCells, 0, D, A);
+        if (h->colwarp) LAUNCHW(k2_dt_cell_e, D.nCells, D, A);
+        else LAUNCH(k_dt_cell_e, D.nCells, 0, D, A);
     }
     if (h->colwarp && !(A.v_mom_eddy_visc2 > 0.0) && !(A.v_theta_eddy_visc2 > 0.0)) {
         LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
@@ -403,6 +405,12 @@ static void compute_solve_diagnostics(H* h, real dt, int time_lev, int rk_step) 
     const real* hh = time_lev == 2 ? D.rho_zz_2 : D.rho_zz;
     const int apvm = h->cfg.config_apvm_upwinding > 0.0;
     const int reconstruct_v = (rk_step == 0 || rk_step == 3);
+    if (h->colwarp) {
+        LAUNCHW(k2_diag_vertex, D.nVertices, D, u);
+        LAUNCHW(k2_diag_cell, D.nCells, D, u, apvm);
+        LAUNCHW(k2_diag_edge, D.nEdges, D, u, hh, reconstruct_v, apvm, h->cfg.config_apvm_upwinding * dt);
+        return;
+    }
     LAUNCH(k_diag_vertex, D.nVertices, 0, D, u);
     LAUNCH(k_diag_cell, D.nCells, 0, D, u, apvm);
     LAUNCH(k_diag_edge, D.nEdges, 0, D, u, hh, reconstruct_v, apvm, h->cfg.config_apvm_upwinding * dt);
