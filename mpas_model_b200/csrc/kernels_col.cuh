@@ -694,3 +694,154 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_e(const Dev D, const Dy
     ST(D.delsq_theta, i, sel(k_lt_nl, dst, 0.0));
     ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
 }
+
+// ------------------------------------------------------------------ atm_advance_acoustic_step_work, cell part (block-tiled)
+// TI:2824-2973.  A block owns AC3_COLS consecutive cells.  Phase 1: each warp assembles the right-hand sides of
+// AC3_COLS/CW_WARPS columns (one after the other) into shared memory.  Phase 2: ONE warp runs the tridiagonal
+// sweeps (TI:2922-2930) of all AC3_COLS columns at once, lane = column, rows padded to an odd stride so that the
+// lanes hit distinct banks -- the serial recurrence costs one warp-instruction per level for 32 columns instead of
+// one per column.  Phase 3: each warp finishes its columns (Rayleigh damping, wwAvg, rho_pp, rtheta_pp).
+// Operation order inside every column is the reference's: bit-identical results.
+#define AC3_COLS 32
+#define AC3_ARRAYS 6                    // rw (rhs / solution), a_tri, alpha_tri, gamma_tri, ts, rs
+__global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    extern __shared__ __align__(16) real sm3[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    const int S = LDK | 1;                                  // odd row stride (LDK is even)
+    real* s_rw = sm3;
+    real* s_a = s_rw + AC3_COLS * S;
+    real* s_al = s_a + AC3_COLS * S;
+    real* s_ga = s_al + AC3_COLS * S;
+    real* s_ts = s_ga + AC3_COLS * S;
+    real* s_rs = s_ts + AC3_COLS * S;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < LDK;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const bool first = small_step == 1;
+    const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
+    const int base = blockIdx.x * AC3_COLS;
+    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    // ---------------- phase 1: right-hand sides
+    for (int cc = 0; cc < AC3_COLS / CW_WARPS; cc++) {
+        const int c = cc * CW_WARPS + wib;
+        const int i = base + c;
+        if (i >= D.nCellsSolve) continue;                   // warp-uniform
+        const int ne = D.nEdgesOnCell[i];
+        const real invArea = D.invAreaCell[i];
+        const int le = min(lane, ne - 1);
+        const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+        const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+        const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
+        r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0);
+        if (!first) {
+            rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
+            rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
+            rho_pp = sel(k_lt_nl, LD(D.rho_pp, i), 0.0);
+        }
+        const r2 tend_rho = LD(D.tend_rho, i), tend_theta = LD(D.tend_theta, i), tend_w = LD(D.tend_w, i);
+        const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
+        const r2 zz = LD(D.zz, i);
+        const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
+        r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
+#define AC_EDGE(E)                                                                                          \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                \
+            const r2 flux = BC(my_f, (E)) * LD(D.ru_p, iEdge) * invArea;                                    \
+            const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                      \
+            rs = selb((E) < ne, rs - flux, rs);                                                             \
+            ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                  \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) AC_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) AC_EDGE(e)
+#undef AC_EDGE
+        const r2 rw_p1 = dn1(rw_p);
+        const r2 coftz1 = dn1(coftz);
+        rs = rho_pp + dts * tend_rho + rs
+             - cofrz * resm * (rw_p1 - rw_p);
+        ts = rtheta_pp + dts * tend_theta + ts
+             - resm * rdzw * (coftz1 * rw_p1
+                              - coftz * rw_p);
+        rs = sel(k_lt_nl, rs, 0.0); ts = sel(k_lt_nl, ts, 0.0);
+        const r2 zzm = up1(zz);
+        const r2 tsm = up1(ts), rsm = up1(rs), rtm = up1(rtheta_pp), rhm = up1(rho_pp), cofwtm = up1(cofwt);
+        const r2 r = rw_p + dts * tend_w
+                     - cofwz * ((zz * ts
+                                 - zzm * tsm)
+                                + resm * (zz * rtheta_pp
+                                          - zzm * rtm))
+                     - cofwr * ((rs + rsm)
+                                + resm * (rho_pp + rhm))
+                     + cofwt * (ts + resm * rtheta_pp)
+                     + cofwtm * (tsm + resm * rtm);
+        const r2 rhs = sel(k_mid, r, rw_p);
+        if (act) {
+            const int o = c * S + k0;
+            s_rw[o] = rhs.x; s_rw[o + 1] = rhs.y; s_a[o] = a_tri.x; s_a[o + 1] = a_tri.y;
+            s_al[o] = al_tri.x; s_al[o + 1] = al_tri.y; s_ga[o] = ga_tri.x; s_ga[o + 1] = ga_tri.y;
+            s_ts[o] = ts.x; s_ts[o + 1] = ts.y; s_rs[o] = rs.x; s_rs[o + 1] = rs.y;
+        }
+    }
+    __syncthreads();
+    // ---------------- phase 2: all columns of the block swept by one warp, lane = column
+    if (wib == 0 && base + lane < D.nCellsSolve) {
+        real* rwv = s_rw + lane * S;
+        const real* av = s_a + lane * S; const real* alv = s_al + lane * S; const real* gav = s_ga + lane * S;
+        real prev = rwv[0];
+#pragma unroll 4
+        for (int kk = 1; kk < nl; kk++) {
+            prev = (rwv[kk] - av[kk] * prev) * alv[kk];
+            rwv[kk] = prev;
+        }
+        real next = rwv[nl];
+#pragma unroll 4
+        for (int kk = nl - 1; kk >= 0; kk--) {
+            next = rwv[kk] - gav[kk] * next;
+            rwv[kk] = next;
+        }
+    }
+    __syncthreads();
+    // ---------------- phase 3: damping, averages, back-substitution of rho_pp and rtheta_pp
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    for (int cc = 0; cc < AC3_COLS / CW_WARPS; cc++) {
+        const int c = cc * CW_WARPS + wib;
+        const int i = base + c;
+        if (i >= D.nCells) continue;
+        // old values of the perturbation variables (zero on the first small step, TI:2850-2860)
+        r2 rtheta_pp_old = mk2(0.0, 0.0);
+        if (!first) rtheta_pp_old = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
+        if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp_old); continue; }
+        r2 rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
+        if (!first) {
+            rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
+            wwAvg = sel(k_le_nl, LD(D.wwAvg, i), 0.0);
+        }
+        const r2 coftz = LD(D.coftz, i), zz = LD(D.zz, i);
+        const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
+        const int o = c * S + (int)kc;
+        r2 r = mk2(s_rw[o], s_rw[o + 1]);
+        const r2 ts = mk2(s_ts[o], s_ts[o + 1]), rs = mk2(s_rs[o], s_rs[o + 1]);
+        wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 - epssm) * rw_p, wwAvg);
+        const r2 zzm = up1(zz);
+        const r2 coftz1 = dn1(coftz);
+        {   // implicit Rayleigh damping on w, TI:2936-2942
+            const r2 dw = rw_save - rw_now;
+            const r2 rd = (r + dw - dts * dss *
+                           (fm * zz + fp * zzm)
+                           * (fm * rho + fp * up1(rho))
+                           * w_now) / (1.0 + dts * dss)
+                          - dw;
+            r = sel(k_mid, rd, r);
+            wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 + epssm) * r, wwAvg);
+        }
+        r = sel(k_le_nl, r, 0.0);
+        const r2 r1 = dn1(r);
+        ST(D.rtheta_pp_old, i, rtheta_pp_old);
+        ST(D.rw_p, i, r);
+        ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
+        ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
+        ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1
+                                                      - coftz * r), 0.0));
+    }
+}

@@ -377,6 +377,15 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
     const real c2 = cp * rcv;
     const real resm = (1.0 - epssm) / (1.0 + epssm);
     LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
+    if (h->colwarp && !getenv("MPASB_ACOUSTIC_V2")) {
+        const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        KScope ks_(h, "k:k3_acoustic_cell");
+        k3_acoustic_cell<<<(unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS), CW_THREADS, smem3, h->stream>>>(h->D, dts, small_step, epssm, resm);
+        h->launches++;
+        return;
+    }
     if (h->colwarp) { LAUNCHW(k2_acoustic_cell, h->D.nCells, h->D, dts, small_step, epssm, resm); return; }
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
