@@ -83,10 +83,19 @@ def measured_peak_gbs():
 # algorithmic bytes per launch of the kernels worth a roofline line, in units of
 # C = nVertLevels * nCells * 8 B (SURVEY.md §8a per-routine model; DESIGN.md §4 per kernel)
 KERNEL_MODEL_C = {
-    "k:k_acoustic_cell": 29.0,       # 1 E + 21 C read, 5 C written (non-first small step)
-    "k:k_dt_cell_f": 22.0,           # w, theta_m (+save), ru/ru_save (E), rw(+save), rho_zz, tendencies
-    "k:k_dt_edge_b": 24.0,
-    "k:k_recover_cell2": 19.0,       # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
+    # acoustic cell solve: 1 E (ru_p or tend_u) + 21 C read, 5 C written on a later small step (29 C); the first
+    # small step of a stage does not read rho_pp, rtheta_pp, rw_p, wwAvg (25 C); 9 first + 3 later per step
+    "k:k3_acoustic_cell": (9 * 25.0 + 3 * 29.0) / 12,
+    "k:k2_acoustic_cell": (9 * 25.0 + 3 * 29.0) / 12,
+    "k:k_acoustic_cell": 29.0,
+    # edge tendency: rk 1 reads 5 E + 8 C + 1 V and writes 3 E (34 C); rk 2,3 read 5 E + 3 C, write 1 E (21 C)
+    "k:k2_dt_edge_b": (3 * 34.0 + 6 * 21.0) / 9,
+    "k:k_dt_edge_b": (3 * 34.0 + 6 * 21.0) / 9,
+    # cell tendency after the per-edge flux split: 2 E fluxes + ru, ru_save (rk > 1) + 13 C read, 3-5 C written
+    "k:k2_dt_cell_f": 24.0,
+    "k:k_dt_cell_f": 22.0,
+    "k:k2_dt_edge_flux": 11.0,       # ru (E), w, theta_m read; 2 E written
+    "k:k2_recover_cell2": 19.0,      # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/), x1.40962 x 55 levels; None = not captured for the current kernel version

@@ -704,7 +704,10 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_e(const Dev D, const Dy
 // Operation order inside every column is the reference's: bit-identical results.
 #define AC3_COLS 32
 #define AC3_ARRAYS 6                    // rw (rhs / solution), a_tri, alpha_tri, gamma_tri, ts, rs
-__global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+#ifndef AC3_WARPS
+#define AC3_WARPS 8                     // warps per block: AC3_COLS / AC3_WARPS columns per warp (8 measured faster than 16)
+#endif
+__global__ void __launch_bounds__(AC3_WARPS * 32, 2) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
     extern __shared__ __align__(16) real sm3[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
@@ -723,8 +726,8 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, r
     const int base = blockIdx.x * AC3_COLS;
     const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
     // ---------------- phase 1: right-hand sides
-    for (int cc = 0; cc < AC3_COLS / CW_WARPS; cc++) {
-        const int c = cc * CW_WARPS + wib;
+    for (int cc = 0; cc < AC3_COLS / AC3_WARPS; cc++) {
+        const int c = cc * AC3_WARPS + wib;
         const int i = base + c;
         if (i >= D.nCellsSolve) continue;                   // warp-uniform
         const int ne = D.nEdgesOnCell[i];
@@ -747,7 +750,8 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, r
 #define AC_EDGE(E)                                                                                          \
         {                                                                                                   \
             const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                \
-            const r2 flux = BC(my_f, (E)) * LD(D.ru_p, iEdge) * invArea;                                    \
+            const r2 ru_p = first ? dts * LD(D.tend_u, iEdge) : LD(D.ru_p, iEdge);   /* TI:2798-2806 */     \
+            const r2 flux = BC(my_f, (E)) * ru_p * invArea;                                                 \
             const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                      \
             rs = selb((E) < ne, rs - flux, rs);                                                             \
             ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                  \
@@ -804,8 +808,8 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, r
     __syncthreads();
     // ---------------- phase 3: damping, averages, back-substitution of rho_pp and rtheta_pp
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
-    for (int cc = 0; cc < AC3_COLS / CW_WARPS; cc++) {
-        const int c = cc * CW_WARPS + wib;
+    for (int cc = 0; cc < AC3_COLS / AC3_WARPS; cc++) {
+        const int c = cc * AC3_WARPS + wib;
         const int i = base + c;
         if (i >= D.nCells) continue;
         // old values of the perturbation variables (zero on the first small step, TI:2850-2860)
@@ -844,4 +848,23 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k3_acoustic_cell(const Dev D, r
         ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1
                                                       - coftz * r), 0.0));
     }
+}
+
+// ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075
+// first != 0: also performs the first-small-step edge update of atm_advance_acoustic_step_work (TI:2798-2806:
+// ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
+__global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    const real mask = 1.0 - D.specZoneMaskEdge[i];
+    const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
+    const r2 divCell2 = -(LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp_old, cell2));
+    const r2 th = LD(D.theta_m, cell1) + LD(D.theta_m, cell2);
+    r2 ru_p;
+    if (first) ru_p = dts * LD(D.tend_u, i);
+    else ru_p = LD(D.ru_p, i);
+    const b2 k_lt_nl = lv.lt(nl);
+    if (first) ST(D.ruAvg, i, sel(k_lt_nl, ru_p, 0.0));
+    ST(D.ru_p, i, sel(k_lt_nl, ru_p + coef_divdamp * (divCell2 - divCell1) * mask / th, 0.0));
 }

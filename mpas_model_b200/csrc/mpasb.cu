@@ -48,6 +48,7 @@ struct mpasb_handle_s {
     bool colwarp = false;          // LDK <= 64 and <= CW_MAXNE edges per cell: the column-warp kernels apply
     int max_ne = 0;                // max(nEdgesOnCell), known once the mesh is uploaded
     bool zb_dirty = true;          // zb_any must be recomputed before the next step
+    bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool profile = false;
     std::map<std::string, ProfRec> prof;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -376,17 +377,20 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
     const real rcv = rgas / (cp - rgas);
     const real c2 = cp * rcv;
     const real resm = (1.0 - epssm) / (1.0 + epssm);
-    LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
-    if (h->colwarp && !getenv("MPASB_ACOUSTIC_V2")) {
+    if (h->colwarp) {
+        // first small step: ru_p = dts * tend_u is evaluated on the fly by the cell kernel and written by the
+        // following divergence-damping kernel (h->ru_p_pending), saving one pass over three edge arrays
+        if (small_step == 1) h->ru_p_pending = true;
+        else LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         KScope ks_(h, "k:k3_acoustic_cell");
-        k3_acoustic_cell<<<(unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS), CW_THREADS, smem3, h->stream>>>(h->D, dts, small_step, epssm, resm);
+        k3_acoustic_cell<<<(unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS), AC3_WARPS * 32, smem3, h->stream>>>(h->D, dts, small_step, epssm, resm);
         h->launches++;
         return;
     }
-    if (h->colwarp) { LAUNCHW(k2_acoustic_cell, h->D.nCells, h->D, dts, small_step, epssm, resm); return; }
+    LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
 }
@@ -394,6 +398,11 @@ static void divergence_damping_3d(H* h, real dts) {           // TI:2987-3075
     Scope sc(h, "atm_divergence_damping_3d");
     const real rdts = 1.0 / dts;
     const real coef_divdamp = 2.0 * h->cfg.config_smdiv * h->cfg.config_len_disp * rdts;
+    if (h->colwarp) {
+        LAUNCHW(k2_divergence_damping, h->D.nEdges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts);
+        h->ru_p_pending = false;
+        return;
+    }
     LAUNCH(k_divergence_damping, h->D.nEdges, 0, h->D, coef_divdamp);
 }
 static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {    // TI:3189-3431
@@ -620,7 +629,12 @@ extern "C" int mpasb_k_compute_moist_coefficients(mpasb_handle h) ENTRY(compute_
 extern "C" int mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts) ENTRY(compute_vert_imp_coefs(h, dts))
 extern "C" int mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt) ENTRY(compute_dyn_tend(h, rk_step, dt))
 extern "C" int mpasb_k_set_smlstep_pert_variables(mpasb_handle h) ENTRY(set_smlstep_pert_variables(h))
-extern "C" int mpasb_k_advance_acoustic_step(mpasb_handle h, mpasb_real dts, int small_step) ENTRY(advance_acoustic_step(h, dts, small_step))
+// called on its own the routine must leave ru_p/ruAvg as the reference does: materialise the deferred edge update
+static void advance_acoustic_step_standalone(H* h, real dts, int small_step) {
+    advance_acoustic_step(h, dts, small_step);
+    if (h->ru_p_pending) { LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, 1, (real)0); h->ru_p_pending = false; }
+}
+extern "C" int mpasb_k_advance_acoustic_step(mpasb_handle h, mpasb_real dts, int small_step) ENTRY(advance_acoustic_step_standalone(h, dts, small_step))
 extern "C" int mpasb_k_divergence_damping_3d(mpasb_handle h, mpasb_real dts) ENTRY(divergence_damping_3d(h, dts))
 extern "C" int mpasb_k_recover_large_step_variables(mpasb_handle h, mpasb_real dt, int ns, int rk_step) ENTRY(recover_large_step_variables(h, dt, ns, rk_step))
 extern "C" int mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(compute_solve_diagnostics(h, dt, 2, rk_step))
