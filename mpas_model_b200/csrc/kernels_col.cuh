@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
 
 // owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
 // Restrictions (the host falls back to k_dt_cell_f otherwise): v_mom_eddy_visc2 == v_theta_eddy_visc2 == 0.
-__global__ void __launch_bounds__(CW_THREADS, 3) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
+#ifndef CELLF_MINB
+#define CELLF_MINB 3
+#endif
+__global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     // one edge of the cell per lane (lanes >= ne repeat the last edge): id, sign, mixing metadata
@@ -702,12 +705,17 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_e(const Dev D, const Dy
 // lanes hit distinct banks -- the serial recurrence costs one warp-instruction per level for 32 columns instead of
 // one per column.  Phase 3: each warp finishes its columns (Rayleigh damping, wwAvg, rho_pp, rtheta_pp).
 // Operation order inside every column is the reference's: bit-identical results.
-#define AC3_COLS 32
+#ifndef AC3_COLS
+#define AC3_COLS 32                     // columns per block = lanes of the sweeping warp
+#endif
+#ifndef AC3_MINB
+#define AC3_MINB 2
+#endif
 #define AC3_ARRAYS 6                    // rw (rhs / solution), a_tri, alpha_tri, gamma_tri, ts, rs
 #ifndef AC3_WARPS
 #define AC3_WARPS 8                     // warps per block: AC3_COLS / AC3_WARPS columns per warp (8 measured faster than 16)
 #endif
-__global__ void __launch_bounds__(AC3_WARPS * 32, 2) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+__global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
     extern __shared__ __align__(16) real sm3[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
@@ -789,7 +797,7 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, 2) k3_acoustic_cell(const Dev 
     }
     __syncthreads();
     // ---------------- phase 2: all columns of the block swept by one warp, lane = column
-    if (wib == 0 && base + lane < D.nCellsSolve) {
+    if (wib == 0 && lane < AC3_COLS && base + lane < D.nCellsSolve) {
         real* rwv = s_rw + lane * S;
         const real* av = s_a + lane * S; const real* alv = s_al + lane * S; const real* gav = s_ga + lane * S;
         real prev = rwv[0];

@@ -70,7 +70,15 @@ def prepare_blocks(n_cells, n_levels, num_scalars, world, tag=""):
     prefix = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.part.{world}{tag}")
     if all(os.path.exists(f"{prefix}.{r}.pkl") for r in range(world)):
         return prefix
-    d, cfg = make_case(n_cells, n_levels, num_scalars=num_scalars)
+    gpath = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.global.pkl")
+    if os.path.exists(gpath):                                   # the global case is shared by every partition count
+        with open(gpath, "rb") as f:
+            d, cfg = pickle.load(f)
+    else:
+        d, cfg = make_case(n_cells, n_levels, num_scalars=num_scalars)
+        with open(gpath + ".tmp", "wb") as f:
+            pickle.dump((d, cfg), f, protocol=4)
+        os.replace(gpath + ".tmp", gpath)
     part = decomp.partition_rcb(d, world)
     decomp.write_partition_file(prefix, part)               # the reference's "<prefix><N>" partition file format
     blocks, ex = decomp.decompose_case(d, cfg, part)

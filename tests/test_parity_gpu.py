@@ -133,3 +133,21 @@ def test_ten_steps_and_invariants(pair):
     q = g.get_array("scalars", 1)[:nC]
     q0 = d["scalars"][:nC]
     assert q.min() >= 0.0 and q[..., 1].max() <= q0[..., 1].max() * (1 + 1e-12)   # monotone transport
+
+
+def test_one_simulated_day(pair):
+    """North-star bar: relative L2 <= 1e-6 on u, w, rho_zz, theta_m, scalars after one simulated day
+    (x1.2562: dt = 2874 s, 30 steps = 23.95 h, then one more step to pass 24 h)."""
+    d, cfg, o, g = pair
+    o.load_block(d); g.load_block(d)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    n_steps = int(np.ceil(86400.0 / dt))
+    for _ in range(n_steps):
+        o.atm_srk3(dt); g.atm_srk3(dt)
+        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+    worst = {}
+    for name in STATE:
+        worst[name] = rel_l2(g.get_array(name, 1), o.get_array(name, 1))
+        assert worst[name] <= 1e-6, (name, worst[name])
+    print(f"one simulated day ({n_steps} steps of {dt:g} s): rel-L2 vs oracle {worst}")
