@@ -100,6 +100,9 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
 #define LD(p, col) ld2((p), (unsigned)(col) * uLDK + kc)
 #define ST(p, col, v) st2((p), (unsigned)(col) * uLDK + kc, act, (v))
 #define BC(v, src) __shfl_sync(CW_FULL, (v), (src))
+// request a column pair into L2 without holding registers: used for operands of a later, dependent phase
+__device__ __forceinline__ void pf2(const real* p, unsigned off) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p + off)); }
+#define PF(p, col) pf2((p), (unsigned)(col) * uLDK + kc)
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f)
 // The reference computes the 3rd/4th-order horizontal flux of w and theta_m inside the cell loop, i.e. every
@@ -733,17 +736,31 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
     const int base = blockIdx.x * AC3_COLS;
     const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    // connectivity of ALL columns of this warp in one pass: lane = (column slot << 3) | edge slot, so the two
+    // dependent index loads (edgesOnCell -> cellsOnEdge/dvEdge) are exposed once per warp, not once per column
+    static_assert(AC3_COLS / AC3_WARPS <= 4 && CW_MAXNE <= 8, "one lane per (column, edge slot)");
+    int m_ne = 1, m_e = 0, m_c1 = 0, m_c2 = 0; real m_f = 0.0, m_invArea = 0.0;
+    {
+        const int mi = base + (lane >> 3) * AC3_WARPS + wib;
+        if ((lane >> 3) < AC3_COLS / AC3_WARPS && mi < D.nCellsSolve) {
+            m_ne = D.nEdgesOnCell[mi];
+            m_invArea = D.invAreaCell[mi];
+            const int le = min(lane & 7, m_ne - 1);
+            m_e = D.edgesOnCell[(unsigned)mi * D.maxEdges + le];
+            m_c1 = D.cellsOnEdge[2 * m_e]; m_c2 = D.cellsOnEdge[2 * m_e + 1];
+            m_f = D.edgesOnCell_sign[(unsigned)mi * D.maxEdges + le] * dts * D.dvEdge[m_e];
+        }
+    }
     // ---------------- phase 1: right-hand sides
     for (int cc = 0; cc < AC3_COLS / AC3_WARPS; cc++) {
         const int c = cc * AC3_WARPS + wib;
         const int i = base + c;
         if (i >= D.nCellsSolve) continue;                   // warp-uniform
-        const int ne = D.nEdgesOnCell[i];
-        const real invArea = D.invAreaCell[i];
-        const int le = min(lane, ne - 1);
-        const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
-        const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
-        const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
+        const int ne = BC(m_ne, cc << 3);
+        const real invArea = BC(m_invArea, cc << 3);
+        // operands of phase 3 (after the solve): start them towards L2 now
+        PF(D.dss, i); PF(D.rw_save, i); PF(D.rw, i); PF(D.rho_zz_2, i); PF(D.w_2, i);
+        if (!first) PF(D.wwAvg, i);
         r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0);
         if (!first) {
             rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
@@ -757,9 +774,10 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
         r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
 #define AC_EDGE(E)                                                                                          \
         {                                                                                                   \
-            const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                \
+            const int src = (cc << 3) + (E);                                                                \
+            const int iEdge = BC(m_e, src), cell1 = BC(m_c1, src), cell2 = BC(m_c2, src);                   \
             const r2 ru_p = first ? dts * LD(D.tend_u, iEdge) : LD(D.ru_p, iEdge);   /* TI:2798-2806 */     \
-            const r2 flux = BC(my_f, (E)) * ru_p * invArea;                                                 \
+            const r2 flux = BC(m_f, src) * ru_p * invArea;                                                  \
             const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                      \
             rs = selb((E) < ne, rs - flux, rs);                                                             \
             ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                  \
@@ -875,4 +893,143 @@ __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D,
     const b2 k_lt_nl = lv.lt(nl);
     if (first) ST(D.ruAvg, i, sel(k_lt_nl, ru_p, 0.0));
     ST(D.ru_p, i, sel(k_lt_nl, ru_p + coef_divdamp * (divCell2 - divCell1) * mask / th, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_recover_large_step_variables_work, parts 1 and 2
+// (1) cell-all, TI:3294-3350 (+ the garbage cell, TI:3282-3284)
+__global__ void __launch_bounds__(CW_THREADS) k2_recover_cell1(const Dev D, real dt, real invNs, int rk_step, real rcv, real rgas_p0) {
+    CW_SETUP(D.nCells + 1)
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
+    if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); return; }
+    const r2 rho_p = LD(D.rho_p_save, i) + LD(D.rho_pp, i);
+    const r2 rho_zz = rho_p + LD(D.rho_base, i);
+    const r2 rtb = LD(D.rtheta_base, i);
+    const r2 zz = LD(D.zz, i);
+    const r2 rw_save = LD(D.rw_save, i);
+    const r2 wwAvg_in = LD(D.wwAvg, i), rw_in = LD(D.rw, i), w_in = LD(D.w_2, i);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    r2 rtheta_p;
+    if (rk_step == 3) {
+        rtheta_p = LD(D.rtheta_p_save, i) + LD(D.rtheta_pp, i)
+                   - dt * rho_zz * LD(D.rt_diabatic_tend, i);
+        const r2 arg = zz * (rgas_p0) * (rtheta_p + rtb);
+        const r2 ex = mk2(pow(arg.x, rcv), pow(arg.y, rcv));
+        ST(D.exner, i, sel(k_lt_nl, ex, 0.0));
+        ST(D.pressure_p, i, sel(k_lt_nl, zz * RGAS * (ex * rtheta_p + rtb
+                                                       * (ex - LD(D.exner_base, i))), 0.0));
+    } else {
+        rtheta_p = LD(D.rtheta_p_save, i) + LD(D.rtheta_pp, i);
+    }
+    ST(D.rho_p, i, sel(k_lt_nl, rho_p, 0.0));
+    ST(D.rho_zz_2, i, sel(k_lt_nl, rho_zz, 0.0));
+    ST(D.rtheta_p, i, sel(k_lt_nl, rtheta_p, 0.0));
+    ST(D.theta_m_2, i, sel(k_lt_nl, (rtheta_p + rtb) / rho_zz, 0.0));
+    // rows 0 and nl: rw = w = 0, wwAvg untouched; rows beyond nl (padding) keep what they held
+    const b2 k_ends = lv.eq(0) || lv.eq(nl);
+    const r2 rw = rw_save + LD(D.rw_p, i);
+    ST(D.wwAvg, i, sel(k_mid, rw_save + (wwAvg_in * invNs), wwAvg_in));
+    ST(D.rw, i, sel(k_mid, rw, sel(k_ends, mk2(0.0, 0.0), rw_in)));
+    ST(D.w_2, i, sel(k_mid, rw / (fm * zz + fp * up1(zz)), sel(k_ends, mk2(0.0, 0.0), w_in)));
+}
+// (2) edge-all, TI:3360-3372
+__global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    const b2 k_lt_nl = lv.lt(nl);
+    const r2 rus = LD(D.ru_save, i);
+    const r2 ru = rus + LD(D.ru_p, i);
+    const r2 rho2 = LD(D.rho_zz_2, cell1) + LD(D.rho_zz_2, cell2);
+    ST(D.ruAvg, i, sel(k_lt_nl, rus + (LD(D.ruAvg, i) * invNs), 0.0));
+    ST(D.ru, i, sel(k_lt_nl, ru, 0.0));
+    ST(D.u_2, i, sel(k_lt_nl, 2. * ru / rho2, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_advance_acoustic_step_work, edge part (small_step > 1)  TI:2751-2796
+__global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    const b2 k_lt_nl = lv.lt(nl);
+    r2 pgrad = ((LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp, cell1)) * D.invDcEdge[i]) / (.5 * (LD(D.zz, cell2) + LD(D.zz, cell1)));
+    pgrad = LD(D.cqu, i) * 0.5 * c2 * (LD(D.exner, cell1) + LD(D.exner, cell2)) * pgrad;
+    pgrad = pgrad + 0.5 * LD(D.zxu, i) * GRAVITY * (LD(D.rho_pp, cell1) + LD(D.rho_pp, cell2));
+    const r2 rup = LD(D.ru_p, i) + dts * (LD(D.tend_u, i) - (1.0 - D.specZoneMaskEdge[i]) * pgrad);
+    ST(D.ru_p, i, sel(k_lt_nl, rup, 0.0));
+    ST(D.ruAvg, i, sel(k_lt_nl, LD(D.ruAvg, i) + rup, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855
+// edge value of every scalar ("horiz_flux_arr"), TI:3670-3751: one warp per edge, the stencil indices and the two
+// possible weights per entry live one per lane and are broadcast; scalars are separate level-contiguous planes
+__global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
+    CW_SETUP(D.nEdges)
+    const int nadv = D.nAdvCellsForEdge[i];
+    int my_c = 0; real my_wp = 0.0, my_wm = 0.0;
+    if (lane < nadv) {
+        my_c = D.advCellsForEdge[(unsigned)i * 15 + lane];
+        const real a = D.adv_coefs[(unsigned)i * 15 + lane], b = D.adv_coefs_3rd[(unsigned)i * 15 + lane];
+        my_wp = a + b; my_wm = a - b;
+    }
+    const b2 pos = nonneg_sign(LD(D.ruAvg, i));
+    const b2 k_lt_nl = lv.lt(nl);
+    for (int s = 0; s < D.num_scalars; s++) {
+        const real* __restrict__ q = D.scalars_2 + (size_t)s * D.cellPlane;
+        r2 acc = mk2(0.0, 0.0);
+        int j0 = 0;
+        if (nadv == 10) {                                   // single expression, TI:3694-3704: no leading 0 +
+            const real wp = BC(my_wp, 0), wm = BC(my_wm, 0);
+            const r2 q2 = LD(q, BC(my_c, 0));
+            acc = mk2((pos.x ? wp : wm) * q2.x, (pos.y ? wp : wm) * q2.y);
+            j0 = 1;
+        }
+#pragma unroll 3
+        for (int j = j0; j < nadv; j++) {
+            const real wp = BC(my_wp, j), wm = BC(my_wm, j);
+            const r2 q2 = LD(q, BC(my_c, j));
+            acc.x = acc.x + (pos.x ? wp : wm) * q2.x;
+            acc.y = acc.y + (pos.y ? wp : wm) * q2.y;
+        }
+        ST(D.horiz_flux_arr + (size_t)s * D.edgePlane, i, sel(k_lt_nl, acc, 0.0));
+    }
+}
+// owned cells: flux divergence + vertical flux + update, TI:3773-3846
+__global__ void __launch_bounds__(CW_THREADS) k2_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const real invArea = D.invAreaCell[i];
+    const r2 rho_old = LD(D.rho_zz, i), rho_new = LD(D.rho_zz_2, i);
+    const r2 rho_zz_new_inv = 1.0 / (weight_time_old * rho_old + weight_time_new * rho_new);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0);
+    const r2 ww = LD(D.wwAvg, i);
+    const b2 k_lt_nl = lv.lt(nl);
+    const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1), kk_zero = lv.lt(1) || lv.ge(nl);
+    for (int s = 0; s < D.num_scalars; s++) {
+        real* qn = D.scalars_2 + (size_t)s * D.cellPlane;
+        const real* __restrict__ hf = D.horiz_flux_arr + (size_t)s * D.edgePlane;
+        r2 tend = mk2(0.0, 0.0);
+#define SC_EDGE(E)                                                                                          \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E));                                                                \
+            const r2 term = BC(my_sgn, (E)) * LD(D.ruAvg, iEdge) * LD(hf, iEdge);                           \
+            tend = selb((E) < ne, tend - term, tend);                                                       \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) SC_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) SC_EDGE(e)
+#undef SC_EDGE
+        tend = tend * invArea + 0.0;        // + scalar_tend_save, zero without physics (TI:3781-3783)
+        const r2 q = LD(qn, i);
+        const r2 qm1 = up1(q), qm2 = up2(q), qp1 = dn1(q);
+        const r2 f2 = ww * (fm * q + fp * qm1);
+        const r2 f3 = flux3_2(qm2, qm1, q, qp1, ww, coef3);
+        const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(kk_edge, f2, f3));
+        const r2 f1 = dn1(fz);
+        const r2 val = (LD(D.scalars + (size_t)s * D.cellPlane, i) * rho_old
+                        + dt * (tend - rdzw * (f1 - fz))) * rho_zz_new_inv;
+        ST(D.scalars_tend + (size_t)s * D.cellPlane, i, mk2(0.0, 0.0));
+        ST(qn, i, sel(k_lt_nl, val, 0.0));
+    }
 }

@@ -381,7 +381,7 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
         // first small step: ru_p = dts * tend_u is evaluated on the fly by the cell kernel and written by the
         // following divergence-damping kernel (h->ru_p_pending), saving one pass over three edge arrays
         if (small_step == 1) h->ru_p_pending = true;
-        else LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
+        else LAUNCHW(k2_acoustic_edge, h->D.nEdges, h->D, dts, c2);
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
@@ -411,8 +411,13 @@ static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {  
     const real p0 = 1.0e+05;
     const real invNs = 1 / (real)ns;
     refresh_zb_flags(h);
-    LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
-    LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
+    if (h->colwarp) {
+        LAUNCHW(k2_recover_cell1, h->D.nCells + 1, h->D, dt, invNs, rk_step, rcv, rgas / p0);
+        LAUNCHW(k2_recover_edge, h->D.nEdges, h->D, invNs);
+    } else {
+        LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
+        LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
+    }
     if (h->colwarp) LAUNCHW(k2_recover_cell2, h->D.nCells, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
     else LAUNCH(k_recover_cell2, h->D.nCells, 0, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
 }
@@ -467,6 +472,11 @@ static void advance_scalars(H* h, real dt, int rk_step) {     // TI:3575-3855
         if (rk_step == 3) weight_time_new = 1.;
     }
     const real weight_time_old = 1. - weight_time_new;
+    if (h->colwarp) {
+        LAUNCHW(k2_scalars_edge, h->D.nEdges, h->D);
+        LAUNCHW(k2_scalars_cell, h->D.nCellsSolve, h->D, dt, weight_time_old, weight_time_new, c.config_coef_3rd_order);
+        return;
+    }
     LAUNCH(k_scalars_edge, h->D.nEdges, 0, h->D);
     LAUNCH(k_scalars_cell, h->D.nCellsSolve, 0, h->D, dt, weight_time_old, weight_time_new, c.config_coef_3rd_order);
 }
