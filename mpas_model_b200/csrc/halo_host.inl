@@ -18,6 +18,9 @@ static const std::vector<GroupDef>& group_table() {
         {"dynamics:tend_u", {{"tend_u", 1, 1, 1}}},
         {"dynamics:rho_pp", {{"rho_pp", 1, 0, 1}}},
         {"dynamics:rtheta_pp", {{"rtheta_pp", 1, 0, 1}}},
+        // not a reference group: "dynamics:rtheta_pp" of small step s merged with "dynamics:rho_pp" of small step s+1
+        // (TI:1302 + TI:1279), which the reference issues back to back around atm_divergence_damping_3d
+        {"dynamics:rtheta_pp,rho_pp", {{"rtheta_pp", 1, 0, 1}, {"rho_pp", 1, 0, 1}}},
         {"dynamics:u_123", {{"u", 2, 1, 7}}},
         {"dynamics:u_3", {{"u", 2, 1, 4}}},
         {"dynamics:scalars", {{"scalars", 2, 0, 3}}},

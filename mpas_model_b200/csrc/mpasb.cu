@@ -48,6 +48,7 @@ struct mpasb_handle_s {
     bool colwarp = false;          // LDK <= 64 and <= CW_MAXNE edges per cell: the column-warp kernels apply
     int max_ne = 0;                // max(nEdgesOnCell), known once the mesh is uploaded
     bool zb_dirty = true;          // zb_any must be recomputed before the next step
+    bool physics_tend_dirty = true; // tend_*_physics must be zeroed before the next step (TI:1091-1093, no physics)
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool profile = false;
     std::map<std::string, ProfRec> prof;
@@ -197,6 +198,7 @@ extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level,
     const size_t o = outer_of(h, f->loc);
     const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
     if (f->inner == IN_NL1_ME) h->zb_dirty = true;
+    if (!strncmp(name, "tend_", 5) && strstr(name, "_physics")) h->physics_tend_dirty = true;
     if (!padded) { CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(real), cudaMemcpyHostToDevice, h->stream)); }
     else {
         real* st = (real*)h->staging;
@@ -539,9 +541,12 @@ static int srk3(H* h, real dt) {
     Dev& D = h->D;
     cudaSetDevice(h->device);
     // TI:967-991, 1091-1093: qtot garbage column and the physics tendencies are zero (no physics)
-    cudaMemsetAsync(D.tend_ru_physics, 0, D.edgePlane * sizeof(real), h->stream);
-    cudaMemsetAsync(D.tend_rtheta_physics, 0, D.cellPlane * sizeof(real), h->stream);
-    cudaMemsetAsync(D.tend_rho_physics, 0, D.cellPlane * sizeof(real), h->stream);
+    if (h->physics_tend_dirty) {      // zero until a host uploads them again (mpasb_set_field marks them dirty)
+        cudaMemsetAsync(D.tend_ru_physics, 0, D.edgePlane * sizeof(real), h->stream);
+        cudaMemsetAsync(D.tend_rtheta_physics, 0, D.cellPlane * sizeof(real), h->stream);
+        cudaMemsetAsync(D.tend_rho_physics, 0, D.cellPlane * sizeof(real), h->stream);
+        h->physics_tend_dirty = false;
+    }
     int dynamics_split = c.config_dynamics_split_steps;
     real dt_dynamics;
     if (c.config_split_dynamics_transport) dt_dynamics = dt / (real)dynamics_split;
@@ -572,9 +577,12 @@ static int srk3(H* h, real dt) {
             if (exchange(h, "dynamics:tend_u")) return 1;
             set_smlstep_pert_variables(h);
             for (int small_step = 1; small_step <= number_sub_steps[rk_step]; small_step++) {
-                if (exchange(h, "dynamics:rho_pp")) return 1;
+                // TI:1279 exchanges rho_pp before every acoustic step.  On the first small step nothing reads the
+                // halo of rho_pp (the edge update is ru_p = dts * tend_u, TI:2798-2806), so that exchange is skipped;
+                // on later ones it is merged into the rtheta_pp exchange (TI:1302) that directly precedes it.
                 advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step);
-                if (exchange(h, "dynamics:rtheta_pp")) return 1;
+                const bool more = small_step < number_sub_steps[rk_step];
+                if (exchange(h, more ? "dynamics:rtheta_pp,rho_pp" : "dynamics:rtheta_pp")) return 1;
                 divergence_damping_3d(h, rk_sub_timestep[rk_step]);
             }
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;

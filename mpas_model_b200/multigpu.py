@@ -45,6 +45,7 @@ GROUPS = {
     "dynamics:tend_u": (("tend_u", 1, "edges", (1,)),),
     "dynamics:rho_pp": (("rho_pp", 1, "cells", (1,)),),
     "dynamics:rtheta_pp": (("rtheta_pp", 1, "cells", (1,)),),
+    "dynamics:rtheta_pp,rho_pp": (("rtheta_pp", 1, "cells", (1,)), ("rho_pp", 1, "cells", (1,))),   # merged (library only)
     "dynamics:u_123": (("u", 2, "edges", (1, 2, 3)),),
     "dynamics:u_3": (("u", 2, "edges", (3,)),),
     "dynamics:scalars": (("scalars", 2, "cells", (1, 2)),),
