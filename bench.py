@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--cells", type=int, default=0, help="override the mesh (10*4^n+2 cells)")
     ap.add_argument("--levels", type=int, default=0)
     ap.add_argument("--scalars", type=int, default=1)
+    ap.add_argument("--precision", default="double", choices=("double", "single"), help="RKIND of the library build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -203,13 +204,13 @@ def main():
     if world > 1:
         from mpas_model_b200 import multigpu as mg
         dist = mg.init_distributed("gloo")
-        g, d, cfg, _ex, _ = mg.setup_rank(n_cells, n_lev, args.scalars, rank, world, local_rank)
+        g, d, cfg, _ex, _ = mg.setup_rank(n_cells, n_lev, args.scalars, rank, world, local_rank, precision=args.precision)
         dt = cfg["config_dt"]
     else:
         from mpas_model_b200.case import make_case
         d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
         dt = cfg["config_dt"]
-        g = Dycore(d, cfg, device=0)
+        g = Dycore(d, cfg, device=0, precision=args.precision)
         g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
 
     def barrier():
@@ -257,7 +258,7 @@ def main():
     if not args.no_e2e:
         host = {}
         for name, lev in set(E2E_FIELDS) | set(E2E_OUT):
-            t = torch.empty(tuple(g.shape(name)), dtype=torch.float64).pin_memory()
+            t = torch.empty(tuple(g.shape(name)), dtype=torch.float64 if g.rdtype == np.float64 else torch.float32).pin_memory()
             host[(name, lev)] = t.numpy()
         for (name, lev) in E2E_FIELDS:
             g._get_real(name, lev, host[(name, lev)])
@@ -303,7 +304,8 @@ def main():
     dom = max(krows.items(), key=lambda kv: kv[1][0])
     dom_name, (dom_ms, dom_cnt) = dom
     peak, peak_src = measured_peak_gbs()
-    C = n_lev * d["nCells"] * 8                       # this rank's block (owned + halo columns)
+    rb = 8 if args.precision == "double" else 4
+    C = n_lev * d["nCells"] * rb                      # this rank's block (owned + halo columns)
     model_c = KERNEL_MODEL_C.get(dom_name)
     dom_us = 1e3 * dom_ms / dom_cnt
     achieved = (model_c * C / (dom_us * 1e-6) / 1e9) if model_c else None
@@ -311,7 +313,7 @@ def main():
                 "frac": (achieved / peak) if achieved else None, "traffic": KERNEL_TRAFFIC.get(dom_name),
                 "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum,
                 "algorithmic_bytes_per_launch": (model_c * C) if model_c else None, "peak_source": peak_src}
-    B_step = model_bytes_per_step(n_cells, n_lev, args.scalars)
+    B_step = model_bytes_per_step(n_cells, n_lev, args.scalars, rb)
     step_gbs = B_step / (ms_per_step * 1e-3) / 1e9
 
     # ---------------- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only)
@@ -331,6 +333,9 @@ def main():
     if rank != 0:
         return
     line = line_common(args, n_cells, n_lev, dt, world)
+    if args.precision == "single":
+        line["dtype"] = "f32"
+        line["config"]["workload"] = line["config"]["workload"].replace("fp64", "fp32 (PRECISION=single build)")
     line.update({
         "value": value, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

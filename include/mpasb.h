@@ -26,7 +26,11 @@
 extern "C" {
 #endif
 
-typedef double mpasb_real;      /* RKIND, PRECISION=double build */
+#ifdef MPASB_SINGLE
+typedef float mpasb_real;       /* RKIND, PRECISION=single build (libmpasb_sp.so) */
+#else
+typedef double mpasb_real;      /* RKIND, PRECISION=double build (libmpasb.so) */
+#endif
 
 /* Block dimensions: mesh pool dims + block%dimensions (mpas_atm_time_integration.F:921-962). */
 typedef struct mpasb_dims {
@@ -124,6 +128,7 @@ int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HAL
 /* 1 if every kernel keeps the reference's operation order without FMA contraction (results bit-identical to
  * the fp64 CPU arithmetic; the only build at present), 0 for a relaxed build */
 int  mpasb_strict_arithmetic(void);
+int  mpasb_real_bytes(void);     /* sizeof(mpasb_real) of this build: 8 (libmpasb.so) or 4 (libmpasb_sp.so) */
 
 /* Instrumentation */
 long mpasb_kernel_launch_count(mpasb_handle h);      /* kernels launched by this handle so far */

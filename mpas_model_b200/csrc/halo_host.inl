@@ -185,8 +185,8 @@ static int halo_exchange(H* h, const char* group) {
     if (P.n_pack) { k_halo_pack<<<dim3(gx, std::min(P.n_pack, 256)), 256, 0, h->stream>>>(P.d_pack, P.d_idx_send, P.d_sendbuf, P.n_pack); h->launches++; }
     a->GroupStart();
     for (size_t p = 0; p < P.peers.size(); p++) {
-        if (P.recv_cnt[p]) a->Recv(P.d_recvbuf + P.recv_off[p], P.recv_cnt[p], ncclFloat64, P.peers[p], (ncclComm_t)hs.comm, h->stream);
-        if (P.send_cnt[p]) a->Send(P.d_sendbuf + P.send_off[p], P.send_cnt[p], ncclFloat64, P.peers[p], (ncclComm_t)hs.comm, h->stream);
+        if (P.recv_cnt[p]) a->Recv(P.d_recvbuf + P.recv_off[p], P.recv_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, h->stream);
+        if (P.send_cnt[p]) a->Send(P.d_sendbuf + P.send_off[p], P.send_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, h->stream);
     }
     ncclResult_t r = a->GroupEnd();
     if (r != ncclSuccess) { h->err = std::string("nccl: ") + a->GetErrorString(r); return 1; }

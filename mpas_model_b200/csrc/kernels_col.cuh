@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_b(const Dev D, const Dy
                                    - 0.5 * LD(D.zxu, i) * (LD(D.dpdz, cell1) + LD(D.dpdz, cell2)));
         const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
         const real r_dc = invDc;
-        const real r_dv = fmin(D.invDvEdge[i], 4 * invDc);
+        const real r_dv = rmin(D.invDvEdge[i], 4 * invDc);
         const r2 u_diffusion = (LD(D.divergence, cell2) - LD(D.divergence, cell1)) * r_dc
                                - (LD(D.vorticity, vertex2) - LD(D.vorticity, vertex1)) * r_dv;
         ST(D.delsq_u, i, sel(k_lt_nl, 0.0 + u_diffusion, 0.0));
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_a(const Dev D, const Dy
         for (int e = CW_NE; e < ne; e++) CELL_A_DEF(e)
 #undef CELL_A_DEF
         const r2 dd = d_diag * d_diag + d_off_diag * d_off_diag;
-        kd = mk2(fmin(A.cs_len2 * sqrt(dd.x), A.kdiff_cap), fmin(A.cs_len2 * sqrt(dd.y), A.kdiff_cap));
+        kd = mk2(rmin(A.cs_len2 * sqrt(dd.x), A.kdiff_cap), rmin(A.cs_len2 * sqrt(dd.y), A.kdiff_cap));
     }
     r2 hd = mk2(0.0, 0.0);
 #define CELL_A_DIV(E) { const r2 ru = LD(D.ru, BC(my_e, (E))); hd = selb((E) < ne, hd + BC(my_es, (E)) * ru, hd); }

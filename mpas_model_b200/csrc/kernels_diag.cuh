@@ -167,30 +167,30 @@ __global__ void k_fill(real* __restrict__ y, real v, size_t n) {
 }
 
 // ------------------------------------------------------------------ summarize_timestep  TI:8286-8319
-__device__ __forceinline__ void atomic_min_f64(real* addr, real v) {
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
     unsigned long long* a = (unsigned long long*)addr;
     unsigned long long old = *a, assumed;
     do { assumed = old; if (__longlong_as_double(assumed) <= v) break;
          old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
 }
-__device__ __forceinline__ void atomic_max_f64(real* addr, real v) {
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
     unsigned long long* a = (unsigned long long*)addr;
     unsigned long long old = *a, assumed;
     do { assumed = old; if (__longlong_as_double(assumed) >= v) break;
          old = atomicCAS(a, assumed, __double_as_longlong(v)); } while (assumed != old);
 }
 // out[0..1] = min/max over x[0:n_items][0:nl]; reductions start from 0.0 as the reference's do (TI:8291-8292)
-__global__ void k_minmax(const real* __restrict__ x, int n_items, int nl, int LDK, real* out) {
+__global__ void k_minmax(const real* __restrict__ x, int n_items, int nl, int LDK, double* out) {
     real mn = 0.0, mx = 0.0;
     const size_t total = (size_t)n_items * LDK;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        if ((int)(t % LDK) < nl) { const real v = x[t]; mn = fmin(mn, v); mx = fmax(mx, v); }
+        if ((int)(t % LDK) < nl) { const real v = x[t]; mn = rmin(mn, v); mx = rmax(mx, v); }
     }
     for (int o = 16; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = rmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = rmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if ((threadIdx.x & 31) == 0) { atomic_min_f64(out, mn); atomic_max_f64(out + 1, mx); }
+    if ((threadIdx.x & 31) == 0) { atomic_min_f64(out, (double)mn); atomic_max_f64(out + 1, (double)mx); }
 }
 
 // ------------------------------------------------------------------ dense host layout <-> padded device layout

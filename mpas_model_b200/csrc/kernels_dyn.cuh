@@ -145,14 +145,14 @@ __global__ void k_dt_cell_a(const Dev D, const DynTendArgs A) {
                 d_diag = d_diag + da[e] * uu - db[e] * vv;
                 d_off_diag = d_off_diag + db[e] * uu + da[e] * vv;
             }
-            kd = fmin(A.cs_len2 * sqrt(d_diag * d_diag + d_off_diag * d_off_diag), A.kdiff_cap);
+            kd = rmin(A.cs_len2 * sqrt(d_diag * d_diag + d_off_diag * d_off_diag), A.kdiff_cap);
         } else {
             kd = A.fixed_visc2;
         }
         if (A.cam_coef > 0.0 && k >= nl - A.n_cam_levels) {       // TI:5278-5296
             real visc2cam = 4.0 * 2.0833 * A.len_disp * A.cam_coef;
             visc2cam = visc2cam * (1.0 - (real)(nl - (k + 1)) / (real)(A.n_cam_levels));
-            kd = fmax(kd, visc2cam);
+            kd = rmax(kd, visc2cam);
         }
         AT(D.kdiff, i, k) = kd;
     }
@@ -197,7 +197,7 @@ __global__ void k_dt_edge_b(const Dev D, const DynTendArgs A) {
                                       - 0.5 * AT(D.zxu, i, k) * (AT(D.dpdz, cell1, k) + AT(D.dpdz, cell2, k)));
         const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
         const real r_dc = invDc;
-        const real r_dv = fmin(D.invDvEdge[i], 4 * invDc);
+        const real r_dv = rmin(D.invDvEdge[i], 4 * invDc);
         const real u_diffusion = (AT(D.divergence, cell2, k) - AT(D.divergence, cell1, k)) * r_dc
                                  - (AT(D.vorticity, vertex2, k) - AT(D.vorticity, vertex1, k)) * r_dv;
         AT(D.delsq_u, i, k) = 0.0 + u_diffusion;
@@ -269,7 +269,7 @@ __global__ void k_dt_edge_d(const Dev D, const DynTendArgs A) {
         const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
         const real u_mix_scale = D.meshScalingDel4[i] * A.h_mom_eddy_visc4;
         const real r_dc = u_mix_scale * A.del4u_div_factor * D.invDcEdge[i];
-        const real r_dv = u_mix_scale * fmin(D.invDvEdge[i], 4 * D.invDcEdge[i]);
+        const real r_dv = u_mix_scale * rmin(D.invDvEdge[i], 4 * D.invDcEdge[i]);
         const real u_diffusion = rho_e * ((AT(D.delsq_divergence, cell2, k) - AT(D.delsq_divergence, cell1, k)) * r_dc
                                           - (AT(D.delsq_vorticity, vertex2, k) - AT(D.delsq_vorticity, vertex1, k)) * r_dv);
         tue = tue - u_diffusion;

@@ -99,7 +99,7 @@ __device__ __forceinline__ real mono_wdtn(const real* __restrict__ so, const rea
                                           int kk, int iCell, real dt, real coef3, int LDK, int nl) {
     if (kk <= 0 || kk >= nl) return 0.0;
     const real ww = AT(D.wwAvg, iCell, kk);
-    const real fu = dt * (fmax(0.0, ww) * AT(so, iCell, kk - 1) + fmin(0.0, ww) * AT(so, iCell, kk));
+    const real fu = dt * (rmax(0.0, ww) * AT(so, iCell, kk - 1) + rmin(0.0, ww) * AT(so, iCell, kk));
     return dt * wdtn_raw(sn, D.wwAvg, D, kk, iCell, coef3, LDK, nl) - fu;
 }
 
@@ -115,13 +115,13 @@ __global__ void k_mono_cell1(const Dev D, int s, real dt, real coef3) {
     const real wd1 = mono_wdtn(so, sn, D, k + 1, i, dt, coef3, LDK, nl);
     const real sok = AT(so, i, k);
     real smax, smin;
-    if (k == 0) { smax = fmax(sok, AT(so, i, 1)); smin = fmin(sok, AT(so, i, 1)); }
-    else if (k == nl - 1) { smax = fmax(sok, AT(so, i, k - 1)); smin = fmin(sok, AT(so, i, k - 1)); }
-    else { smax = fmax(fmax(AT(so, i, k - 1), sok), AT(so, i, k + 1)); smin = fmin(fmin(AT(so, i, k - 1), sok), AT(so, i, k + 1)); }
+    if (k == 0) { smax = rmax(sok, AT(so, i, 1)); smin = rmin(sok, AT(so, i, 1)); }
+    else if (k == nl - 1) { smax = rmax(sok, AT(so, i, k - 1)); smin = rmin(sok, AT(so, i, k - 1)); }
+    else { smax = rmax(rmax(AT(so, i, k - 1), sok), AT(so, i, k + 1)); smin = rmin(rmin(AT(so, i, k - 1), sok), AT(so, i, k + 1)); }
     const int ne = D.nEdgesOnCell[i];
     for (int e = 0; e < ne; e++) {
         const real v = AT(so, D.cellsOnCell[(size_t)i * D.maxEdges + e], k);
-        smax = fmax(smax, v); smin = fmin(smin, v);
+        smax = rmax(smax, v); smin = rmin(smin, v);
     }
     AT(D.s_max, i, k) = smax; AT(D.s_min, i, k) = smin;
     // upwind vertical update, TI:4428-4446
@@ -129,17 +129,17 @@ __global__ void k_mono_cell1(const Dev D, int s, real dt, real coef3) {
     const real rdnw = D.rdzw[k];
     if (k <= nl - 2) {
         const real ww = AT(D.wwAvg, i, k + 1);
-        const real fu1 = dt * (fmax(0.0, ww) * sok + fmin(0.0, ww) * AT(so, i, k + 1));
+        const real fu1 = dt * (rmax(0.0, ww) * sok + rmin(0.0, ww) * AT(so, i, k + 1));
         snew = snew - fu1 * rdnw;
     }
     if (k >= 1) {
         const real ww = AT(D.wwAvg, i, k);
-        const real fu0 = dt * (fmax(0.0, ww) * AT(so, i, k - 1) + fmin(0.0, ww) * sok);
+        const real fu0 = dt * (rmax(0.0, ww) * AT(so, i, k - 1) + rmin(0.0, ww) * sok);
         snew = snew + fu0 * rdnw;
     }
     AT(D.scalar_new, i, k) = snew;
-    AT(D.scale_arr, i, k) = -rdnw * (fmin(0.0, wd1) - fmax(0.0, wd0));                      // SCALE_IN
-    AT(D.scale_arr + D.cellPlane, i, k) = -rdnw * (fmax(0.0, wd1) - fmin(0.0, wd0));        // SCALE_OUT
+    AT(D.scale_arr, i, k) = -rdnw * (rmin(0.0, wd1) - rmax(0.0, wd0));                      // SCALE_IN
+    AT(D.scale_arr + D.cellPlane, i, k) = -rdnw * (rmax(0.0, wd1) - rmin(0.0, wd0));        // SCALE_OUT
 }
 // (C2) edges: high-order flux (4356-4413), upwind flux and their difference (4467-4487)
 __global__ void k_mono_edge2(const Dev D, int s, real dt) {
@@ -168,7 +168,7 @@ __global__ void k_mono_edge2(const Dev D, int s, real dt) {
             }
         }
     }
-    const real fup = D.dvEdge[i] * dt * (fmax(0.0, uh) * AT(so, cell1, k) + fmin(0.0, uh) * AT(so, cell2, k));
+    const real fup = D.dvEdge[i] * dt * (rmax(0.0, uh) * AT(so, cell1, k) + rmin(0.0, uh) * AT(so, cell2, k));
     AT(D.flux_upwind_tmp, i, k) = fup;
     AT(D.flux_tmp, i, k) = dt * flux - fup;
 }
@@ -185,16 +185,16 @@ __global__ void k_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
         const real sg = D.edgesOnCell_sign[(size_t)i * D.maxEdges + e];
         const real ft = AT(D.flux_tmp, iEdge, k);
         snew = snew - sg * AT(D.flux_upwind_tmp, iEdge, k) * invArea;
-        sout = sout - fmax(0.0, sg * ft) * invArea;
-        sin_ = sin_ - fmin(0.0, sg * ft) * invArea;
+        sout = sout - rmax(0.0, sg * ft) * invArea;
+        sin_ = sin_ - rmin(0.0, sg * ft) * invArea;
     }
     AT(D.scalar_new, i, k) = snew;
     const real eps = 1.e-20;
     const real rl = AT(rho_lim, i, k);
     real scale_factor = (AT(D.s_max, i, k) * rl - snew) / (sin_ + eps);
-    AT(D.scale_arr, i, k) = fmin(1.0, fmax(0.0, scale_factor));
+    AT(D.scale_arr, i, k) = rmin(1.0, rmax(0.0, scale_factor));
     scale_factor = (AT(D.s_min, i, k) * rl - snew) / (sout - eps);
-    AT(D.scale_arr + D.cellPlane, i, k) = fmin(1.0, fmax(0.0, scale_factor));
+    AT(D.scale_arr + D.cellPlane, i, k) = rmin(1.0, rmax(0.0, scale_factor));
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
 __global__ void k_mono_edge4(const Dev D) {
@@ -204,16 +204,16 @@ __global__ void k_mono_edge4(const Dev D) {
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     RP s_in = D.scale_arr; RP s_out = D.scale_arr + D.cellPlane;
     real flux = AT(D.flux_tmp, i, k);
-    flux = fmax(0.0, flux) * fmin(AT(s_out, cell1, k), AT(s_in, cell2, k))
-         + fmin(0.0, flux) * fmin(AT(s_in, cell1, k), AT(s_out, cell2, k));
+    flux = rmax(0.0, flux) * rmin(AT(s_out, cell1, k), AT(s_in, cell2, k))
+         + rmin(0.0, flux) * rmin(AT(s_in, cell1, k), AT(s_out, cell2, k));
     AT(D.flux_arr, i, k) = flux;
 }
 __device__ __forceinline__ real mono_wdtn_scaled(const Dev& D, int kk, int iCell, int LDK, int nl) {
     if (kk <= 0 || kk >= nl) return 0.0;
     RP s_in = D.scale_arr; RP s_out = D.scale_arr + D.cellPlane;
     real flux = AT(D.wdtn, iCell, kk);
-    flux = fmax(0.0, flux) * fmin(AT(s_out, iCell, kk - 1), AT(s_in, iCell, kk))
-         + fmin(0.0, flux) * fmin(AT(s_out, iCell, kk), AT(s_in, iCell, kk - 1));
+    flux = rmax(0.0, flux) * rmin(AT(s_out, iCell, kk - 1), AT(s_in, iCell, kk))
+         + rmin(0.0, flux) * rmin(AT(s_out, iCell, kk), AT(s_in, iCell, kk - 1));
     return flux;
 }
 // (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
@@ -221,7 +221,7 @@ __global__ void k_mono_cell5(const Dev D, int s, const real* __restrict__ rho_di
     KI;
     if (i >= D.nCells || k >= nl) return;
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
-    if (i >= D.nCellsSolve) { AT(out, i, k) = fmax(0.0, AT(out, i, k)); return; }
+    if (i >= D.nCellsSolve) { AT(out, i, k) = rmax(0.0, AT(out, i, k)); return; }
     const real w0 = mono_wdtn_scaled(D, k, i, LDK, nl), w1 = mono_wdtn_scaled(D, k + 1, i, LDK, nl);
     const int ne = D.nEdgesOnCell[i];
     const real invArea = D.invAreaCell[i];
@@ -231,5 +231,5 @@ __global__ void k_mono_cell5(const Dev D, int s, const real* __restrict__ rho_di
         snew = snew - D.edgesOnCell_sign[(size_t)i * D.maxEdges + e] * AT(D.flux_arr, iEdge, k) * invArea;
     }
     snew = (snew + (-D.rdzw[k] * (w1 - w0))) / AT(rho_div, i, k);
-    AT(out, i, k) = fmax(0.0, snew);
+    AT(out, i, k) = rmax(0.0, snew);
 }

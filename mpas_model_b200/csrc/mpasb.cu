@@ -41,7 +41,7 @@ struct mpasb_handle_s {
     std::vector<FieldRec> fields;
     std::map<std::string, int> index;
     void* staging = nullptr; size_t staging_bytes = 0;
-    real* d_minmax = nullptr;
+    double* d_minmax = nullptr;
     std::string err;
     long launches = 0;
     int cpb = 4;
@@ -130,7 +130,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
         set_dev_ptr(h, f);
     }
     h->staging_bytes = max_bytes;
-    if (cudaMalloc(&h->staging, max_bytes) != cudaSuccess || cudaMalloc(&h->d_minmax, 4 * sizeof(real)) != cudaSuccess ||
+    if (cudaMalloc(&h->staging, max_bytes) != cudaSuccess || cudaMalloc(&h->d_minmax, 4 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->D.zb_any, ((size_t)dims->nCells + 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->D.adv_flux_w, h->D.edgePlane * sizeof(real)) != cudaSuccess ||
         cudaMalloc(&h->D.adv_flux_theta, h->D.edgePlane * sizeof(real)) != cudaSuccess) {
@@ -176,6 +176,7 @@ extern "C" long mpasb_kernel_launch_count(mpasb_handle h) { return h->launches; 
 // 1: every kernel keeps the reference's operation order and is built without FMA contraction, so results are
 // bit-identical to the fp64 CPU arithmetic (the only build at present; a relaxed build would return 0)
 extern "C" int mpasb_strict_arithmetic(void) { return 1; }
+extern "C" int mpasb_real_bytes(void) { return (int)sizeof(mpasb_real); }
 extern "C" int mpasb_synchronize(mpasb_handle h) { cudaSetDevice(h->device); CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
 
 static FieldRec* find_field(H* h, const char* name) {
@@ -614,12 +615,14 @@ extern "C" int mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep) { (void)
 extern "C" int mpasb_minmax(mpasb_handle h, mpasb_real out[4]) {
     cudaSetDevice(h->device);
     const Dev& D = h->D;
-    CUDA_OK(cudaMemsetAsync(h->d_minmax, 0, 4 * sizeof(real), h->stream));
+    double tmp[4];
+    CUDA_OK(cudaMemsetAsync(h->d_minmax, 0, 4 * sizeof(double), h->stream));
     k_minmax<<<296, 256, 0, h->stream>>>(D.w_2, D.nCellsSolve, D.nl, D.LDK, h->d_minmax);
     k_minmax<<<296, 256, 0, h->stream>>>(D.u_2, D.nEdgesSolve, D.nl, D.LDK, h->d_minmax + 2);
     h->launches += 2;
-    CUDA_OK(cudaMemcpyAsync(out, h->d_minmax, 4 * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(tmp, h->d_minmax, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (int n = 0; n < 4; n++) out[n] = (mpasb_real)tmp[n];
     return 0;
 }
 

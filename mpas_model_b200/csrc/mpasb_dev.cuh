@@ -9,7 +9,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// RKIND: PRECISION=double (default) or PRECISION=single (-DMPASB_SINGLE, reference Makefile: PRECISION=single)
+#ifdef MPASB_SINGLE
+typedef float real;
+#else
 typedef double real;
+#endif
 
 enum { LOC_CELL = 0, LOC_EDGE = 1, LOC_VERTEX = 2, LOC_LEVS = 3 };
 enum { IN_ONE, IN_NL, IN_NL1, IN_ME, IN_ME2, IN_VD, IN_TWO, IN_F15, IN_NL1_ME, IN_S_NL, IN_NL_TWO };
@@ -44,6 +49,14 @@ struct Dev {
 #define RV_ 461.6
 #define PRANDTL 1.0
 
+// min/max in RKIND whatever the literal types of the arguments (fmax(0.0, x) would not resolve in the single build)
+#ifdef MPASB_SINGLE
+__device__ __forceinline__ real rmax(real a, real b) { return fmaxf(a, b); }
+__device__ __forceinline__ real rmin(real a, real b) { return fminf(a, b); }
+#else
+__device__ __forceinline__ real rmax(real a, real b) { return fmax(a, b); }
+__device__ __forceinline__ real rmin(real a, real b) { return fmin(a, b); }
+#endif
 __device__ __forceinline__ real sign1(real x) { return copysign(1.0, x); }      // Fortran sign(1.0, x)
 
 // statement functions, mpas_atm_time_integration.F:5156-5161

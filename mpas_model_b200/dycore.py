@@ -25,6 +25,7 @@ from .fields import FIELDS, host_shape
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPASB_LIB") or os.path.join(_HERE, "csrc", "libmpasb.so")
+LIB_PATH_SINGLE = os.path.join(_HERE, "csrc", "libmpasb_sp.so")      # PRECISION=single build (RKIND = float)
 
 
 class Dims(C.Structure):
@@ -80,6 +81,8 @@ class Backend:
     moving a block dict (numpy, 0-based) through the by-name field ABI."""
 
     dims: Dims
+    rdtype = np.float64          # RKIND of the bound library
+    creal = C.c_double
 
     # -- to be provided by the concrete binding
     def _set_real(self, name, lev, arr): raise NotImplementedError
@@ -98,11 +101,11 @@ class Backend:
                 a = a + 1                     # the ABI is 1-based, like the Fortran pools
             self._set_int(name, np.ascontiguousarray(a))
         else:
-            a = np.ascontiguousarray(arr, dtype=np.float64).reshape(shp)
+            a = np.ascontiguousarray(arr, dtype=self.rdtype).reshape(shp)
             self._set_real(name, time_level, a)
 
     def get_array(self, name, time_level=1):
-        out = np.empty(self.shape(name), dtype=np.float64)
+        out = np.empty(self.shape(name), dtype=self.rdtype)
         self._get_real(name, time_level, out)
         return out
 
@@ -132,12 +135,13 @@ class Backend:
         return {n: self.get_array(n, time_level) for n in names}
 
 
-def _load_lib():
-    if not os.path.exists(LIB_PATH):
+def _load_lib(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"CUDA library {LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"CUDA library {path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the dycore step)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.mpasb_last_error.restype = C.c_char_p
     lib.mpasb_last_error.argtypes = [C.c_void_p]
     lib.mpasb_kernel_launch_count.restype = C.c_long
@@ -148,8 +152,10 @@ def _load_lib():
 class Dycore(Backend):
     """One mesh block resident on one GPU."""
 
-    def __init__(self, block: dict, cfg: dict, device: int = 0):
-        self.lib = _load_lib()
+    def __init__(self, block: dict, cfg: dict, device: int = 0, precision: str = "double"):
+        self.lib = _load_lib(LIB_PATH_SINGLE if precision == "single" else None)
+        if self.lib.mpasb_real_bytes() == 4:
+            self.rdtype, self.creal = np.float32, C.c_float
         self.dims = make_dims(block)
         self.config = make_config(cfg, block)
         self.cfg = dict(cfg)
@@ -193,10 +199,10 @@ class Dycore(Backend):
         self._check(self.lib.mpasb_init_coupled_diagnostics(self._h), "init_coupled_diagnostics")
 
     def atm_init_solve_diagnostics(self, dt):
-        self._check(self.lib.mpasb_init_solve_diagnostics(self._h, C.c_double(dt)), "init_solve_diagnostics")
+        self._check(self.lib.mpasb_init_solve_diagnostics(self._h, self.creal(dt)), "init_solve_diagnostics")
 
     def atm_srk3(self, dt, itimestep=1):
-        self._check(self.lib.mpasb_step(self._h, C.c_double(dt), C.c_int(itimestep)), "mpasb_step")
+        self._check(self.lib.mpasb_step(self._h, self.creal(dt), C.c_int(itimestep)), "mpasb_step")
 
     atm_timestep = atm_srk3      # config_time_integration == 'SRK3' is the only integrator (TI:773-790)
 
@@ -204,7 +210,7 @@ class Dycore(Backend):
         self._check(self.lib.mpasb_shift_time_levels(self._h), "shift_time_levels")
 
     def summarize_timestep(self):
-        out = (C.c_double * 4)()
+        out = (self.creal * 4)()
         self._check(self.lib.mpasb_minmax(self._h, out), "minmax")
         return tuple(out)
 
@@ -261,5 +267,5 @@ class Dycore(Backend):
     # -- one *_work routine at a time (parity tests)
     def k(self, routine, *args):
         fn = getattr(self.lib, "mpasb_k_" + routine)
-        cargs = [C.c_double(a) if isinstance(a, float) else C.c_int(a) for a in args]
+        cargs = [self.creal(a) if isinstance(a, float) else C.c_int(a) for a in args]
         self._check(fn(self._h, *cargs), routine)

@@ -106,7 +106,7 @@ def init_distributed(backend="gloo"):
     return dist
 
 
-def setup_rank(n_cells, n_levels, num_scalars, rank, world, device):
+def setup_rank(n_cells, n_levels, num_scalars, rank, world, device, precision="double"):
     """Create this rank's ``Dycore`` with halo lists and NCCL communicator, run the init sequence."""
     from .dycore import Dycore
     dist = init_distributed()
@@ -116,7 +116,7 @@ def setup_rank(n_cells, n_levels, num_scalars, rank, world, device):
     dist.broadcast_object_list(box, src=0)
     rec = load_block(box[0], rank)
     block, cfg, ex = rec["block"], rec["cfg"], rec["ex"]
-    g = Dycore(block, cfg, device=device)
+    g = Dycore(block, cfg, device=device, precision=precision)
     for kind, k in KINDS:
         g.set_halo_lists(k, ex[kind])
     uid = [g.nccl_unique_id() if rank == 0 else None]
