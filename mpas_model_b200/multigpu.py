@@ -77,14 +77,18 @@ def prepare_blocks(n_cells, n_levels, num_scalars, world, tag=""):
             d, cfg = pickle.load(f)
     else:
         d, cfg = make_case(n_cells, n_levels, num_scalars=num_scalars)
-        with open(gpath + ".tmp", "wb") as f:
-            pickle.dump((d, cfg), f, protocol=4)
-        os.replace(gpath + ".tmp", gpath)
+        if n_cells <= 200000:                                   # 4 GB at x1.163842; not worth 17 GB at x1.655362
+            with open(gpath + ".tmp", "wb") as f:
+                pickle.dump((d, cfg), f, protocol=4)
+            os.replace(gpath + ".tmp", gpath)
     part = decomp.partition_rcb(d, world)
     decomp.write_partition_file(prefix, part)               # the reference's "<prefix><N>" partition file format
     blocks, ex = decomp.decompose_case(d, cfg, part)
     for r in range(world):
-        b = dict(blocks[r])
+        # keep what the library consumes (the field table) plus scalars, ids and small geometry; the init-only
+        # intermediates (zb/zb3 per edge, deriv_two, *_init) are half of a block's bytes
+        b = {k: v for k, v in blocks[r].items()
+             if not isinstance(v, np.ndarray) or k in FIELDS or v.nbytes < (4 << 20) or k.startswith("indexTo")}
         with open(f"{prefix}.{r}.pkl.tmp", "wb") as f:
             pickle.dump({"block": b, "cfg": cfg, "ex": ex[r], "nCellsGlobal": d["nCells"]}, f, protocol=4)
         os.replace(f"{prefix}.{r}.pkl.tmp", f"{prefix}.{r}.pkl")
