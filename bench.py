@@ -11,7 +11,9 @@ natural for a fixed global mesh family, so N = 2/4 use x1.163842 and N = 8 uses 
 BASELINE.json names them: per-GPU work is 40962 / 81921 / 40961 / 81920 columns, i.e. weak scaling
 within a factor of two; cell_columns_per_s is the figure comparable across N).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident whole-job steps/s; `e2e` is the
+Prints ONE JSON line (rank 0).  `value` is the device-resident whole-job rate in cell-column
+updates/s (nCells x steps/s: the BASELINE throughput figure that is comparable across the
+per-N meshes; `steps_per_s` and `sdpd` are in the same line); `e2e` is the
 same step driven through the C ABI with HOST buffers (restart-state upload, diagnostics
 recompute, step, state download inside the timed region).
 """
@@ -109,14 +111,16 @@ def workload_for(args):
 
 def line_common(args, n_cells, n_lev, dt, world):
     return {
-        "metric": "JW wave dycore steps/sec", "unit": "steps/s", "n_gpus": world, "higher_is_better": True,
+        "metric": "JW wave dycore cell-column updates/sec (= steps/sec x nCells; steps_per_s and sdpd alongside)",
+        "unit": "cell-columns/s", "n_gpus": world, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (generated icosahedral SCVT mesh + JW case 2 initial state)",
         "config": {"workload": f"JW baroclinic wave x1.{n_cells} {n_lev} levels fp64 dt={dt:g}s S={args.scalars}",
                    "cells_per_gpu": n_cells // world,
                    "decomposition": "single block" if world == 1 else f"{world} blocks (recursive coordinate bisection), one per GPU, reference halo lists",
-                   "scaling_note": "BASELINE.json names one mesh per GPU count (x1.40962 @1, x1.163842 @2/4, x1.655362 @8); "
-                                   "compare cell_columns_per_s across N, steps/s only within one mesh",
+                   "scaling_note": "BASELINE.json names one mesh per GPU count (x1.40962 @1, x1.163842 @2/4, x1.655362 @8), so "
+                                   "`value` is the one BASELINE throughput figure that is comparable across N: cell-column "
+                                   "updates/s = nCells x steps/s; steps_per_s and sdpd are reported beside it",
                    "l2": "no flush: every step streams the block's fields (>= 3.5 GB at 40962 cells x 55 levels), >> 126 MB L2",
                    "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"},
     }
@@ -155,16 +159,17 @@ def reference_arm(args, rank, world):
     for _ in range(steps):
         o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
     el = time.time() - t0
-    v = frac * steps / el
+    sps = frac * steps / el                       # whole-mesh steps/s
+    v = n_cells * sps                             # cell-column updates/s (the line's unit)
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
     line = line_common(args, n_cells, n_lev, dt, args.gpus)
     line["config"]["implementation"] = "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build"
     line.update({
-        "impl": "reference", "value": v, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 / v,
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+        "impl": "reference", "value": v, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 / sps,
+        "cpu_baseline": {"value": v, "unit": "cell-columns/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} full atm_srk3 steps on {sample_what}"},
-        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sdpd": dt * v, "cell_columns_per_s": n_cells * v,
+        "e2e": {"value": v, "unit": "cell-columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_per_s": sps, "sdpd": dt * sps, "cell_columns_per_s": v,
     })
     print(json.dumps(line))
 
@@ -245,7 +250,8 @@ def main():
     barrier()
     launches = int(sum_over_ranks(g.kernel_launch_count() - l0))
     ms_per_step = max_over_ranks(ms) / args.steps
-    value = 1e3 / ms_per_step
+    steps_per_s = 1e3 / ms_per_step
+    value = n_cells * steps_per_s                 # cell-column updates/s over all ranks (the line's unit)
     mm = g.summarize_timestep()
     if dist is not None:
         t = torch.tensor([-mm[0], mm[1], -mm[2], mm[3]], dtype=torch.float64)
@@ -287,7 +293,7 @@ def main():
             e2e_step()
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-        e2e = {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+        e2e = {"value": n_cells / e2e_s, "unit": "cell-columns/s", "steps_per_s": 1.0 / e2e_s, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": 1e3 * e2e_s}
     clocks = sampler.stop()
 
@@ -327,7 +333,7 @@ def main():
         while n < 3 or (time.time() - t0 < 10.0 and n < 20):
             o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); n += 1
         el = time.time() - t0
-        cpu = {"value": n / el, "unit": "steps/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())),
+        cpu = {"value": n_cells * n / el, "unit": "cell-columns/s", "steps_per_s": n / el, "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())),
                "kind": "port", "sample": f"{n} full atm_srk3 steps of the same workload (C++/OpenMP restatement, not the Fortran build)"}
 
     if rank != 0:
@@ -342,7 +348,7 @@ def main():
         "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs,
                           "frac_of_measured_peak": step_gbs / (peak * world), "frac_of_nominal_8TBs": step_gbs / (8000.0 * world)},
         "cpu_baseline": cpu,
-        "sdpd": dt * value, "cell_columns_per_s": n_cells * value,
+        "steps_per_s": steps_per_s, "sdpd": dt * steps_per_s, "cell_columns_per_s": value,
         "minmax_w_u": list(minmax),
         "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:14]},
     })
