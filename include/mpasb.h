@@ -63,6 +63,7 @@ typedef struct mpasb_config {
     double config_h_theta_eddy_visc2, config_h_theta_eddy_visc4, config_v_theta_eddy_visc2;
     double config_apvm_upwinding, config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days;
     double cf1, cf2, cf3, sphere_radius;
+    int on_a_sphere;                        /* mesh attribute (logical), mpas_vector_reconstruction.F:250 */
 } mpasb_config;
 
 typedef struct mpasb_handle_s* mpasb_handle;
@@ -93,6 +94,13 @@ int  mpasb_synchronize(mpasb_handle h);
  * atm_compute_solve_diagnostics without rk_step (mpas_atm_core.F:515-527). */
 int  mpasb_init_coupled_diagnostics(mpasb_handle h);
 int  mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt);
+
+/* mpas_reconstruct (src/operators/mpas_vector_reconstruction.F:205-330): uReconstructX/Y/Z/Zonal/Meridional from u of
+ * the given time level through the init-time field coeffs_reconstruct; mpasb_step already ends with the call of
+ * TI:1606 (time level 2, owned cells), mpas_atm_core.F:543 is (1, 0) at start-up.
+ * atm_compute_output_diagnostics (mpas_atm_core.F:901-950): theta, rho, pressure of the given time level. */
+int  mpasb_reconstruct(mpasb_handle h, int time_level, int include_halos);
+int  mpasb_compute_output_diagnostics(mpasb_handle h, int time_level);
 
 /* Kernel-level entry points, one per *_work routine, operating on the
  * device-resident fields of the handle (parity tests drive one at a time). */

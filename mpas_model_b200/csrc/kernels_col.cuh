@@ -1033,3 +1033,84 @@ __global__ void __launch_bounds__(CW_THREADS) k2_scalars_cell(const Dev D, real 
         ST(qn, i, sel(k_lt_nl, val, 0.0));
     }
 }
+
+// ------------------------------------------------------------------ atm_compute_vert_imp_coefs_work  TI:2225-2366 (block-tiled)
+// Same tiling as k3_acoustic_cell.  Phase 1: each warp computes the acoustic coefficients cofwr, cofwz, coftz, cofwt and
+// the tridiagonal rows (a, b, c) of VIC_COLS/VIC_WARPS columns, lane = level pair, vertical neighbours by shuffle.
+// Phase 2: ONE warp runs the LU recurrence alpha = 1/(b - a*gamma), gamma = c*alpha (TI:2352-2355) of all VIC_COLS
+// columns at once, lane = column, rows of odd stride in shared memory (alpha/gamma overwrite b/c).
+// Phase 3: the warps write alpha_tri and gamma_tri.  Operation order inside a column is the reference's.
+#define VIC_COLS 32
+#define VIC_WARPS 8
+__global__ void __launch_bounds__(VIC_WARPS * 32) k3_vert_imp_coefs(const Dev D, real dtseps, real c2, real rcv) {
+    extern __shared__ __align__(16) real smv[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    const int S = LDK | 1;
+    real* s_a = smv;
+    real* s_b = s_a + VIC_COLS * S;
+    real* s_c = s_b + VIC_COLS * S;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < LDK;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
+    const int base = blockIdx.x * VIC_COLS;
+    const r2 fzm = LD(D.fzm, 0), fzp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0), rdzu = LD(D.rdzu, 0);
+    const r2 cofrz = dtseps * rdzw;
+    if (blockIdx.x == 0 && wib == 0) ST(D.cofrz, 0, sel(k_lt_nl, cofrz, 0.0));
+    const r2 rdzwm = up1(rdzw), cofrzm = up1(cofrz);
+    for (int cc = 0; cc < VIC_COLS / VIC_WARPS; cc++) {
+        const int c = cc * VIC_WARPS + wib;
+        const int i = base + c;
+        if (i >= D.nCellsSolve) continue;                   // warp-uniform
+        const r2 zz = LD(D.zz, i), p = LD(D.exner, i), t = LD(D.theta_m_2, i), cqw = LD(D.cqw, i);
+        const r2 qtotal = LD(D.qtot, i), rb = LD(D.rho_base, i), rtb = LD(D.rtheta_base, i), rt = LD(D.rtheta_p, i), pb = LD(D.exner_base, i);
+        const r2 zzm = up1(zz);
+        const r2 zint = fzm * zz + fzp * zzm;
+        const r2 cofwr = sel(k_mid, .5 * dtseps * GRAVITY * zint, 0.0);
+        const r2 cofwz = sel(k_mid, dtseps * c2 * zint
+                                    * rdzu * cqw * (fzm * p + fzp * up1(p)), 0.0);
+        const r2 coftz = sel(k_mid, dtseps * (fzm * t + fzp * up1(t)), 0.0);
+        const r2 cofwt = sel(k_lt_nl, .5 * dtseps * rcv * zz * GRAVITY * rb / (1. + qtotal)
+                                      * p / ((rtb + rt) * pb), 0.0);
+        const r2 coftzm = up1(coftz), coftzp = dn1(coftz), cofwtm = up1(cofwt);
+        const r2 a = -cofwz * coftzm * rdzwm * zzm
+                     + cofwr * cofrzm
+                     - cofwtm * coftzm * rdzwm;
+        const r2 b = 1.
+                     + cofwz * (coftz * rdzw * zz
+                                + coftz * rdzwm * zzm)
+                     - coftz * (cofwt * rdzw
+                                - cofwtm * rdzwm)
+                     + cofwr * (cofrz - cofrzm);
+        const r2 cc_ = -cofwz * coftzp * rdzw * zz
+                       - cofwr * cofrz
+                       + cofwt * coftzp * rdzw;
+        if (act) {
+            const int o = c * S + k0;
+            s_a[o] = a.x; s_a[o + 1] = a.y; s_b[o] = b.x; s_b[o + 1] = b.y; s_c[o] = cc_.x; s_c[o + 1] = cc_.y;
+        }
+        ST(D.cofwr, i, cofwr); ST(D.cofwz, i, cofwz); ST(D.coftz, i, coftz); ST(D.cofwt, i, cofwt);
+        ST(D.a_tri, i, sel(k_mid, a, 0.0));
+    }
+    __syncthreads();
+    if (wib == 0 && lane < VIC_COLS && base + lane < D.nCellsSolve) {
+        const real* av = s_a + lane * S; real* bv = s_b + lane * S; real* cv = s_c + lane * S;
+        real g = 0.;
+#pragma unroll 4
+        for (int kk = 1; kk < nl; kk++) {
+            const real al = 1. / (bv[kk] - av[kk] * g);
+            g = cv[kk] * al;
+            bv[kk] = al; cv[kk] = g;
+        }
+    }
+    __syncthreads();
+    for (int cc = 0; cc < VIC_COLS / VIC_WARPS; cc++) {
+        const int c = cc * VIC_WARPS + wib;
+        const int i = base + c;
+        if (i >= D.nCellsSolve) continue;
+        const int o = c * S + (int)kc;
+        ST(D.alpha_tri, i, sel(k_mid, mk2(s_b[o], s_b[o + 1]), 0.0));
+        ST(D.gamma_tri, i, sel(k_mid, mk2(s_c[o], s_c[o + 1]), 0.0));
+    }
+}

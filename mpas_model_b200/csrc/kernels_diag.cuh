@@ -161,6 +161,38 @@ __global__ void k_scale_from(real* __restrict__ y, const real* __restrict__ x, r
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) y[t] = x[t] * s;
 }
+// One launch for a whole list of element-wise column copies/accumulations (atm_rk_integration_setup, TI:1930-2039, and
+// atm_rk_dynamics_substep_finish, TI:7013-7191): blockIdx.y selects the segment, blockIdx.x strides over its
+// 16-byte element pairs.  op 0: d = s;  1: d = s + d;  2: d = s, then s = d * scale;  3: d = s + d, then s = d * scale.
+#define SEG_MAX 16
+struct Seg { real* d; real* s; unsigned n2; int op; };        // n2 = number of 16-byte pairs (LDK is even)
+struct SegList { Seg seg[SEG_MAX]; real scale; };
+#define SEG_BLOCKS 296                                        // blocks per segment: 2 per SM
+__global__ void __launch_bounds__(256) k_segments(const SegList L) {
+    const Seg g = L.seg[blockIdx.y];
+#ifdef MPASB_SINGLE
+    typedef float2 v2;
+#else
+    typedef double2 v2;
+#endif
+    v2* __restrict__ d = reinterpret_cast<v2*>(g.d);
+    v2* __restrict__ s = reinterpret_cast<v2*>(g.s);
+    const unsigned stride = gridDim.x * blockDim.x;
+    if (g.op == 0) {
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < g.n2; t += stride) d[t] = s[t];
+    } else if (g.op == 1) {
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < g.n2; t += stride) {
+            const v2 x = s[t], y = d[t]; v2 r; r.x = x.x + y.x; r.y = x.y + y.y; d[t] = r;
+        }
+    } else {
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < g.n2; t += stride) {
+            v2 r = s[t];
+            if (g.op == 3) { const v2 y = d[t]; r.x = r.x + y.x; r.y = r.y + y.y; }
+            d[t] = r;
+            v2 q; q.x = r.x * L.scale; q.y = r.y * L.scale; s[t] = q;
+        }
+    }
+}
 __global__ void k_fill(real* __restrict__ y, real v, size_t n) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) y[t] = v;

@@ -20,6 +20,7 @@
 #include "kernels_diag.cuh"
 #include "kernels_transport.cuh"
 #include "kernels_col.cuh"
+#include "kernels_output.cuh"
 #include "halo.cuh"
 
 enum { T_REAL = 0, T_INT = 1 };
@@ -66,12 +67,12 @@ static int inner_dense1(const H* h, int in) {
         case IN_ONE: return 1; case IN_NL: return d.nVertLevels; case IN_NL1: return d.nVertLevels + 1;
         case IN_ME: return d.maxEdges; case IN_ME2: return d.maxEdges2; case IN_VD: return d.vertexDegree;
         case IN_TWO: return 2; case IN_F15: return 15; case IN_NL1_ME: return d.nVertLevels + 1;
-        case IN_S_NL: return d.num_scalars; case IN_NL_TWO: return d.nVertLevels;
+        case IN_S_NL: return d.num_scalars; case IN_NL_TWO: return d.nVertLevels; case IN_THREE_ME: return 3;
     }
     return 1;
 }
 static int inner_dense2(const H* h, int in) {
-    switch (in) { case IN_NL1_ME: return h->dims.maxEdges; case IN_S_NL: return h->dims.nVertLevels; case IN_NL_TWO: return 2; default: return 1; }
+    switch (in) { case IN_NL1_ME: return h->dims.maxEdges; case IN_S_NL: return h->dims.nVertLevels; case IN_NL_TWO: return 2; case IN_THREE_ME: return h->dims.maxEdges; default: return 1; }
 }
 static size_t outer_of(const H* h, int loc) {
     switch (loc) { case LOC_CELL: return (size_t)h->dims.nCells + 1; case LOC_EDGE: return (size_t)h->dims.nEdges + 1;
@@ -84,7 +85,7 @@ static size_t dev_count_of(const H* h, int loc, int in) {
         case IN_NL1_ME: return o * h->dims.maxEdges * L;
         case IN_S_NL: return o * L * h->dims.num_scalars;
         case IN_NL_TWO: return o * L * 2;
-        default: return o * inner_dense1(h, in);
+        default: return o * inner_dense1(h, in) * inner_dense2(h, in);
     }
 }
 
@@ -291,20 +292,33 @@ struct KScope {
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
 
-static void copy_cols(H* h, real* dst, const real* src, size_t ncols) {      // [0, ncols) columns, garbage column untouched
-    cudaMemcpyAsync(dst, src, ncols * h->D.LDK * sizeof(real), cudaMemcpyDeviceToDevice, h->stream);
-}
 
 // ------------------------------------------------------------------ routines
+struct SegBuilder {       // collects the column ranges of one routine into one k_segments launch
+    H* h; SegList L; int n = 0;
+    explicit SegBuilder(H* h_) : h(h_) { L.scale = 1.0; }
+    void add(real* d, const real* s, size_t ncols, int op = 0) {
+        if (n == SEG_MAX) flush();
+        L.seg[n].d = d; L.seg[n].s = const_cast<real*>(s); L.seg[n].n2 = (unsigned)(ncols * h->D.LDK / 2); L.seg[n].op = op; n++;
+    }
+    void flush() {
+        if (!n) return;
+        KScope ks_(h, "k:k_segments");
+        k_segments<<<dim3(SEG_BLOCKS, n), 256, 0, h->stream>>>(L);
+        h->launches++; n = 0;
+    }
+};
 static void rk_integration_setup(H* h) {       // TI:1930-2039
     Scope sc(h, "atm_rk_integration_setup");
     Dev& D = h->D; const size_t nC = D.nCells, nE = D.nEdges;
-    copy_cols(h, D.ru_save, D.ru, nE); copy_cols(h, D.u_2, D.u, nE);
-    copy_cols(h, D.rtheta_p_save, D.rtheta_p, nC); copy_cols(h, D.rho_p_save, D.rho_p, nC);
-    copy_cols(h, D.theta_m_2, D.theta_m, nC); copy_cols(h, D.rho_zz_2, D.rho_zz, nC);
-    copy_cols(h, D.rho_zz_old_split, D.rho_zz, nC);
-    copy_cols(h, D.rw_save, D.rw, nC); copy_cols(h, D.w_2, D.w, nC);
-    for (int s = 0; s < D.num_scalars; s++) copy_cols(h, D.scalars_2 + s * D.cellPlane, D.scalars + s * D.cellPlane, nC);
+    SegBuilder sb(h);
+    sb.add(D.ru_save, D.ru, nE); sb.add(D.u_2, D.u, nE);
+    sb.add(D.rtheta_p_save, D.rtheta_p, nC); sb.add(D.rho_p_save, D.rho_p, nC);
+    sb.add(D.theta_m_2, D.theta_m, nC); sb.add(D.rho_zz_2, D.rho_zz, nC);
+    sb.add(D.rho_zz_old_split, D.rho_zz, nC);
+    sb.add(D.rw_save, D.rw, nC); sb.add(D.w_2, D.w, nC);
+    for (int s = 0; s < D.num_scalars; s++) sb.add(D.scalars_2 + s * D.cellPlane, D.scalars + s * D.cellPlane, nC);
+    sb.flush();
     cudaMemsetAsync(D.theta_m_2 + nC * D.LDK, 0, D.LDK * sizeof(real), h->stream);          // TI:1987
 }
 static void compute_moist_coefficients(H* h) { // TI:2042-2146
@@ -317,6 +331,15 @@ static void compute_vert_imp_coefs(H* h, real dts) {   // TI:2225-2366
     const real dtseps = .5 * dts * (1. + h->cfg.config_epssm);
     const real rcv = rgas / (cp - rgas);
     const real c2 = cp * rcv;
+    if (h->colwarp) {
+        const size_t smem3 = (size_t)3 * VIC_COLS * (h->D.LDK | 1) * sizeof(real);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k3_vert_imp_coefs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
+        KScope ks_(h, "k:k3_vert_imp_coefs");
+        k3_vert_imp_coefs<<<(unsigned)((h->D.nCellsSolve + VIC_COLS - 1) / VIC_COLS), VIC_WARPS * 32, smem3, h->stream>>>(h->D, dtseps, c2, rcv);
+        h->launches++;
+        return;
+    }
     const size_t smem = (size_t)9 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_vert_imp_coefs, h->D.nCellsSolve, smem, h->D, dtseps, c2, rcv);
 }
@@ -445,24 +468,19 @@ static void rk_dynamics_substep_finish(H* h, int dynamics_substep, int dynamics_
     Scope sc(h, "atm_rk_dynamics_substep_finish");
     Dev& D = h->D; const size_t nC = D.nCells, nE = D.nEdges, L = D.LDK;
     cudaMemsetAsync(D.theta_m + nC * L, 0, L * sizeof(real), h->stream);                    // TI:7082
-    const real inv_dynamics_split = 1.0 / (real)dynamics_split;
+    SegBuilder sb(h);
+    sb.L.scale = 1.0 / (real)dynamics_split;                                                // inv_dynamics_split
     if (dynamics_substep < dynamics_split) {
-        copy_cols(h, D.ru_save, D.ru, nE); copy_cols(h, D.u, D.u_2, nE);
-        copy_cols(h, D.rtheta_p_save, D.rtheta_p, nC); copy_cols(h, D.rho_p_save, D.rho_p, nC);
-        copy_cols(h, D.theta_m, D.theta_m_2, nC); copy_cols(h, D.rho_zz, D.rho_zz_2, nC);
-        copy_cols(h, D.rw_save, D.rw, nC); copy_cols(h, D.w, D.w_2, nC);
+        sb.add(D.ru_save, D.ru, nE); sb.add(D.u, D.u_2, nE);
+        sb.add(D.rtheta_p_save, D.rtheta_p, nC); sb.add(D.rho_p_save, D.rho_p, nC);
+        sb.add(D.theta_m, D.theta_m_2, nC); sb.add(D.rho_zz, D.rho_zz_2, nC);
+        sb.add(D.rw_save, D.rw, nC); sb.add(D.w, D.w_2, nC);
     }
-    if (dynamics_substep == 1) {
-        copy_cols(h, D.ruAvg_split, D.ruAvg, nE); copy_cols(h, D.wwAvg_split, D.wwAvg, nC);
-    } else {
-        LAUNCH1D(k_add_into, nE * L, D.ruAvg_split, D.ruAvg, nE * L);
-        LAUNCH1D(k_add_into, nC * L, D.wwAvg_split, D.wwAvg, nC * L);
-    }
-    if (dynamics_substep == dynamics_split) {
-        LAUNCH1D(k_scale_from, nE * L, D.ruAvg, D.ruAvg_split, inv_dynamics_split, nE * L);
-        LAUNCH1D(k_scale_from, nC * L, D.wwAvg, D.wwAvg_split, inv_dynamics_split, nC * L);
-        copy_cols(h, D.rho_zz, D.rho_zz_old_split, nC);
-    }
+    // *_split = (first substep ? Avg : *_split + Avg); on the last substep also Avg = *_split * inv_dynamics_split
+    const int op = (dynamics_substep == 1 ? 0 : 1) + (dynamics_substep == dynamics_split ? 2 : 0);
+    sb.add(D.ruAvg_split, D.ruAvg, nE, op); sb.add(D.wwAvg_split, D.wwAvg, nC, op);
+    if (dynamics_substep == dynamics_split) sb.add(D.rho_zz, D.rho_zz_old_split, nC);
+    sb.flush();
 }
 static void advance_scalars(H* h, real dt, int rk_step) {     // TI:3575-3855
     Scope sc(h, "atm_advance_scalars");
@@ -525,6 +543,23 @@ static void init_coupled_diagnostics(H* h) {                  // TI:6776-7010
     LAUNCH(k_initcd_cell1, h->D.nCells, 0, h->D, rv / rgas, rcv, rgas / p0);
     LAUNCH(k_initcd_edge, h->D.nEdges, 0, h->D);
     LAUNCH(k_initcd_cell2, h->D.nCells, 0, h->D);
+}
+
+// mpas_reconstruct_2d (mpas_vector_reconstruction.F:205-330): cell-centre velocity from the edge-normal component
+static void reconstruct(H* h, int time_lev, int include_halos) {
+    Scope sc(h, "mpas_reconstruct");
+    const Dev& D = h->D;
+    const real* u = time_lev == 2 ? D.u_2 : D.u;
+    const int n = include_halos ? D.nCells : D.nCellsSolve;
+    if (h->colwarp) LAUNCHW(k2_reconstruct, n, D, u, n, h->cfg.on_a_sphere);
+    else LAUNCH(k_reconstruct, n, 0, D, u, n, h->cfg.on_a_sphere);
+}
+// atm_compute_output_diagnostics (mpas_atm_core.F:901-950): theta, rho, pressure for the history stream
+static void compute_output_diagnostics(H* h, int time_lev) {
+    Scope sc(h, "atm_compute_output_diagnostics");
+    const Dev& D = h->D;
+    const real* qv = (time_lev == 2 ? D.scalars_2 : D.scalars) + (size_t)D.index_qv * D.cellPlane;
+    LAUNCH(k_output_diagnostics, D.nCells, 0, D, time_lev == 2 ? D.theta_m_2 : D.theta_m, time_lev == 2 ? D.rho_zz_2 : D.rho_zz, qv, rv / rgas);
 }
 
 // ------------------------------------------------------------------ halo exchange (mpas_halo.F:498-846)
@@ -605,6 +640,7 @@ static int srk3(H* h, real dt) {
             if (rk_step < 3) if (exchange(h, "dynamics:scalars")) return 1;
         }
     }
+    reconstruct(h, 2, 0);                         // TI:1596-1611: uReconstruct* from u (time level 2), owned cells
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -645,6 +681,8 @@ extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
 #define ENTRY(body) { cudaSetDevice(h->device); body; CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
 extern "C" int mpasb_init_coupled_diagnostics(mpasb_handle h) ENTRY(init_coupled_diagnostics(h))
 extern "C" int mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt) ENTRY(compute_solve_diagnostics(h, dt, 1, 0))
+extern "C" int mpasb_reconstruct(mpasb_handle h, int time_level, int include_halos) ENTRY(reconstruct(h, time_level, include_halos))
+extern "C" int mpasb_compute_output_diagnostics(mpasb_handle h, int time_level) ENTRY(compute_output_diagnostics(h, time_level))
 extern "C" int mpasb_k_rk_integration_setup(mpasb_handle h) ENTRY(rk_integration_setup(h))
 extern "C" int mpasb_k_compute_moist_coefficients(mpasb_handle h) ENTRY(compute_moist_coefficients(h))
 extern "C" int mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts) ENTRY(compute_vert_imp_coefs(h, dts))

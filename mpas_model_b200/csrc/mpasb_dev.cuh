@@ -17,7 +17,7 @@ typedef double real;
 #endif
 
 enum { LOC_CELL = 0, LOC_EDGE = 1, LOC_VERTEX = 2, LOC_LEVS = 3 };
-enum { IN_ONE, IN_NL, IN_NL1, IN_ME, IN_ME2, IN_VD, IN_TWO, IN_F15, IN_NL1_ME, IN_S_NL, IN_NL_TWO };
+enum { IN_ONE, IN_NL, IN_NL1, IN_ME, IN_ME2, IN_VD, IN_TWO, IN_F15, IN_NL1_ME, IN_S_NL, IN_NL_TWO, IN_THREE_ME };
 
 #define FIELD_REAL(name) real* name; real* name##_2;
 #define FIELD_INT(name) int* name;

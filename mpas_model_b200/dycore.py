@@ -49,7 +49,7 @@ _CFG_REAL = ("config_epssm", "config_smdiv", "config_len_disp", "config_coef_3rd
 
 
 class Config(C.Structure):
-    _fields_ = [(n, C.c_int) for n in _CFG_INT] + [(n, C.c_double) for n in _CFG_REAL]
+    _fields_ = [(n, C.c_int) for n in _CFG_INT] + [(n, C.c_double) for n in _CFG_REAL] + [("on_a_sphere", C.c_int)]
 
 
 def make_dims(d: dict) -> Dims:
@@ -73,6 +73,7 @@ def make_config(cfg: dict, d: dict) -> Config:
     for n in _CFG_REAL:
         setattr(c, n, float(d[n] if n in ("cf1", "cf2", "cf3", "sphere_radius") else cfg.get(n, 0.0)))
     c.config_print_global_minmax_vel = 1
+    c.on_a_sphere = int(cfg.get("on_a_sphere", 1))
     return c
 
 
@@ -208,6 +209,14 @@ class Dycore(Backend):
 
     def mpas_pool_shift_time_levels(self):
         self._check(self.lib.mpasb_shift_time_levels(self._h), "shift_time_levels")
+
+    def mpas_reconstruct(self, time_level=1, include_halos=False):
+        """mpas_vector_reconstruction.F:205 on ``u`` of ``time_level`` -> ``uReconstruct*``."""
+        self._check(self.lib.mpasb_reconstruct(self._h, C.c_int(time_level), C.c_int(int(include_halos))), "mpas_reconstruct")
+
+    def atm_compute_output_diagnostics(self, time_level=1):
+        """mpas_atm_core.F:901: ``theta``, ``rho``, ``pressure`` of ``time_level``."""
+        self._check(self.lib.mpasb_compute_output_diagnostics(self._h, C.c_int(time_level)), "atm_compute_output_diagnostics")
 
     def summarize_timestep(self):
         out = (self.creal * 4)()

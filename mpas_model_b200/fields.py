@@ -39,7 +39,7 @@ def host_shape(fd: FieldDef, dims) -> tuple:
     inner = {
         "ONE": (), "NL": (nl,), "NL1": (nl + 1,), "ME": (dims.maxEdges,), "ME2": (dims.maxEdges2,),
         "VD": (dims.vertexDegree,), "TWO": (2,), "F15": (15,), "NL1_ME": (dims.maxEdges, nl + 1),
-        "S_NL": (nl, dims.num_scalars), "NL_TWO": (2, nl),
+        "S_NL": (nl, dims.num_scalars), "NL_TWO": (2, nl), "THREE_ME": (dims.maxEdges, 3),
     }[fd.inner]
     outer = {"CELL": (dims.nCells + 1,), "EDGE": (dims.nEdges + 1,), "VERTEX": (dims.nVertices + 1,), "LEVS": ()}[fd.loc]
     return outer + inner

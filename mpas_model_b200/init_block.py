@@ -161,4 +161,7 @@ def init_block(d: dict, cfg: dict) -> dict:
     d["specZoneMaskEdge"] = np.zeros(nE + 1)
     d["bdyMaskCell"] = np.zeros(nC + 1, dtype=np.int32)
     d["bdyMaskEdge"] = np.zeros(nE + 1, dtype=np.int32)
+    # mpas_atm_core.F:534-535: mpas_rbf_interp_initialize (-> mpas_initialize_vectors), mpas_init_reconstruct -> coeffs_reconstruct (owned cells)
+    from .reconstruct import mpas_init_reconstruct
+    mpas_init_reconstruct(d)
     return d

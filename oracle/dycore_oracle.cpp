@@ -37,7 +37,7 @@ struct I1 { int* p; inline int& operator()(int i) const { return p[i - 1]; } };
 struct I2 { int* p; int n1; inline int& operator()(int k, int i) const { return p[(size_t)(i - 1) * n1 + (k - 1)]; } };
 
 enum Loc { CELL, EDGE, VERTEX, LEVS };
-enum Inner { ONE, NL, NL1, ME, ME2, VD, TWO, F15, NL1_ME, S_NL, NL_TWO };
+enum Inner { ONE, NL, NL1, ME, ME2, VD, TWO, F15, NL1_ME, S_NL, NL_TWO, THREE_ME };
 enum Type { REAL, INT };
 enum Target { NONE, LOCAL, T_CELL, T_EDGE, T_VERTEX };
 struct FieldDef { const char* name; Loc loc; Inner inner; int levels; Type type; };
@@ -68,12 +68,12 @@ struct Block {
             case ONE: return 1; case NL: return d.nVertLevels; case NL1: return d.nVertLevels + 1;
             case ME: return d.maxEdges; case ME2: return d.maxEdges2; case VD: return d.vertexDegree;
             case TWO: return 2; case F15: return 15; case NL1_ME: return d.nVertLevels + 1;
-            case S_NL: return d.num_scalars; case NL_TWO: return d.nVertLevels;
+            case S_NL: return d.num_scalars; case NL_TWO: return d.nVertLevels; case THREE_ME: return 3;
         }
         return 1;
     }
     int inner2(Inner in) const {
-        switch (in) { case NL1_ME: return d.maxEdges; case S_NL: return d.nVertLevels; case NL_TWO: return 2; default: return 1; }
+        switch (in) { case NL1_ME: return d.maxEdges; case S_NL: return d.nVertLevels; case NL_TWO: return 2; case THREE_ME: return d.maxEdges; default: return 1; }
     }
     long outer(Loc l) const {
         switch (l) { case CELL: return d.nCells + 1; case EDGE: return d.nEdges + 1; case VERTEX: return d.nVertices + 1; case LEVS: return 1; }
@@ -1436,6 +1436,68 @@ static void atm_init_coupled_diagnostics(Block& b, int time_lev) {
         }
 }
 
+// ============================================================ mpas_vector_reconstruction.F:205-330 (mpas_reconstruct_2d)
+static void mpas_reconstruct(Block& b, int time_lev, bool includeHalos) {
+    const int nVertLevels = b.d.nVertLevels;
+    const int nCells = includeHalos ? b.d.nCells : b.d.nCellsSolve;
+    I1 nEdgesOnCell = b.i1("nEdgesOnCell"); I2 edgesOnCell = b.i2("edgesOnCell");
+    A3 coeffs_reconstruct = b.r3("coeffs_reconstruct");
+    A1 latCell = b.r1("latCell"), lonCell = b.r1("lonCell");
+    A2 u = b.r2("u", time_lev);
+    A2 uReconstructX = b.r2("uReconstructX"), uReconstructY = b.r2("uReconstructY"), uReconstructZ = b.r2("uReconstructZ");
+    A2 uReconstructZonal = b.r2("uReconstructZonal"), uReconstructMeridional = b.r2("uReconstructMeridional");
+    #pragma omp parallel for
+    for (int iCell = 1; iCell <= nCells; iCell++) {
+        for (int k = 1; k <= nVertLevels; k++) {
+            uReconstructX(k, iCell) = 0.0;
+            uReconstructY(k, iCell) = 0.0;
+            uReconstructZ(k, iCell) = 0.0;
+        }
+        for (int i = 1; i <= nEdgesOnCell(iCell); i++) {
+            const int iEdge = edgesOnCell(i, iCell);
+            for (int k = 1; k <= nVertLevels; k++) {
+                uReconstructX(k, iCell) = uReconstructX(k, iCell) + coeffs_reconstruct(1, i, iCell) * u(k, iEdge);
+                uReconstructY(k, iCell) = uReconstructY(k, iCell) + coeffs_reconstruct(2, i, iCell) * u(k, iEdge);
+                uReconstructZ(k, iCell) = uReconstructZ(k, iCell) + coeffs_reconstruct(3, i, iCell) * u(k, iEdge);
+            }
+        }
+    }
+    if (b.c.on_a_sphere) {
+        #pragma omp parallel for
+        for (int iCell = 1; iCell <= nCells; iCell++) {
+            const real clat = std::cos(latCell(iCell)), slat = std::sin(latCell(iCell));
+            const real clon = std::cos(lonCell(iCell)), slon = std::sin(lonCell(iCell));
+            for (int k = 1; k <= nVertLevels; k++) {
+                uReconstructZonal(k, iCell) = -uReconstructX(k, iCell) * slon + uReconstructY(k, iCell) * clon;
+                uReconstructMeridional(k, iCell) = -(uReconstructX(k, iCell) * clon + uReconstructY(k, iCell) * slon) * slat
+                                                   + uReconstructZ(k, iCell) * clat;
+            }
+        }
+    } else {
+        for (int iCell = 1; iCell <= nCells; iCell++)
+            for (int k = 1; k <= nVertLevels; k++) {
+                uReconstructZonal(k, iCell) = uReconstructX(k, iCell);
+                uReconstructMeridional(k, iCell) = uReconstructY(k, iCell);
+            }
+    }
+}
+
+// ============================================================ mpas_atm_core.F:901-950
+static void atm_compute_output_diagnostics(Block& b, int time_lev) {
+    const int nVertLevels = b.d.nVertLevels, nCells = b.d.nCells, index_qv = b.d.index_qv;
+    A2 theta_m = b.r2("theta_m", time_lev), rho_zz = b.r2("rho_zz", time_lev), zz = b.r2("zz");
+    A3 scalars = b.r3("scalars", time_lev);
+    A2 theta = b.r2("theta"), rho = b.r2("rho"), pressure_p = b.r2("pressure_p"), pressure_base = b.r2("pressure_base"),
+       pressure = b.r2("pressure");
+    #pragma omp parallel for
+    for (int iCell = 1; iCell <= nCells; iCell++)
+        for (int k = 1; k <= nVertLevels; k++) {
+            theta(k, iCell) = theta_m(k, iCell) / (1. + rvord * scalars(index_qv, k, iCell));
+            rho(k, iCell) = rho_zz(k, iCell) * zz(k, iCell);
+            pressure(k, iCell) = pressure_base(k, iCell) + pressure_p(k, iCell);
+        }
+}
+
 // ============================================================ TI:7013-7191
 static void atm_rk_dynamics_substep_finish(Block& b, int dynamics_substep, int dynamics_split) {
     const int nVertLevels = b.d.nVertLevels;
@@ -1612,6 +1674,7 @@ static void atm_srk3(Domain& dom, real dt) {
             if (rk_step < 3) exchange_halo_group(dom, "dynamics:scalars");
         }
     }
+    FOR_BLOCKS mpas_reconstruct(*bp, 2, false);                                   // TI:1596-1611
 }
 
 // ============================================================ C API (ctypes)
@@ -1695,6 +1758,8 @@ void oracle_rk_dynamics_substep_finish(void* h, int s, int n) { atm_rk_dynamics_
 void oracle_advance_scalars(void* h, double dt, int rk_step) { atm_advance_scalars(*(Block*)h, dt, rk_step); }
 // the monotonic transport split at its two exchange points (TI:4155, TI:4568), for drivers that
 // perform the halo exchanges themselves (mpas_model_b200/multigpu.py: srk3_host_exchange)
+void oracle_reconstruct(void* h, int time_lev, int include_halos) { mpas_reconstruct(*(Block*)h, time_lev, include_halos != 0); }
+void oracle_compute_output_diagnostics(void* h, int time_lev) { atm_compute_output_diagnostics(*(Block*)h, time_lev); }
 void oracle_advance_scalars_mono_pre(void* h, double dt) { mono_pre_update(*(Block*)h, dt); }
 void oracle_advance_scalars_mono_a(void* h, double dt, int s) {
     Block& b = *(Block*)h;

@@ -81,6 +81,10 @@ class OracleDycore(Backend):
     def atm_srk3(self, dt, itimestep=1): step([self], dt)
     atm_timestep = atm_srk3
     def mpas_pool_shift_time_levels(self): self.lib.oracle_shift_time_levels(self._h)
+    def mpas_reconstruct(self, time_level=1, include_halos=False):
+        self.lib.oracle_reconstruct(self._h, C.c_int(time_level), C.c_int(int(include_halos)))
+    def atm_compute_output_diagnostics(self, time_level=1):
+        self.lib.oracle_compute_output_diagnostics(self._h, C.c_int(time_level))
 
     def summarize_timestep(self):
         out = (C.c_double * 4)()

@@ -68,7 +68,8 @@ def test_every_routine_in_sequence(pair):
         diffs = compare_all(o, g)
         worst = max(diffs.items(), key=lambda kv: kv[1])
         report.append((label, worst))
-        uses_pow = label.startswith("recover_large_step_variables") and label.endswith("3)")
+        # pow() in exner (rk 3), cos/sin of lat/lon in the zonal/meridional rotation of mpas_reconstruct
+        uses_pow = (label.startswith("recover_large_step_variables") and label.endswith("3)")) or label.startswith("mpas_reconstruct")
         if not g.strict_arithmetic():
             assert worst[1] <= TOL_ROUTINE_FAST, (label, worst)
         elif uses_pow:
@@ -112,6 +113,32 @@ def test_one_step(pair):
         assert r <= TOL_STEP, (name, r)
     mo, mg = o.summarize_timestep(), g.summarize_timestep()
     assert np.allclose(mo, mg, rtol=1e-12, atol=0), (mo, mg)
+
+
+def test_reconstruct_and_output_diagnostics(pair):
+    """mpas_reconstruct (run by the step itself, TI:1606, and on its own at start-up,
+    mpas_atm_core.F:543) and atm_compute_output_diagnostics (mpas_atm_core.F:901) against the oracle."""
+    d, cfg, o, g = pair
+    o.load_block(d); g.load_block(d)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    names = ("uReconstructX", "uReconstructY", "uReconstructZ", "uReconstructZonal", "uReconstructMeridional")
+    for b in (o, g):
+        b.mpas_reconstruct(1, False)
+        b.atm_compute_output_diagnostics(1)
+    for n in names[:3]:
+        assert np.array_equal(g.get_array(n), o.get_array(n)), n            # same accumulation order: bit for bit
+    for n in names[3:] + ("theta", "rho", "pressure"):
+        assert rel_l2(g.get_array(n), o.get_array(n)) <= TOL_ROUTINE, n
+    assert 30.0 < g.get_array("uReconstructZonal").max() < 40.0             # the JW jet
+    o.atm_srk3(dt); g.atm_srk3(dt)                                          # the step ends with mpas_reconstruct(u level 2)
+    for n in names:
+        assert rel_l2(g.get_array(n), o.get_array(n)) <= TOL_STEP, n
+    for b in (o, g):
+        b.mpas_reconstruct(2, True)                                         # includeHalos variant (single block: same cells)
+        b.atm_compute_output_diagnostics(2)
+    for n in names + ("theta", "rho", "pressure"):
+        assert rel_l2(g.get_array(n), o.get_array(n)) <= TOL_STEP, n
 
 
 def test_ten_steps_and_invariants(pair):

@@ -84,3 +84,7 @@ def srk3_stepwise(backends, cfg, dt, after=None):
             call("advance_scalars", rk_t[rk - 1], rk)
         else:
             call("advance_scalars_mono", rk_t[rk - 1])
+    for b in backends:                      # TI:1596-1611
+        b.mpas_reconstruct(2, False)
+    if after:
+        after("mpas_reconstruct(2, False)")
