@@ -165,7 +165,7 @@ static int halo_build_plan(H* h, const GroupDef& gd, HaloGroupPlan& P) {
     return 0;
 }
 
-static int halo_exchange(H* h, const char* group) {
+static int halo_exchange(H* h, const char* group, cudaStream_t stream) {
     HaloState& hs = h->halo;
     const GroupDef* gd = nullptr;
     for (const GroupDef& g : group_table()) if (!strcmp(g.name, group)) gd = &g;
@@ -182,22 +182,22 @@ static int halo_exchange(H* h, const char* group) {
     if (!hs.comm) { h->err = "halo lists are set but mpasb_comm_init was not called"; return 1; }
     NcclApi* a = nccl_api();
     const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((P.max_seg + 255) / 256, 64));
-    if (P.n_pack) { k_halo_pack<<<dim3(gx, std::min(P.n_pack, 256)), 256, 0, h->stream>>>(P.d_pack, P.d_idx_send, P.d_sendbuf, P.n_pack); h->launches++; }
+    if (P.n_pack) { k_halo_pack<<<dim3(gx, std::min(P.n_pack, 256)), 256, 0, stream>>>(P.d_pack, P.d_idx_send, P.d_sendbuf, P.n_pack); h->launches++; }
     a->GroupStart();
     for (size_t p = 0; p < P.peers.size(); p++) {
-        if (P.recv_cnt[p]) a->Recv(P.d_recvbuf + P.recv_off[p], P.recv_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, h->stream);
-        if (P.send_cnt[p]) a->Send(P.d_sendbuf + P.send_off[p], P.send_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, h->stream);
+        if (P.recv_cnt[p]) a->Recv(P.d_recvbuf + P.recv_off[p], P.recv_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, stream);
+        if (P.send_cnt[p]) a->Send(P.d_sendbuf + P.send_off[p], P.send_cnt[p], (sizeof(real) == 8 ? ncclFloat64 : ncclFloat32), P.peers[p], (ncclComm_t)hs.comm, stream);
     }
     ncclResult_t r = a->GroupEnd();
     if (r != ncclSuccess) { h->err = std::string("nccl: ") + a->GetErrorString(r); return 1; }
-    if (P.n_unpack) { k_halo_unpack<<<dim3(gx, std::min(P.n_unpack, 256)), 256, 0, h->stream>>>(P.d_unpack, P.d_idx_recv, P.d_recvbuf, P.n_unpack); h->launches++; }
+    if (P.n_unpack) { k_halo_unpack<<<dim3(gx, std::min(P.n_unpack, 256)), 256, 0, stream>>>(P.d_unpack, P.d_idx_recv, P.d_recvbuf, P.n_unpack); h->launches++; }
     return 0;
 }
 
 extern "C" int mpasb_exchange_halo_group(mpasb_handle h, const char* group_name) {
     cudaSetDevice(h->device);
     if (!h->halo.active) return 0;
-    if (halo_exchange(h, group_name)) return 1;
+    if (exchange(h, group_name)) return 1;
     CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }

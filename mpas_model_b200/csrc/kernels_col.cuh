@@ -145,6 +145,124 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
     ST(D.adv_flux_theta, i, sel(lv.lt(nl), ruk * ft, 0.0));
 }
 
+// ---- the same per-edge flux with the stencil columns staged in shared memory by bulk copies (TMA) ----
+// k2_dt_edge_flux gathers 20 columns of 448 B per edge through L1 (the L1 data pipe is what bounds it).  Here a block
+// owns EF_EB consecutive edges; the UNION of their stencil cells (47 on average for 32 edges of a Morton-ordered
+// icosahedral mesh, against 320 gathers) is precomputed at upload (flux_tiles, mpasb.cu) and each of its w / theta_m
+// columns is brought into shared memory ONCE: the union is covered by RUNS of consecutive cell indices (cells are
+// Morton-ordered, so 9 runs on average when gaps of <= EF_GAP unused cells are bridged: 14 % more columns than the
+// union), one cp.async.bulk (UBLKCP) of ncols x 448 B per run and field, completion on an mbarrier.
+// The 10-cell stencil sums then read shared memory (LDS.128, conflict free: lane l reads bytes [16 l, 16 l + 16) of a
+// 448-byte row).  Tiles whose union exceeds EF_MAXT columns (about 1 %) gather from global memory as before.
+// Accumulation order per edge is unchanged: bit-identical to k2_dt_edge_flux.
+#define EF_EB 32                        // edges per block
+#define EF_MAXT 80                      // staged columns per block and field
+#define EF_MAXR 24                      // runs of consecutive cells per block
+#define EF_GAP 2                        // unused cells bridged inside a run
+#define EF_EPW (EF_EB / CW_WARPS)       // edges per warp
+#ifndef EF_MINB
+#define EF_MINB 3
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev D, const int4* __restrict__ tile_hdr,
+                                                             const int4* __restrict__ tile_runs, const unsigned char* __restrict__ tile_slot) {
+    extern __shared__ __align__(128) unsigned char ef_raw[];
+    __shared__ __align__(8) unsigned long long ef_bar;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    real* s_w = reinterpret_cast<real*>(ef_raw);
+    real* s_t = s_w + EF_MAXT * LDK;
+    const int tile = blockIdx.x;
+    const int4 hdr = tile_hdr[tile];                        // (runs, staged columns, active-edge mask); runs < 0: gather from global memory
+    const int nt = hdr.x;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < LDK;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const unsigned bar = smem_u32(&ef_bar);
+    if (nt > 0) {
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, (unsigned)(hdr.y * 2 * LDK * sizeof(real))); }
+        __syncthreads();
+        if ((int)threadIdx.x < 2 * nt) {                    // thread 2r: w columns of run r, thread 2r + 1: theta_m columns
+            const int4 run = tile_runs[tile * EF_MAXR + (threadIdx.x >> 1)];        // (first cell, columns, first slot)
+            const unsigned bytes = (unsigned)(run.y * LDK * sizeof(real));
+            if (threadIdx.x & 1) bulk_g2s(smem_u32(s_t + run.z * LDK), D.theta_m_2 + (size_t)run.x * LDK, bytes, bar);
+            else bulk_g2s(smem_u32(s_w + run.z * LDK), D.w_2 + (size_t)run.x * LDK, bytes, bar);
+        }
+    }
+    // per-edge metadata and the edge's own column while the copies are in flight: every load is addressed by the edge
+    // index alone (the active mask and the stencil length come with the tile tables), so all of them are in flight together
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    int e_nadv[EF_EPW], e_c[EF_EPW]; real e_wp[EF_EPW], e_wm[EF_EPW]; r2 e_ru[EF_EPW];
+    const int l15 = min(lane, 14);
+#pragma unroll
+    for (int q = 0; q < EF_EPW; q++) {
+        const int i = tile * EF_EB + q * CW_WARPS + wib;
+        const unsigned ic = (unsigned)min(i, D.nEdges);    // the garbage row of the per-edge arrays
+        const int sl = tile_slot[(unsigned)i * 15 + l15];
+        const int cg = D.advCellsForEdge[ic * 15 + l15];
+        const real a = D.adv_coefs[ic * 15 + l15], b = D.adv_coefs_3rd[ic * 15 + l15];
+        e_ru[q] = LD(D.ru, ic);
+        const bool valid = lane < 15 && sl != 0xff;
+        e_nadv[q] = __popc(__ballot_sync(CW_FULL, valid));
+        e_c[q] = nt > 0 ? sl : cg;
+        e_wp[q] = a + b; e_wm[q] = a - b;
+    }
+    if (nt > 0) mbar_wait(bar, 0);
+#pragma unroll
+    for (int q = 0; q < EF_EPW; q++) {
+        if (!((hdr.z >> (q * CW_WARPS + wib)) & 1)) continue;                      // warp-uniform: edge without an owned cell
+        const int i = tile * EF_EB + q * CW_WARPS + wib;
+        const r2 ruk = e_ru[q];
+        const r2 ruw = fm * ruk + fp * up1(ruk);
+        const b2 pw = nonneg_sign(ruw), pt = nonneg_sign(ruk);
+        r2 fw = mk2(0.0, 0.0), ft = mk2(0.0, 0.0);
+        const int nadv = e_nadv[q];
+        if (nt > 0) {
+#pragma unroll 5
+            for (int j = 0; j < nadv; j++) {
+                const int sl = BC(e_c[q], j);
+                const real wp = BC(e_wp[q], j), wm = BC(e_wm[q], j);
+                const r2 w2 = *reinterpret_cast<const r2*>(s_w + sl * LDK + kc), t2 = *reinterpret_cast<const r2*>(s_t + sl * LDK + kc);
+                fw.x = fw.x + (pw.x ? wp : wm) * w2.x;
+                fw.y = fw.y + (pw.y ? wp : wm) * w2.y;
+                ft.x = ft.x + (pt.x ? wp : wm) * t2.x;
+                ft.y = ft.y + (pt.y ? wp : wm) * t2.y;
+            }
+        } else {
+#pragma unroll 5
+            for (int j = 0; j < nadv; j++) {
+                const int c = BC(e_c[q], j);
+                const real wp = BC(e_wp[q], j), wm = BC(e_wm[q], j);
+                const r2 w2 = LD(D.w_2, c), t2 = LD(D.theta_m_2, c);
+                fw.x = fw.x + (pw.x ? wp : wm) * w2.x;
+                fw.y = fw.y + (pw.y ? wp : wm) * w2.y;
+                ft.x = ft.x + (pt.x ? wp : wm) * t2.x;
+                ft.y = ft.y + (pt.y ? wp : wm) * t2.y;
+            }
+        }
+        ST(D.adv_flux_w, i, sel(lv.ge(1) && lv.lt(nl), ruw * fw, 0.0));
+        ST(D.adv_flux_theta, i, sel(lv.lt(nl), ruk * ft, 0.0));
+    }
+}
+
 // owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
 // Restrictions (the host falls back to k_dt_cell_f otherwise): v_mom_eddy_visc2 == v_theta_eddy_visc2 == 0.
 #ifndef CELLF_MINB

@@ -53,7 +53,16 @@ struct mpasb_handle_s {
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool profile = false;
     std::map<std::string, ProfRec> prof;
+    // stencil-union tiles of the TMA-staged advective flux kernel (k4_dt_edge_flux): host copies of the lists they
+    // are derived from, and the derived device tables
+    std::vector<int> hc_advCells, hc_nAdv, hc_cellsOnEdge;
+    bool tiles_dirty = true, tiles_ok = false;
+    int4* d_tile_hdr = nullptr; int4* d_tile_runs = nullptr; unsigned char* d_tile_slot = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+    // halo exchanges that do not feed the next kernel run on comm_stream, concurrently with that kernel
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool comm_pending = false, overlap = true;
     HaloState halo;
 };
 typedef mpasb_handle_s H;
@@ -103,6 +112,13 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->kev0); cudaEventCreate(&h->kev1);
     cudaEventCreate(&h->tev0); cudaEventCreate(&h->tev1);
+    {   // highest priority: the small pack / NCCL / unpack kernels must get SM slots while a full-grid compute kernel runs
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest);
+    }
+    cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+    h->overlap = !getenv("MPASB_NO_OVERLAP");
     memset(&h->D, 0, sizeof(Dev));
     Dev& D = h->D;
     D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
@@ -164,9 +180,15 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->D.zb_any) cudaFree(h->D.zb_any);
     if (h->D.adv_flux_w) cudaFree(h->D.adv_flux_w);
     if (h->D.adv_flux_theta) cudaFree(h->D.adv_flux_theta);
+    if (h->d_tile_hdr) cudaFree(h->d_tile_hdr);
+    if (h->d_tile_runs) cudaFree(h->d_tile_runs);
+    if (h->d_tile_slot) cudaFree(h->d_tile_slot);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : {h->kev0, h->kev1, h->tev0, h->tev1}) if (e) cudaEventDestroy(e);
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -249,6 +271,9 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
         for (long n = 0; n < count; n++) h->max_ne = std::max(h->max_ne, src[n]);
         h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS");
     }
+    if (!strcmp(name, "advCellsForEdge")) { h->hc_advCells.assign(src, src + count); h->tiles_dirty = true; }
+    if (!strcmp(name, "nAdvCellsForEdge")) { h->hc_nAdv.assign(src, src + count); h->tiles_dirty = true; }
+    if (!strcmp(name, "cellsOnEdge")) { h->hc_cellsOnEdge.assign(src, src + count); h->tiles_dirty = true; }
     CUDA_OK(cudaMemcpyAsync(st, src, count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     k_int_to_zero_based<<<nblk(count), 256, 0, h->stream>>>((int*)f->d[0], st, (size_t)count, f->target == TG_NONE ? 0 : 1);
     h->launches++;
@@ -308,6 +333,9 @@ struct SegBuilder {       // collects the column ranges of one routine into one 
         h->launches++; n = 0;
     }
 };
+static int exchange(H* h, const char* group);
+static int exchange_async(H* h, const char* group);
+static void comm_wait(H* h);
 static void rk_integration_setup(H* h) {       // TI:1930-2039
     Scope sc(h, "atm_rk_integration_setup");
     Dev& D = h->D; const size_t nC = D.nCells, nE = D.nEdges;
@@ -363,12 +391,75 @@ static DynTendArgs dyn_tend_args(H* h, int rk_step, real dt) {
         A.rayleigh_coef_inverse = 1.0 / ((real)A.n_rayleigh_levels * (c.config_rayleigh_damp_u_timescale_days * 86400.0));
     return A;
 }
-static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
+// Per block of EF_EB consecutive edges: the distinct stencil cells of its active edges (advCellsForEdge of edges that
+// touch an owned cell), covered by runs of consecutive cell indices (gaps of <= EF_GAP unused cells are bridged), and
+// for every stencil entry the shared-memory slot of its cell.  Derived from the host's own connectivity at upload;
+// tiles that need more than EF_MAXR runs or EF_MAXT staged columns are marked -1 (global gathers).
+static void build_flux_tiles(H* h) {
+    h->tiles_dirty = false; h->tiles_ok = false;
+    const int nE = h->dims.nEdges, nC = h->dims.nCells;
+    if ((long)h->hc_advCells.size() != (long)(nE + 1) * 15 || (long)h->hc_nAdv.size() != nE + 1 || (long)h->hc_cellsOnEdge.size() != (long)(nE + 1) * 2) return;
+    if ((h->D.LDK * sizeof(real)) % 16 != 0 || getenv("MPASB_NO_TMA_FLUX")) return;        // bulk copies move 16-byte multiples
+    const int nTiles = (nE + EF_EB - 1) / EF_EB;
+    std::vector<int4> hdr(nTiles, make_int4(0, 0, 0, 0));
+    std::vector<int4> runs((size_t)nTiles * EF_MAXR, make_int4(0, 0, 0, 0));
+    std::vector<int> stamp(nC + 1, -1), slotof(nC + 1, 0), tmp;
+    std::vector<unsigned char> slot((size_t)nTiles * EF_EB * 15, 0xff);      // 0xff: beyond the stencil / inactive edge
+    for (int t = 0; t < nTiles; t++) {
+        tmp.clear();
+        const int e0 = t * EF_EB, e1 = std::min(nE, (t + 1) * EF_EB);
+        auto active = [&](int e) {
+            const int c1 = h->hc_cellsOnEdge[2 * (size_t)e] - 1, c2 = h->hc_cellsOnEdge[2 * (size_t)e + 1] - 1;      // host lists are 1-based
+            return c1 < h->dims.nCellsSolve || c2 < h->dims.nCellsSolve;
+        };
+        for (int e = e0; e < e1; e++) {
+            if (!active(e)) continue;
+            for (int j = 0; j < h->hc_nAdv[e]; j++) {
+                const int c = h->hc_advCells[(size_t)e * 15 + j] - 1;
+                if (c < 0 || c > nC) return;                                             // malformed list: keep the gather kernel
+                if (stamp[c] != t) { stamp[c] = t; tmp.push_back(c); }
+            }
+        }
+        if (tmp.empty()) continue;
+        unsigned mask = 0;
+        for (int e = e0; e < e1; e++) if (active(e)) mask |= 1u << (e - e0);
+        std::sort(tmp.begin(), tmp.end());
+        int nr = 0, total = 0; bool ok = true;
+        int4* R = &runs[(size_t)t * EF_MAXR];
+        for (size_t n = 0; n < tmp.size();) {
+            size_t m = n;
+            while (m + 1 < tmp.size() && tmp[m + 1] - tmp[m] <= EF_GAP + 1) m++;
+            const int ncols = tmp[m] - tmp[n] + 1;
+            if (nr == EF_MAXR || total + ncols > EF_MAXT) { ok = false; break; }
+            R[nr++] = make_int4(tmp[n], ncols, total, 0);
+            for (size_t q = n; q <= m; q++) slotof[tmp[q]] = total + (tmp[q] - tmp[n]);
+            total += ncols; n = m + 1;
+        }
+        hdr[t] = ok ? make_int4(nr, total, (int)mask, 0) : make_int4(-1, 0, (int)mask, 0);
+        for (int e = e0; e < e1; e++) {
+            if (!active(e)) continue;
+            for (int j = 0; j < h->hc_nAdv[e]; j++) slot[(size_t)e * 15 + j] = ok ? (unsigned char)slotof[h->hc_advCells[(size_t)e * 15 + j] - 1] : (unsigned char)0;
+        }
+    }
+    if (h->d_tile_hdr) { cudaFree(h->d_tile_hdr); cudaFree(h->d_tile_runs); cudaFree(h->d_tile_slot); h->d_tile_hdr = nullptr; }
+    if (cudaMalloc(&h->d_tile_hdr, hdr.size() * sizeof(int4)) != cudaSuccess || cudaMalloc(&h->d_tile_runs, runs.size() * sizeof(int4)) != cudaSuccess ||
+        cudaMalloc(&h->d_tile_slot, slot.size()) != cudaSuccess) return;
+    cudaMemcpy(h->d_tile_hdr, hdr.data(), hdr.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tile_runs, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_tile_slot, slot.data(), slot.size(), cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(k4_dt_edge_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * EF_MAXT * h->D.LDK * sizeof(real)));
+    h->tiles_ok = true;
+}
+// in_step: called from srk3, where (a) the exchange of w, pv_edge, rho_edge of the previous stage may still be in flight
+// while the first kernel (which reads none of them) runs, and (b) tend_u is final before the w/theta tendencies are
+// computed, so its exchange (TI:1228) is started here and overlaps them
+static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) {    // TI:4982-6240
     Scope sc(h, "atm_compute_dyn_tend");
     const Dev& D = h->D;
     const DynTendArgs A = dyn_tend_args(h, rk_step, dt);
     if (h->colwarp && !(A.cam_coef > 0.0)) LAUNCHW(k2_dt_cell_a, D.nCells, D, A);
     else LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
+    comm_wait(h);
     if (h->colwarp && !A.rayleigh_damp_u) LAUNCHW(k2_dt_edge_b, D.nEdges, D, A);
     else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
@@ -377,14 +468,25 @@ static void compute_dyn_tend(H* h, int rk_step, real dt) {    // TI:4982-6240
             LAUNCH(k_dt_delsq_cell, D.nCells, 0, D);
         }
         LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
+    }
+    if (in_step && exchange_async(h, "dynamics:tend_u")) return 1;
+    if (rk_step == 1) {
         if (h->colwarp) LAUNCHW(k2_dt_cell_e, D.nCells, D, A);
         else LAUNCH(k_dt_cell_e, D.nCells, 0, D, A);
     }
     if (h->colwarp && !(A.v_mom_eddy_visc2 > 0.0) && !(A.v_theta_eddy_visc2 > 0.0)) {
-        LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
+        if (h->tiles_dirty) build_flux_tiles(h);
+        if (h->tiles_ok) {
+            KScope ks_(h, "k:k4_dt_edge_flux");
+            k4_dt_edge_flux<<<(unsigned)((D.nEdges + EF_EB - 1) / EF_EB), CW_THREADS, 2 * EF_MAXT * D.LDK * sizeof(real), h->stream>>>(
+                D, h->d_tile_hdr, h->d_tile_runs, h->d_tile_slot);
+            h->launches++;
+        }
+        else LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
         LAUNCHW(k2_dt_cell_f, D.nCellsSolve, D, A);
     }
     else LAUNCH(k_dt_cell_f, D.nCellsSolve, 0, D, A);
+    return 0;
 }
 static void refresh_zb_flags(H* h) {
     if (!h->zb_dirty) return;
@@ -431,7 +533,9 @@ static void divergence_damping_3d(H* h, real dts) {           // TI:2987-3075
     }
     LAUNCH(k_divergence_damping, h->D.nEdges, 0, h->D, coef_divdamp);
 }
-static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {    // TI:3189-3431
+// in_step: u (time level 2) is final after the edge kernel, so its layer-3 exchange (TI:1371) is started before the
+// kernel that finishes w and overlaps it
+static int recover_large_step_variables(H* h, real dt, int ns, int rk_step, bool in_step = false) {    // TI:3189-3431
     Scope sc(h, "atm_recover_large_step_variables");
     const real rcv = rgas / (cp - rgas);
     const real p0 = 1.0e+05;
@@ -444,8 +548,10 @@ static void recover_large_step_variables(H* h, real dt, int ns, int rk_step) {  
         LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
         LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
     }
+    if (in_step && exchange_async(h, "dynamics:u_3")) return 1;
     if (h->colwarp) LAUNCHW(k2_recover_cell2, h->D.nCells, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
     else LAUNCH(k_recover_cell2, h->D.nCells, 0, h->D, h->cfg.cf1, h->cfg.cf2, h->cfg.cf3);
+    return 0;
 }
 static void compute_solve_diagnostics(H* h, real dt, int time_lev, int rk_step) {  // TI:6337-6773
     Scope sc(h, "atm_compute_solve_diagnostics");
@@ -501,7 +607,6 @@ static void advance_scalars(H* h, real dt, int rk_step) {     // TI:3575-3855
     LAUNCH(k_scalars_edge, h->D.nEdges, 0, h->D);
     LAUNCH(k_scalars_cell, h->D.nCellsSolve, 0, h->D, dt, weight_time_old, weight_time_new, c.config_coef_3rd_order);
 }
-static int exchange(H* h, const char* group);
 static int advance_scalars_mono(H* h, real dt) {              // TI:4012-4734
     Scope sc(h, "atm_advance_scalars_mono");
     const Dev& D = h->D;
@@ -565,10 +670,30 @@ static void compute_output_diagnostics(H* h, int time_lev) {
 // ------------------------------------------------------------------ halo exchange (mpas_halo.F:498-846)
 #include "halo_host.inl"
 
+// the compute stream waits for an exchange started with exchange_async
+static void comm_wait(H* h) {
+    if (!h->comm_pending) return;
+    cudaStreamWaitEvent(h->stream, h->ev_done, 0);
+    h->comm_pending = false;
+}
 static int exchange(H* h, const char* group) {
     if (!h->halo.active) return 0;                // single block: exchange lists are empty (mpas_dmpar.F:2074-2153)
+    comm_wait(h);
     Scope sc(h, "exchange_halo_group");
-    return halo_exchange(h, group);
+    return halo_exchange(h, group, h->stream);
+}
+// Start an exchange whose fields are final but that the NEXT kernels neither read (halo) nor write: pack, send/recv and
+// unpack run on comm_stream while the compute stream continues; comm_wait() is called before the first consumer.
+static int exchange_async(H* h, const char* group) {
+    if (!h->halo.active) return 0;
+    if (!h->overlap || h->profile) return exchange(h, group);
+    comm_wait(h);
+    cudaEventRecord(h->ev_ready, h->stream);
+    cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0);
+    if (halo_exchange(h, group, h->comm_stream)) return 1;
+    cudaEventRecord(h->ev_done, h->comm_stream);
+    h->comm_pending = true;
+    return 0;
 }
 
 // ------------------------------------------------------------------ atm_srk3  TI:803-1725
@@ -609,8 +734,8 @@ static int srk3(H* h, real dt) {
         if (exchange(h, "dynamics:exner")) return 1;
         for (int rk_step = 1; rk_step <= 3; rk_step++) {
             if (c.config_time_integration_order == 3 && rk_step == 2) compute_vert_imp_coefs(h, rk_sub_timestep[rk_step]);
-            compute_dyn_tend(h, rk_step, dt);
-            if (exchange(h, "dynamics:tend_u")) return 1;
+            if (compute_dyn_tend(h, rk_step, dt, true)) return 1;        // starts the exchange of tend_u (TI:1228)
+            comm_wait(h);
             set_smlstep_pert_variables(h);
             for (int small_step = 1; small_step <= number_sub_steps[rk_step]; small_step++) {
                 // TI:1279 exchanges rho_pp before every acoustic step.  On the first small step nothing reads the
@@ -622,10 +747,12 @@ static int srk3(H* h, real dt) {
                 divergence_damping_3d(h, rk_sub_timestep[rk_step]);
             }
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
-            recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step);
-            if (exchange(h, "dynamics:u_3")) return 1;
+            if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, true)) return 1;   // starts u_3 (TI:1371)
+            comm_wait(h);
             compute_solve_diagnostics(h, dt, 2, rk_step);
-            if (exchange(h, "dynamics:w,pv_edge,rho_edge")) return 1;
+            // TI:1424.  Stages 1 and 2: the next kernels (vertical coefficients, first cell kernel of the tendencies) read none
+            // of the three fields, so the exchange overlaps them; after stage 3 the substep roll copies w and must wait
+            if (rk_step < 3 ? exchange_async(h, "dynamics:w,pv_edge,rho_edge") : exchange(h, "dynamics:w,pv_edge,rho_edge")) return 1;
         }
         if (dynamics_substep < dynamics_split)
             if (exchange(h, "dynamics:theta_m,pressure_p,rtheta_p")) return 1;
@@ -640,6 +767,7 @@ static int srk3(H* h, real dt) {
             if (rk_step < 3) if (exchange(h, "dynamics:scalars")) return 1;
         }
     }
+    comm_wait(h);
     reconstruct(h, 2, 0);                         // TI:1596-1611: uReconstruct* from u (time level 2), owned cells
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(e); return 1; }
@@ -686,7 +814,7 @@ extern "C" int mpasb_compute_output_diagnostics(mpasb_handle h, int time_level) 
 extern "C" int mpasb_k_rk_integration_setup(mpasb_handle h) ENTRY(rk_integration_setup(h))
 extern "C" int mpasb_k_compute_moist_coefficients(mpasb_handle h) ENTRY(compute_moist_coefficients(h))
 extern "C" int mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts) ENTRY(compute_vert_imp_coefs(h, dts))
-extern "C" int mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt) ENTRY(compute_dyn_tend(h, rk_step, dt))
+extern "C" int mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt) ENTRY(if (compute_dyn_tend(h, rk_step, dt)) return 1)
 extern "C" int mpasb_k_set_smlstep_pert_variables(mpasb_handle h) ENTRY(set_smlstep_pert_variables(h))
 // called on its own the routine must leave ru_p/ruAvg as the reference does: materialise the deferred edge update
 static void advance_acoustic_step_standalone(H* h, real dts, int small_step) {
@@ -695,7 +823,7 @@ static void advance_acoustic_step_standalone(H* h, real dts, int small_step) {
 }
 extern "C" int mpasb_k_advance_acoustic_step(mpasb_handle h, mpasb_real dts, int small_step) ENTRY(advance_acoustic_step_standalone(h, dts, small_step))
 extern "C" int mpasb_k_divergence_damping_3d(mpasb_handle h, mpasb_real dts) ENTRY(divergence_damping_3d(h, dts))
-extern "C" int mpasb_k_recover_large_step_variables(mpasb_handle h, mpasb_real dt, int ns, int rk_step) ENTRY(recover_large_step_variables(h, dt, ns, rk_step))
+extern "C" int mpasb_k_recover_large_step_variables(mpasb_handle h, mpasb_real dt, int ns, int rk_step) ENTRY(if (recover_large_step_variables(h, dt, ns, rk_step)) return 1)
 extern "C" int mpasb_k_compute_solve_diagnostics(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(compute_solve_diagnostics(h, dt, 2, rk_step))
 extern "C" int mpasb_k_rk_dynamics_substep_finish(mpasb_handle h, int s, int n) ENTRY(rk_dynamics_substep_finish(h, s, n))
 extern "C" int mpasb_k_advance_scalars(mpasb_handle h, mpasb_real dt, int rk_step) ENTRY(advance_scalars(h, dt, rk_step))
