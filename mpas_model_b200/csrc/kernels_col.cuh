@@ -30,6 +30,35 @@
 #define CW_MINB 2                       // resident blocks per SM the register allocation aims for
 #endif
 
+// resident blocks per SM each kernel's register allocation aims for (1 = no constraint); tuned on B200, DESIGN.md §4
+#ifndef MB_EDGE_B
+#define MB_EDGE_B 6
+#endif
+#ifndef MB_SML
+#define MB_SML 5
+#endif
+#ifndef MB_REC2
+#define MB_REC2 6
+#endif
+#ifndef MB_DIAG_E
+#define MB_DIAG_E 0
+#endif
+#ifndef MB_REC1
+#define MB_REC1 4
+#endif
+#ifndef MB_DIAG_C
+#define MB_DIAG_C 5
+#endif
+#ifndef MB_CELL_A
+#define MB_CELL_A 6
+#endif
+#ifndef MB_CELL_E
+#define MB_CELL_E 4
+#endif
+#ifndef MB_SC_CELL
+#define MB_SC_CELL 4
+#endif
+
 struct __align__(2 * sizeof(real)) r2 { real x, y; };
 struct b2 { bool x, y; };
 
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev
 // Restriction (host falls back to k_dt_edge_b otherwise): config_rayleigh_damp_u off.
 // This kernel is bound by the L1 data pipe (46 gathered columns per edge), not by latency: it is kept at
 // ~64 registers for 32 resident warps per SM rather than unrolled for more loads in flight (measured).
-__global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
+__global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
@@ -558,7 +587,7 @@ __global__ void __launch_bounds__(CW_THREADS, CW_MINB) k2_acoustic_cell(const De
 // ------------------------------------------------------------------ atm_set_smlstep_pert_variables_work  TI:2427-2508
 // zb_cell/zb3_cell are [cell][edge slot][LDK]; requires maxEdges >= CW_NE (slots beyond nEdgesOnCell exist and are skipped)
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
-__global__ void __launch_bounds__(CW_THREADS) k2_smlstep_pert(const Dev D) {
+__global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -588,7 +617,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_smlstep_pert(const Dev D) {
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
-__global__ void __launch_bounds__(CW_THREADS) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
+__global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     CW_SETUP(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -646,7 +675,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
     ST(D.pv_vertex, i, sel(k_lt_nl, D.fVertex[i] + vort, 0.0));
 }
 // (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
-__global__ void __launch_bounds__(CW_THREADS) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
+__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
     CW_SETUP(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -690,7 +719,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_cell(const Dev D, const re
     if (apvm) ST(D.pv_cell, i, sel(k_lt_nl, pvc, 0.0));
 }
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
-__global__ void __launch_bounds__(CW_THREADS) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
+__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
@@ -727,7 +756,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_edge(const Dev D, const re
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (a)
 // cell-all: Smagorinsky kdiff (rk 1, TI:5226-5296), h_divergence (5307-5338), tend_rho + dpdz (rk 1, 5345-5362).
 // Restriction (host falls back to k_dt_cell_a otherwise): config_mpas_cam_coef == 0.
-__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
+__global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -773,7 +802,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_a(const Dev D, const Dy
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
 // rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
-__global__ void __launch_bounds__(CW_THREADS) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
+__global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -1015,7 +1044,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D,
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, parts 1 and 2
 // (1) cell-all, TI:3294-3350 (+ the garbage cell, TI:3282-3284)
-__global__ void __launch_bounds__(CW_THREADS) k2_recover_cell1(const Dev D, real dt, real invNs, int rk_step, real rcv, real rgas_p0) {
+__global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const Dev D, real dt, real invNs, int rk_step, real rcv, real rgas_p0) {
     CW_SETUP(D.nCells + 1)
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
     if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); return; }
@@ -1111,7 +1140,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
     }
 }
 // owned cells: flux divergence + vertical flux + update, TI:3773-3846
-__global__ void __launch_bounds__(CW_THREADS) k2_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
+__global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);

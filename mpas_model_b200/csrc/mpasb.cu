@@ -399,7 +399,10 @@ static void build_flux_tiles(H* h) {
     h->tiles_dirty = false; h->tiles_ok = false;
     const int nE = h->dims.nEdges, nC = h->dims.nCells;
     if ((long)h->hc_advCells.size() != (long)(nE + 1) * 15 || (long)h->hc_nAdv.size() != nE + 1 || (long)h->hc_cellsOnEdge.size() != (long)(nE + 1) * 2) return;
-    if ((h->D.LDK * sizeof(real)) % 16 != 0 || getenv("MPASB_NO_TMA_FLUX")) return;        // bulk copies move 16-byte multiples
+    // Opt-in (MPASB_TMA_FLUX=1): measured on B200 the staged kernel takes 113 us against 109 us for the L1 gathers of
+    // k2_dt_edge_flux -- shared-memory reads go through the same 64 B/clk/SM LSU data pipe that bounds the gathers
+    // (profiles/r1_ncu_step_metrics_u.csv: 73 % pipe busy), so staging does not lift the bound.
+    if ((h->D.LDK * sizeof(real)) % 16 != 0 || !getenv("MPASB_TMA_FLUX")) return;          // bulk copies move 16-byte multiples
     const int nTiles = (nE + EF_EB - 1) / EF_EB;
     std::vector<int4> hdr(nTiles, make_int4(0, 0, 0, 0));
     std::vector<int4> runs((size_t)nTiles * EF_MAXR, make_int4(0, 0, 0, 0));
