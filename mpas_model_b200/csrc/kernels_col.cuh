@@ -53,7 +53,7 @@
 #define MB_CELL_A 6
 #endif
 #ifndef MB_CELL_E
-#define MB_CELL_E 4
+#define MB_CELL_E 3
 #endif
 #ifndef MB_SC_CELL
 #define MB_SC_CELL 4
@@ -809,17 +809,23 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev 
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    // one of the two cells of every edge is this cell: its columns are loaded once, only the other cell is gathered
+    const bool my_is1 = my_c1 == i, my_is2 = my_c2 == i;
+    const int my_oth = my_is1 ? my_c2 : my_c1;
     const real my_dv = D.dvEdge[my_e], my_idc = D.invDcEdge[my_e], my_msd2 = D.meshScalingDel2[my_e];
     const real r_areaCell = D.invAreaCell[i];
+    const r2 kd_own = LD(D.kdiff, i), w_own = LD(D.w_2, i), th_own = LD(D.theta_m_2, i);
     r2 dsw = mk2(0.0, 0.0), twe = mk2(0.0, 0.0), dst = mk2(0.0, 0.0), tte = mk2(0.0, 0.0);
 #define CELL_E_EDGE(E)                                                                                      \
     {                                                                                                       \
-        const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                    \
+        const int iEdge = BC(my_e, (E)), oth = BC(my_oth, (E));                                             \
+        const bool is1 = BC(my_is1, (E)), is2 = BC(my_is2, (E));                                            \
         const real sg = BC(my_sgn, (E)), dv = BC(my_dv, (E)), idc = BC(my_idc, (E)), msd2 = BC(my_msd2, (E)); \
         const r2 rho_e = LD(D.rho_edge, iEdge);                                                             \
-        const r2 kd1 = LD(D.kdiff, cell1), kd2 = LD(D.kdiff, cell2);                                        \
-        const r2 dw = LD(D.w_2, cell2) - LD(D.w_2, cell1);                                                  \
-        const r2 dth = LD(D.theta_m_2, cell2) - LD(D.theta_m_2, cell1);                                     \
+        const r2 kd_o = LD(D.kdiff, oth), w_o = LD(D.w_2, oth), th_o = LD(D.theta_m_2, oth);                \
+        const r2 kd1 = selb(is1, kd_own, kd_o), kd2 = selb(is2, kd_own, kd_o);                              \
+        const r2 dw = selb(is2, w_own, w_o) - selb(is1, w_own, w_o);                                        \
+        const r2 dth = selb(is2, th_own, th_o) - selb(is1, th_own, th_o);                                   \
         {                                                                                                   \
             const real edge_sign = 0.5 * r_areaCell * sg * dv * idc;                                        \
             r2 w_turb_flux = edge_sign * (rho_e + up1(rho_e)) * dw;                                         \
@@ -886,7 +892,7 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
     // connectivity of ALL columns of this warp in one pass: lane = (column slot << 3) | edge slot, so the two
     // dependent index loads (edgesOnCell -> cellsOnEdge/dvEdge) are exposed once per warp, not once per column
     static_assert(AC3_COLS / AC3_WARPS <= 4 && CW_MAXNE <= 8, "one lane per (column, edge slot)");
-    int m_ne = 1, m_e = 0, m_c1 = 0, m_c2 = 0; real m_f = 0.0, m_invArea = 0.0;
+    int m_ne = 1, m_e = 0, m_oth = 0; bool m_is1 = false, m_is2 = false; real m_f = 0.0, m_invArea = 0.0;
     {
         const int mi = base + (lane >> 3) * AC3_WARPS + wib;
         if ((lane >> 3) < AC3_COLS / AC3_WARPS && mi < D.nCellsSolve) {
@@ -894,7 +900,9 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
             m_invArea = D.invAreaCell[mi];
             const int le = min(lane & 7, m_ne - 1);
             m_e = D.edgesOnCell[(unsigned)mi * D.maxEdges + le];
-            m_c1 = D.cellsOnEdge[2 * m_e]; m_c2 = D.cellsOnEdge[2 * m_e + 1];
+            // one of the two cells of every edge is the column itself: only the other cell's theta_m is gathered
+            const int c1 = D.cellsOnEdge[2 * m_e], c2 = D.cellsOnEdge[2 * m_e + 1];
+            m_is1 = c1 == mi; m_is2 = c2 == mi; m_oth = m_is1 ? c2 : c1;
             m_f = D.edgesOnCell_sign[(unsigned)mi * D.maxEdges + le] * dts * D.dvEdge[m_e];
         }
     }
@@ -918,14 +926,17 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
         const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
         const r2 zz = LD(D.zz, i);
         const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
+        const r2 th_own = LD(D.theta_m, i);
         r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
 #define AC_EDGE(E)                                                                                          \
         {                                                                                                   \
             const int src = (cc << 3) + (E);                                                                \
-            const int iEdge = BC(m_e, src), cell1 = BC(m_c1, src), cell2 = BC(m_c2, src);                   \
+            const int iEdge = BC(m_e, src);                                                                 \
+            const bool is1 = BC(m_is1, src), is2 = BC(m_is2, src);                                          \
+            const r2 th_o = LD(D.theta_m, BC(m_oth, src));                                                  \
             const r2 ru_p = first ? dts * LD(D.tend_u, iEdge) : LD(D.ru_p, iEdge);   /* TI:2798-2806 */     \
             const r2 flux = BC(m_f, src) * ru_p * invArea;                                                  \
-            const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                      \
+            const r2 th = selb(is2, th_own, th_o) + selb(is1, th_own, th_o);                                \
             rs = selb((E) < ne, rs - flux, rs);                                                             \
             ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                  \
         }
