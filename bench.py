@@ -99,9 +99,25 @@ KERNEL_MODEL_C = {
     "k:k2_dt_edge_flux": 11.0,       # ru (E), w, theta_m read; 2 E written
     "k:k2_recover_cell2": 19.0,      # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/), x1.40962 x 55 levels; None = not captured for the current kernel version
-KERNEL_TRAFFIC = {}
+
+
+def kernel_traffic(kernel, n_cells, n_lev, rb):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one step in the
+    committed ncu capture profiles/r1_ncu_step_metrics.csv (tools/ncu_step_metrics.sh: x1.40962 x 55 levels, fp64).
+    Only valid for that workload; None otherwise."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_step_metrics.csv")
+    if not (os.path.exists(path) and (n_cells, n_lev, rb) == (40962, 55, 8)):
+        return None
+    import csv
+    tot, launches = 0.0, set()
+    with open(path, errors="ignore") as f:
+        rows = [r for r in csv.reader(f) if len(r) > 10]
+    hdr = rows[0]
+    ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    for r in rows[1:]:
+        if r[ik].split("(")[0] == kernel and r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[iv].replace(",", "")); launches.add(r[iid])
+    return tot / len(launches) if launches else None
 
 
 def workload_for(args):
@@ -316,7 +332,8 @@ def main():
     dom_us = 1e3 * dom_ms / dom_cnt
     achieved = (model_c * C / (dom_us * 1e-6) / 1e9) if model_c else None
     roofline = {"bound": "hbm", "kernel": dom_name[2:], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": KERNEL_TRAFFIC.get(dom_name),
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": kernel_traffic(dom_name[2:], n_cells, n_lev, rb) if world == 1 else None,
                 "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum,
                 "algorithmic_bytes_per_launch": (model_c * C) if model_c else None, "peak_source": peak_src}
     B_step = model_bytes_per_step(n_cells, n_lev, args.scalars, rb)

@@ -88,6 +88,13 @@ int  mpasb_shift_time_levels(mpasb_handle h);
 /* summarize_timestep (TI:7914-8357): out = {min w, max w, min u, max u} of level 2,
  * reductions start from 0 as in TI:8291-8292. */
 int  mpasb_minmax(mpasb_handle h, mpasb_real out[4]);
+/* The same without stalling the host: _async enqueues, behind the step, the reductions of w and u,
+ * of every scalar (config_print_global_minmax_sca, TI:8322-8342) and the NaN tests of w and u (TI:8258-8281); _fetch
+ * waits for their copy to the host.  minmax = {min w, max w, min u, max u, min s1, max s1, ...}, 4 <= n_minmax <=
+ * 2*(2+num_scalars); nan_count = {NaNs in w, NaNs in u} (may be NULL).  A nonzero count is what the reference turns
+ * into MPAS_LOG_CRIT "NaN detected in 'w' field." (TI:8268, 8280). */
+int  mpasb_summarize_timestep_async(mpasb_handle h);
+int  mpasb_summarize_timestep_fetch(mpasb_handle h, mpasb_real* minmax, long n_minmax, long nan_count[2]);
 int  mpasb_synchronize(mpasb_handle h);
 
 /* Init-time routines of the path: atm_init_coupled_diagnostics (TI:6776) and

@@ -225,6 +225,24 @@ __global__ void k_minmax(const real* __restrict__ x, int n_items, int nl, int LD
     if ((threadIdx.x & 31) == 0) { atomic_min_f64(out, (double)mn); atomic_max_f64(out + 1, (double)mx); }
 }
 
+// the same reduction plus a NaN count (fmin/fmax drop NaNs; TI:8258-8281 tests every element with ieee_is_nan)
+__global__ void k_minmax_nan(const real* __restrict__ x, int n_items, int nl, int LDK, double* out, unsigned long long* n_nan) {
+    real mn = 0.0, mx = 0.0; unsigned bad = 0;
+    const size_t total = (size_t)n_items * LDK;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        if ((int)(t % LDK) < nl) { const real v = x[t]; mn = rmin(mn, v); mx = rmax(mx, v); bad += (v != v); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = rmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = rmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_min_f64(out, (double)mn); atomic_max_f64(out + 1, (double)mx);
+        if (bad) atomicAdd(n_nan, (unsigned long long)bad);
+    }
+}
+
 // ------------------------------------------------------------------ dense host layout <-> padded device layout
 // dst[o][0:LDK] <- src[o][0:ninner] (zero padded)
 __global__ void k_pad(real* __restrict__ dst, const real* __restrict__ src, size_t nouter, int ninner, int LDK) {

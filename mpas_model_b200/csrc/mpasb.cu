@@ -43,6 +43,9 @@ struct mpasb_handle_s {
     std::map<std::string, int> index;
     void* staging = nullptr; size_t staging_bytes = 0;
     double* d_minmax = nullptr;
+    // asynchronous summarize_timestep: device results (2 * (2 + num_scalars) doubles + 2 NaN counters as doubles' bit
+    // patterns), pinned host copy, completion event
+    double* d_summary = nullptr; double* h_summary = nullptr; cudaEvent_t ev_summary = nullptr; bool summary_pending = false;
     std::string err;
     long launches = 0;
     int cpb = 4;
@@ -177,6 +180,9 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(f.d[l]);
     if (h->staging) cudaFree(h->staging);
     if (h->d_minmax) cudaFree(h->d_minmax);
+    if (h->d_summary) cudaFree(h->d_summary);
+    if (h->h_summary) cudaFreeHost(h->h_summary);
+    if (h->ev_summary) cudaEventDestroy(h->ev_summary);
     if (h->D.zb_any) cudaFree(h->D.zb_any);
     if (h->D.adv_flux_w) cudaFree(h->D.adv_flux_w);
     if (h->D.adv_flux_theta) cudaFree(h->D.adv_flux_theta);
@@ -790,6 +796,45 @@ extern "C" int mpasb_minmax(mpasb_handle h, mpasb_real out[4]) {
     CUDA_OK(cudaMemcpyAsync(tmp, h->d_minmax, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     for (int n = 0; n < 4; n++) out[n] = (mpasb_real)tmp[n];
+    return 0;
+}
+
+// summarize_timestep without a host stall.  _async enqueues, behind the step on the compute stream,
+// the min/max reductions of w and u (TI:8286-8319), of every scalar (config_print_global_minmax_sca, TI:8322-8342) and
+// the NaN tests of w and u (TI:8258-8281), followed by one copy into pinned host memory; the host keeps going (e.g. it
+// launches the next step) and _fetch waits for that copy only.  Layout of `minmax`: {min w, max w, min u, max u,
+// min s1, max s1, ...}; nan_count = {NaNs in w, NaNs in u} over owned elements of time level 2.
+extern "C" int mpasb_summarize_timestep_async(mpasb_handle h) {
+    cudaSetDevice(h->device);
+    const Dev& D = h->D;
+    const int S = D.num_scalars, nval = 2 * (2 + S) + 2;
+    if (!h->d_summary) {
+        CUDA_OK(cudaMalloc(&h->d_summary, nval * sizeof(double)));
+        CUDA_OK(cudaMallocHost(&h->h_summary, nval * sizeof(double)));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_summary, cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaMemsetAsync(h->d_summary, 0, nval * sizeof(double), h->stream));
+    unsigned long long* nan = reinterpret_cast<unsigned long long*>(h->d_summary + 2 * (2 + S));
+    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.w_2, D.nCellsSolve, D.nl, D.LDK, h->d_summary, nan);
+    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.u_2, D.nEdgesSolve, D.nl, D.LDK, h->d_summary + 2, nan + 1);
+    for (int s = 0; s < S; s++)
+        k_minmax<<<296, 256, 0, h->stream>>>(D.scalars_2 + (size_t)s * D.cellPlane, D.nCellsSolve, D.nl, D.LDK, h->d_summary + 4 + 2 * s);
+    h->launches += 2 + S;
+    CUDA_OK(cudaMemcpyAsync(h->h_summary, h->d_summary, nval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaEventRecord(h->ev_summary, h->stream));
+    h->summary_pending = true;
+    return 0;
+}
+extern "C" int mpasb_summarize_timestep_fetch(mpasb_handle h, mpasb_real* minmax, long n_minmax, long nan_count[2]) {
+    cudaSetDevice(h->device);
+    if (!h->summary_pending) { h->err = "mpasb_summarize_timestep_fetch without a pending mpasb_summarize_timestep_async"; return 1; }
+    const int S = h->D.num_scalars;
+    if (n_minmax < 4 || n_minmax > 2 * (2 + S)) { h->err = "mpasb_summarize_timestep_fetch: n_minmax out of range"; return 2; }
+    CUDA_OK(cudaEventSynchronize(h->ev_summary));
+    h->summary_pending = false;
+    for (long n = 0; n < n_minmax; n++) minmax[n] = (mpasb_real)h->h_summary[n];
+    const unsigned long long* nan = reinterpret_cast<const unsigned long long*>(h->h_summary + 2 * (2 + S));
+    if (nan_count) { nan_count[0] = (long)nan[0]; nan_count[1] = (long)nan[1]; }
     return 0;
 }
 

@@ -223,6 +223,18 @@ class Dycore(Backend):
         self._check(self.lib.mpasb_minmax(self._h, out), "minmax")
         return tuple(out)
 
+    def summarize_timestep_async(self):
+        """Enqueue the step summary behind the step; the host does not wait."""
+        self._check(self.lib.mpasb_summarize_timestep_async(self._h), "summarize_timestep_async")
+
+    def summarize_timestep_fetch(self, scalars=True):
+        """-> (minmax array {min w, max w, min u, max u[, min s1, max s1, ...]}, (NaNs in w, NaNs in u))."""
+        n = 2 * (2 + (self.dims.num_scalars if scalars else 0))
+        out = (self.creal * n)()
+        nan = (C.c_long * 2)()
+        self._check(self.lib.mpasb_summarize_timestep_fetch(self._h, out, C.c_long(n), nan), "summarize_timestep_fetch")
+        return np.array(out[:], dtype=np.float64), (int(nan[0]), int(nan[1]))
+
     def synchronize(self):
         self._check(self.lib.mpasb_synchronize(self._h), "synchronize")
 

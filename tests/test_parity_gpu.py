@@ -141,6 +141,32 @@ def test_reconstruct_and_output_diagnostics(pair):
         assert rel_l2(g.get_array(n), o.get_array(n)) <= TOL_STEP, n
 
 
+def test_summarize_timestep_async_and_nan_guard(pair):
+    """the step summary computed behind the step without stalling the host, scalar min/max
+    (config_print_global_minmax_sca, TI:8322-8342) and the NaN tests of TI:8258-8281."""
+    d, cfg, o, g = pair
+    o.load_block(d); g.load_block(d)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    o.atm_srk3(dt)
+    g.atm_srk3(dt); g.summarize_timestep_async()            # both only enqueued; the fetch below is the first wait
+    mm, nans = g.summarize_timestep_fetch()
+    assert nans == (0, 0)
+    assert np.allclose(mm[:4], o.summarize_timestep(), rtol=1e-12, atol=0)
+    nC = d["nCells"]
+    q = g.get_array("scalars", 2)[:nC]
+    for s in range(d["num_scalars"]):
+        assert mm[4 + 2 * s] == min(0.0, q[..., s].min()) and mm[5 + 2 * s] == max(0.0, q[..., s].max()), s
+    w = g.get_array("w", 2)
+    w[3, 5] = np.nan; w[7, 2] = np.nan
+    g.set_array("w", w, 2)
+    g.summarize_timestep_async()
+    mm2, nans = g.summarize_timestep_fetch(scalars=False)
+    assert nans == (2, 0) and len(mm2) == 4 and np.allclose(mm2[2:], mm[2:4])
+    with pytest.raises(RuntimeError):
+        g.summarize_timestep_fetch()                         # nothing pending
+
+
 def test_ten_steps_and_invariants(pair):
     d, cfg, o, g = pair
     o.load_block(d); g.load_block(d)
