@@ -167,6 +167,41 @@ def test_summarize_timestep_async_and_nan_guard(pair):
         g.summarize_timestep_fetch()                         # nothing pending
 
 
+VARIANTS = {
+    # namelist options of SURVEY.md §5 away from their defaults; each one switches kernels or code paths
+    "order3_substeps4": dict(config_time_integration_order=3, config_number_of_sub_steps=4),
+    "no_dynamics_split": dict(config_dynamics_split_steps=1, config_number_of_sub_steps=6),
+    "fixed_mixing": dict(config_horiz_mixing="2d_fixed", config_h_mom_eddy_visc2=1.0e4, config_h_theta_eddy_visc2=1.0e4,
+                         config_h_mom_eddy_visc4=1.0e13, config_h_theta_eddy_visc4=1.0e13),
+    "vertical_mixing": dict(config_v_mom_eddy_visc2=10.0, config_v_theta_eddy_visc2=10.0, config_mix_full=False),
+    "rayleigh_u_and_cam_damping": dict(config_rayleigh_damp_u=True, config_number_rayleigh_damp_u_levels=4,
+                                       config_mpas_cam_coef=2.0, config_number_cam_damping_levels=3),
+    "no_apvm_not_monotonic": dict(config_apvm_upwinding=0.0, config_monotonic=False, config_epssm=0.2, config_smdiv=0.2),
+    "generic_kernels": dict(),          # MPASB_GENERIC_KERNELS=1: the one-thread-per-(level, column) family
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_namelist_variants(tiny_case, variant, monkeypatch):
+    """Two steps with non-default namelist options (and with the generic kernel family forced) stay within the
+    north-star bar of the oracle run with the same options."""
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d, cfg0 = tiny_case
+    cfg = dict(cfg0, **VARIANTS[variant])
+    if variant == "generic_kernels":
+        monkeypatch.setenv("MPASB_GENERIC_KERNELS", "1")
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    for _ in range(2):
+        o.atm_srk3(dt); g.atm_srk3(dt)
+        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+    worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
+    assert max(worst.values()) <= 10 * TOL_STEP, (variant, worst)
+    g.close(); o.close()
+
+
 def test_ten_steps_and_invariants(pair):
     d, cfg, o, g = pair
     o.load_block(d); g.load_block(d)
