@@ -1272,3 +1272,209 @@ __global__ void __launch_bounds__(VIC_WARPS * 32) k3_vert_imp_coefs(const Dev D,
         ST(D.gamma_tri, i, sel(k_mid, mk2(s_c[o], s_c[o + 1]), 0.0));
     }
 }
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, parts (c) and (d), rk 1
+// del^2 of delsq_u on vertices (TI:5512-5529) and on cells (TI:5532-5551)
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_vertex(const Dev D) {
+    CW_SETUP(D.nVertices)
+    const int lj = min(lane, 2);
+    const int my_e = D.edgesOnVertex[3 * i + lj];
+    const real my_s = D.invAreaTriangle[i] * D.dcEdge[my_e] * D.edgesOnVertex_sign[3 * i + lj];
+    r2 acc = mk2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < 3; j++) acc = acc + BC(my_s, j) * LD(D.delsq_u, BC(my_e, j));
+    ST(D.delsq_vorticity, i, sel(lv.lt(nl), acc, 0.0));
+}
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_s = D.invAreaCell[i] * D.dvEdge[my_e] * D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    r2 acc = mk2(0.0, 0.0);
+#define DELSQ_C(E) { const r2 du = LD(D.delsq_u, BC(my_e, (E))); acc = selb((E) < ne, acc + BC(my_s, (E)) * du, acc); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) DELSQ_C(e)
+    for (int e = CW_NE; e < ne; e++) DELSQ_C(e)
+#undef DELSQ_C
+    ST(D.delsq_divergence, i, sel(lv.lt(nl), acc, 0.0));
+}
+// owned edges: del^4 of u (TI:5558-5584) and the final sum (TI:5694-5701).
+// Restrictions (the host falls back to k_dt_edge_d otherwise): v_mom_eddy_visc2 == 0, no Rayleigh damping of u.
+__global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const DynTendArgs A) {
+    CW_SETUP(D.nEdgesSolve)
+    r2 tue = LD(D.tend_u_euler, i);
+    if (A.h_mom_eddy_visc4 > 0.0) {
+        const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+        const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
+        const real u_mix_scale = D.meshScalingDel4[i] * A.h_mom_eddy_visc4;
+        const real r_dc = u_mix_scale * A.del4u_div_factor * D.invDcEdge[i];
+        const real r_dv = u_mix_scale * rmin(D.invDvEdge[i], 4 * D.invDcEdge[i]);
+        const r2 u_diffusion = LD(D.rho_edge, i) * ((LD(D.delsq_divergence, cell2) - LD(D.delsq_divergence, cell1)) * r_dc
+                                                   - (LD(D.delsq_vorticity, vertex2) - LD(D.delsq_vorticity, vertex1)) * r_dv);
+        tue = tue - u_diffusion;
+    }
+    const r2 tu = LD(D.tend_u, i) + tue + LD(D.tend_ru_physics, i);
+    const b2 k_lt_nl = lv.lt(nl);
+    ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
+    ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_advance_scalars_mono_work, edge part (C2)
+// high-order flux of scalar s (TI:4356-4413: one expression when the stencil has 10 cells, a running sum otherwise),
+// upwind flux and their difference (TI:4467-4487); same arithmetic as k_mono_edge2
+__device__ __forceinline__ r2 max0(r2 a) { return mk2(rmax(0.0, a.x), rmax(0.0, a.y)); }
+__device__ __forceinline__ r2 min0(r2 a) { return mk2(rmin(0.0, a.x), rmin(0.0, a.y)); }
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, real dt) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
+    const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
+    // every load is unconditional (an inactive edge, one without an owned cell, runs zero stencil iterations)
+    const int nadv_i = D.nAdvCellsForEdge[i];
+    const int nadv = (cell1 < D.nCellsSolve || cell2 < D.nCellsSolve) ? nadv_i : 0;
+    const int lj = min(lane, 14);
+    const int my_c = D.advCellsForEdge[(unsigned)i * 15 + lj];
+    const real my_a = D.adv_coefs[(unsigned)i * 15 + lj], my_b = D.adv_coefs_3rd[(unsigned)i * 15 + lj];
+    const real my_wp = my_a + my_b, my_wm = my_a - my_b;
+    const r2 uh = LD(D.ruAvg, i);
+    const r2 so1 = LD(so, cell1), so2 = LD(so, cell2);
+    const bool ten = nadv == 10;                                // warp-uniform: TI:4371-4384 vs TI:4386-4399
+    const bool px = uh.x > 0, py = uh.y > 0;
+    const real sx = sign1(uh.x), sy = sign1(uh.y);
+    r2 acc = mk2(0.0, 0.0);
+#pragma unroll 5
+    for (int j = 0; j < nadv; j++) {
+        const r2 q2 = LD(sn, BC(my_c, j));
+        const real a = BC(my_a, j), b = BC(my_b, j), wp = BC(my_wp, j), wm = BC(my_wm, j);
+        const real wx = ten ? (px ? wp : wm) : uh.x * (a + sx * b);
+        const real wy = ten ? (py ? wp : wm) : uh.y * (a + sy * b);
+        acc.x = acc.x + wx * q2.x;
+        acc.y = acc.y + wy * q2.y;
+    }
+    const r2 flux = ten ? uh * acc : acc;
+    const r2 fup = D.dvEdge[i] * dt * (max0(uh) * so1 + min0(uh) * so2);
+    const b2 k_lt_nl = lv.lt(nl);
+    ST(D.flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
+    ST(D.flux_tmp, i, sel(k_lt_nl, dt * flux - fup, 0.0));
+}
+
+// ------------------------------------------------------------------ atm_advance_scalars_mono_work, the other parts
+__device__ __forceinline__ r2 max2(r2 a, r2 b) { return mk2(rmax(a.x, b.x), rmax(a.y, b.y)); }
+__device__ __forceinline__ r2 min2(r2 a, r2 b) { return mk2(rmin(a.x, b.x), rmin(a.y, b.y)); }
+// (B) owned cells: re-integrated density, TI:4177-4204
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real dt) {
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le], my_dv = D.dvEdge[my_e];
+    const real invArea = D.invAreaCell[i];
+    r2 r = mk2(0.0, 0.0);
+#define RHO_INT_EDGE(E) { const r2 ru = LD(D.ruAvg, BC(my_e, (E))); r = selb((E) < ne, r - BC(my_sgn, (E)) * ru * BC(my_dv, (E)) * invArea, r); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) RHO_INT_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) RHO_INT_EDGE(e)
+#undef RHO_INT_EDGE
+    const r2 ww = LD(D.wwAvg, i);
+    ST(D.rho_zz_int, i, sel(lv.lt(nl), LD(D.rho_zz, i) + dt * (r - LD(D.rdzw, 0) * (dn1(ww) - ww)), 0.0));
+}
+// (C1) owned cells: vertical fluxes, bounds, vertical part of the upwind update and of scale_arr  TI:4277-4344, 4426-4459
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, real dt, real coef3) {
+    CW_SETUP(D.nCellsSolve)
+    const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
+    const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
+    const int ne = D.nEdgesOnCell[i];
+    const int my_c = D.cellsOnCell[(unsigned)i * D.maxEdges + min(lane, ne - 1)];
+    const r2 q = LD(so, i), n = LD(sn, i), ww = LD(D.wwAvg, i), rho = LD(D.rho_zz, i);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdnw = LD(D.rdzw, 0);
+    const r2 qm1 = up1(q), qp1 = dn1(q), nm1 = up1(n), nm2 = up2(n), np1 = dn1(n);
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl), kk_edge = lv.eq(1) || lv.eq(nl - 1);
+    // interface k: upwind flux and (high-order - upwind) flux; zero at the boundaries
+    const r2 fu = dt * (max0(ww) * qm1 + min0(ww) * q);
+    const r2 raw = sel(kk_edge, ww * (fm * n + fp * nm1), flux3_2(nm2, nm1, n, np1, ww, coef3));
+    const r2 wd0 = sel(k_mid, dt * raw - fu, 0.0);
+    const r2 wd1 = dn1(wd0);
+    // bounds over the column and the neighbouring cells
+    r2 smax = sel(lv.eq(0), max2(q, qp1), sel(lv.eq(nl - 1), max2(q, qm1), max2(max2(qm1, q), qp1)));
+    r2 smin = sel(lv.eq(0), min2(q, qp1), sel(lv.eq(nl - 1), min2(q, qm1), min2(min2(qm1, q), qp1)));
+#define MONO_NBR(E) { const r2 v = LD(so, BC(my_c, (E))); smax = selb((E) < ne, max2(smax, v), smax); smin = selb((E) < ne, min2(smin, v), smin); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) MONO_NBR(e)
+    for (int e = CW_NE; e < ne; e++) MONO_NBR(e)
+#undef MONO_NBR
+    // upwind vertical update, TI:4428-4446
+    r2 snew = q * rho;
+    snew = sel(lv.lt(nl - 1), snew - dn1(fu) * rdnw, snew);
+    snew = sel(lv.ge(1), snew + fu * rdnw, snew);
+    ST(D.wdtn, i, wd0);
+    ST(D.s_max, i, sel(k_lt_nl, smax, 0.0));
+    ST(D.s_min, i, sel(k_lt_nl, smin, 0.0));
+    ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
+    ST(D.scale_arr, i, sel(k_lt_nl, -rdnw * (min0(wd1) - max0(wd0)), 0.0));                     // SCALE_IN
+    ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));       // SCALE_OUT
+}
+// (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const real invArea = D.invAreaCell[i];
+    r2 snew = LD(D.scalar_new, i), sin_ = LD(D.scale_arr, i), sout = LD(D.scale_arr + D.cellPlane, i);
+#define MONO3_EDGE(E)                                                                                       \
+    {                                                                                                       \
+        const int iEdge = BC(my_e, (E)); const real sg = BC(my_sgn, (E));                                   \
+        const r2 ft = LD(D.flux_tmp, iEdge), fup = LD(D.flux_upwind_tmp, iEdge);                            \
+        snew = selb((E) < ne, snew - sg * fup * invArea, snew);                                             \
+        sout = selb((E) < ne, sout - max0(sg * ft) * invArea, sout);                                        \
+        sin_ = selb((E) < ne, sin_ - min0(sg * ft) * invArea, sin_);                                        \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) MONO3_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) MONO3_EDGE(e)
+#undef MONO3_EDGE
+    const real eps = 1.e-20;
+    const r2 rl = LD(rho_lim, i);
+    const r2 f_in = (LD(D.s_max, i) * rl - snew) / (sin_ + eps);
+    const r2 f_out = (LD(D.s_min, i) * rl - snew) / (sout - eps);
+    const b2 k_lt_nl = lv.lt(nl);
+    ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
+    ST(D.scale_arr, i, sel(k_lt_nl, min2(splat(1.0), max0(f_in)), 0.0));
+    ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, min2(splat(1.0), max0(f_out)), 0.0));
+}
+// (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
+    CW_SETUP(D.nEdges)
+    const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    const real* __restrict__ s_in = D.scale_arr; const real* __restrict__ s_out = D.scale_arr + D.cellPlane;
+    const r2 flux = LD(D.flux_tmp, i);
+    const r2 f = max0(flux) * min2(LD(s_out, cell1), LD(s_in, cell2))
+               + min0(flux) * min2(LD(s_in, cell1), LD(s_out, cell2));
+    ST(D.flux_arr, i, sel(lv.lt(nl), f, 0.0));
+}
+// (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* __restrict__ rho_div) {
+    CW_SETUP(D.nCells)
+    real* out = D.scalars_2 + (size_t)s * D.cellPlane;
+    const b2 k_lt_nl = lv.lt(nl);
+    if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); return; }       // warp-uniform
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const real invArea = D.invAreaCell[i];
+    const r2 s_in = LD(D.scale_arr, i), s_out = LD(D.scale_arr + D.cellPlane, i), wd = LD(D.wdtn, i);
+    const r2 w0 = sel(lv.ge(1) && k_lt_nl, max0(wd) * min2(up1(s_out), s_in) + min0(wd) * min2(s_out, up1(s_in)), 0.0);
+    const r2 w1 = dn1(w0);
+    r2 snew = LD(D.scalar_new, i);
+#define MONO5_EDGE(E) { const r2 fa = LD(D.flux_arr, BC(my_e, (E))); snew = selb((E) < ne, snew - BC(my_sgn, (E)) * fa * invArea, snew); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) MONO5_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) MONO5_EDGE(e)
+#undef MONO5_EDGE
+    snew = (snew + (-LD(D.rdzw, 0) * (w1 - w0))) / LD(rho_div, i);
+    ST(out, i, sel(k_lt_nl, max0(snew), 0.0));
+}

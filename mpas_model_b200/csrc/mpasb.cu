@@ -473,10 +473,11 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
     else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
         if (A.h_mom_eddy_visc4 > 0.0) {
-            LAUNCH(k_dt_delsq_vertex, D.nVertices, 0, D);
-            LAUNCH(k_dt_delsq_cell, D.nCells, 0, D);
+            if (h->colwarp) { LAUNCHW(k2_dt_delsq_vertex, D.nVertices, D); LAUNCHW(k2_dt_delsq_cell, D.nCells, D); }
+            else { LAUNCH(k_dt_delsq_vertex, D.nVertices, 0, D); LAUNCH(k_dt_delsq_cell, D.nCells, 0, D); }
         }
-        LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
+        if (h->colwarp && !(A.v_mom_eddy_visc2 > 0.0) && !A.rayleigh_damp_u) LAUNCHW(k2_dt_edge_d, D.nEdgesSolve, D, A);
+        else LAUNCH(k_dt_edge_d, D.nEdgesSolve, 0, D, A);
     }
     if (in_step && exchange_async(h, "dynamics:tend_u")) return 1;
     if (rk_step == 1) {
@@ -622,15 +623,15 @@ static int advance_scalars_mono(H* h, real dt) {              // TI:4012-4734
     const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
     LAUNCH(k_mono_pre, D.nCellsSolve, 0, D, dt);
     if (exchange(h, "dynamics:scalars_old")) return 1;
-    if (adv_density) LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt);
+    if (adv_density) { if (h->colwarp) LAUNCHW(k2_mono_rho_int, D.nCellsSolve, D, dt); else LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt); }
     const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
     for (int s = 0; s < D.num_scalars; s++) {
-        LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
-        LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
-        LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+        if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+        if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+        if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
         if (exchange(h, "dynamics:scale")) return 1;
-        LAUNCH(k_mono_edge4, D.nEdges, 0, D);
-        LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+        if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+        if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
     }
     return 0;
 }
@@ -639,17 +640,17 @@ static void mono_pre(H* h, real dt) { LAUNCH(k_mono_pre, h->D.nCellsSolve, 0, h-
 static void mono_a(H* h, real dt, int s) {
     const Dev& D = h->D;
     const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
-    if (s == 0 && adv_density) LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt);
+    if (s == 0 && adv_density) { if (h->colwarp) LAUNCHW(k2_mono_rho_int, D.nCellsSolve, D, dt); else LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt); }
     const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
-    LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
-    LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
-    LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+    if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+    if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+    if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
 }
 static void mono_b(H* h, int s) {
     const Dev& D = h->D;
     const real* rho = h->cfg.config_split_dynamics_transport ? D.rho_zz_int : D.rho_zz_2;
-    LAUNCH(k_mono_edge4, D.nEdges, 0, D);
-    LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+    if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+    if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
 }
 static void init_coupled_diagnostics(H* h) {                  // TI:6776-7010
     const real rcv = rgas / (cp - rgas);
