@@ -1478,3 +1478,127 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
     snew = (snew + (-LD(D.rdzw, 0) * (w1 - w0))) / LD(rho_div, i);
     ST(out, i, sel(k_lt_nl, max0(snew), 0.0));
 }
+
+// ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f) split in two
+// k2_dt_cell_f carries the operands of both the w and the theta_m tendency (80 registers with 192 bytes of spills, 24
+// warps per SM).  The two tendencies share only rw and the cell's connectivity, so they are also available as two
+// kernels with about half the live state each; same expressions, same order: bit-identical to k2_dt_cell_f.
+#ifndef MB_CELL_FW
+#define MB_CELL_FW 5
+#endif
+#ifndef MB_CELL_FT
+#define MB_CELL_FT 4
+#endif
+__global__ void __launch_bounds__(CW_THREADS, MB_CELL_FW) k2_dt_cell_fw(const Dev D, const DynTendArgs A) {     // tend_w, TI:5713-5757, 5838-5945
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const real invArea = D.invAreaCell[i];
+    r2 tw = mk2(0.0, 0.0);
+#define CELL_FW_EDGE(E) { const r2 fxw = LD(D.adv_flux_w, BC(my_e, (E))); tw = selb((E) < ne, tw - BC(my_sgn, (E)) * fxw, tw); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) CELL_FW_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) CELL_FW_EDGE(e)
+#undef CELL_FW_EDGE
+    r2 twe = LD(D.tend_w_euler, i);
+    const r2 twe_in = twe;
+    const b2 k_ge1 = lv.ge(1), k_lt_nl = lv.lt(nl);
+    if (A.rk_step == 1 && A.h_mom_eddy_visc4 > 0.0) {
+        const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+        const real my_f = D.meshScalingDel4[my_e];
+        const real my_dv = D.dvEdge[my_e], my_idc = D.invDcEdge[my_e];
+        const real r_areaCell = A.h_mom_eddy_visc4 * invArea;
+#define CELL_FW_DEL4(E)                                                                                     \
+        {                                                                                                   \
+            const real edge_sign = BC(my_f, (E)) * r_areaCell * BC(my_dv, (E)) * BC(my_sgn, (E)) * BC(my_idc, (E)); \
+            const r2 d = LD(D.delsq_w, BC(my_c2, (E))) - LD(D.delsq_w, BC(my_c1, (E)));                     \
+            twe = selb((E) < ne, twe - edge_sign * d, twe);                                                 \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) CELL_FW_DEL4(e)
+        for (int e = CW_NE; e < ne; e++) CELL_FW_DEL4(e)
+#undef CELL_FW_DEL4
+    }
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdzu = LD(D.rdzu, 0);
+    const r2 rw = LD(D.rw, i), w = LD(D.w_2, i);
+    const r2 rwm1 = up1(rw);
+    const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1), kk_zero = lv.lt(1) || lv.ge(nl);
+    const r2 wm1 = up1(w), wm2 = up2(w), wp1 = dn1(w);
+    const r2 f2 = 0.25 * (rw + rwm1) * (w + wm1);
+    const r2 f3 = flux3_2(wm2, wm1, w, wp1, 0.5 * (rw + rwm1), 1.0);
+    const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(kk_edge, f2, f3));
+    const r2 f1 = dn1(fz);
+    tw = tw * invArea - rdzu * (f1 - fz);
+    if (A.rk_step == 1) {
+        const r2 pp = LD(D.pressure_p, i), dpdz = LD(D.dpdz, i), cqw = LD(D.cqw, i);
+        const r2 twe_new = twe - cqw * (rdzu * (pp - up1(pp)) - (fm * dpdz + fp * up1(dpdz)));
+        twe = sel(k_ge1 && k_lt_nl, twe_new, twe_in);
+        ST(D.tend_w_euler, i, twe);
+    }
+    ST(D.tend_w, i, sel(k_ge1 && k_lt_nl, tw + twe, 0.0));
+}
+__global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const Dev D, const DynTendArgs A) {     // tend_theta, TI:5956-6016, 6066-6126, 6134-6197
+    CW_SETUP(D.nCellsSolve)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    const real my_dv = D.dvEdge[my_e];
+    const real invArea = D.invAreaCell[i];
+    r2 tt = mk2(0.0, 0.0);
+#define CELL_FT_EDGE(E) { const r2 fxt = LD(D.adv_flux_theta, BC(my_e, (E))); tt = selb((E) < ne, tt - BC(my_sgn, (E)) * fxt, tt); }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) CELL_FT_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) CELL_FT_EDGE(e)
+#undef CELL_FT_EDGE
+    r2 tte = LD(D.tend_theta_euler, i);
+    if (A.rk_step > 1) {          // perturbation flux for the rtheta_pp equation, TI:5995-6016
+#define CELL_FT_PERT(E)                                                                                     \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                \
+            const real sg = BC(my_sgn, (E)), dv = BC(my_dv, (E));                                           \
+            const r2 flux = sg * dv * (LD(D.ru_save, iEdge) - LD(D.ru, iEdge)) * 0.5 * (LD(D.theta_m, cell2) + LD(D.theta_m, cell1)); \
+            tt = selb((E) < ne, tt - flux, tt);                                                             \
+        }
+#pragma unroll 3
+        for (int e = 0; e < CW_NE; e++) CELL_FT_PERT(e)
+        for (int e = CW_NE; e < ne; e++) CELL_FT_PERT(e)
+#undef CELL_FT_PERT
+    }
+    const b2 k_lt_nl = lv.lt(nl);
+    if (A.rk_step == 1 && A.h_theta_eddy_visc4 > 0.0) {
+        const real my_f = D.meshScalingDel4[my_e], my_idc = D.invDcEdge[my_e];
+        const real r_areaCell = A.h_theta_eddy_visc4 * A.prandtl_inv * invArea;
+#define CELL_FT_DEL4(E)                                                                                     \
+        {                                                                                                   \
+            const real edge_sign = BC(my_f, (E)) * r_areaCell * BC(my_dv, (E)) * BC(my_sgn, (E)) * BC(my_idc, (E)); \
+            const r2 d = LD(D.delsq_theta, BC(my_c2, (E))) - LD(D.delsq_theta, BC(my_c1, (E)));             \
+            tte = selb((E) < ne, tte - edge_sign * d, tte);                                                 \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) CELL_FT_DEL4(e)
+        for (int e = CW_NE; e < ne; e++) CELL_FT_DEL4(e)
+#undef CELL_FT_DEL4
+    }
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0);
+    const r2 rw = LD(D.rw, i), t = LD(D.theta_m_2, i), ts = LD(D.theta_m, i), rws = LD(D.rw_save, i);
+    const r2 rho = LD(D.rho_zz_2, i), tend_rho = LD(D.tend_rho, i), rtdiab = LD(D.rt_diabatic_tend, i);
+    const r2 trp = LD(D.tend_rtheta_physics, i);
+    const b2 kk_zero = lv.lt(1) || lv.ge(nl);
+    const r2 tm1 = up1(t), tm2 = up2(t), tp1 = dn1(t), tsm1 = up1(ts);
+    const r2 ftop = rws * (fm * t + fp * tm1);
+    const r2 flow = rw * (fm * t + fp * tm1);
+    const r2 f3 = flux3_2(tm2, tm1, t, tp1, rw, A.coef_3rd_order);
+    const r2 fpert = sel(lv.eq(1), flow, f3) + (rws - rw) * (fm * ts + fp * tsm1);
+    const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(lv.eq(nl - 1), ftop, fpert));
+    const r2 f1 = dn1(fz);
+    tt = tt * invArea - rdzw * (f1 - fz);
+    const r2 out_rthdynten = sel(k_lt_nl, (tt - tend_rho * t) / rho, 0.0);
+    tt = tt + rho * rtdiab;
+    if (A.rk_step == 1) ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
+    ST(D.rthdynten, i, out_rthdynten);
+    ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
+}

@@ -493,7 +493,9 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
             h->launches++;
         }
         else LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
-        LAUNCHW(k2_dt_cell_f, D.nCellsSolve, D, A);
+        static const bool split_f = getenv("MPASB_SPLIT_CELL_F") != nullptr;
+        if (split_f) { LAUNCHW(k2_dt_cell_fw, D.nCellsSolve, D, A); LAUNCHW(k2_dt_cell_ft, D.nCellsSolve, D, A); }
+        else LAUNCHW(k2_dt_cell_f, D.nCellsSolve, D, A);
     }
     else LAUNCH(k_dt_cell_f, D.nCellsSolve, 0, D, A);
     return 0;
