@@ -139,6 +139,15 @@ int  mpasb_set_halo_lists(mpasb_handle h, int kind /*0 cell,1 edge,2 vertex*/, i
 int  mpasb_comm_init(mpasb_handle h, int rank, int world_size, const void* nccl_unique_id /*128 bytes*/);
 int  mpasb_get_nccl_unique_id(void* out128);
 int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HALOS:90-167 names */
+/* Optional: exchanges by direct stores into the neighbours' mailboxes over NVLink (CUDA IPC) instead of NCCL send/recv.
+ * After mpasb_set_halo_lists and mpasb_comm_init, on every rank of ONE node (2..9 ranks):
+ *   n = mpasb_p2p_max_message(h)                      largest message of this rank, in reals
+ *   mpasb_p2p_prepare(h, max over ranks of n, out)    allocates mailbox + flags, writes two 64-byte IPC handles
+ *   mpasb_p2p_open(h, handles of all ranks)           world x 128 bytes in rank order (host all-gather)
+ * From then on every exchange of the handle is one put kernel and one get kernel. */
+long mpasb_p2p_max_message(mpasb_handle h);
+int  mpasb_p2p_prepare(mpasb_handle h, long slot_elems, void* out_handles128);
+int  mpasb_p2p_open(mpasb_handle h, const void* all_handles);
 
 /* 1 if every kernel keeps the reference's operation order without FMA contraction (results bit-identical to
  * the fp64 CPU arithmetic; the only build at present), 0 for a relaxed build */

@@ -33,6 +33,12 @@ struct HaloState {
     void* comm = nullptr;               // ncclComm_t
     void* nccl_lib = nullptr;
     int parity = 0;                     // flips with mpas_pool_shift_time_levels
+    // CUDA-IPC peer-to-peer exchange (k_halo_put / k_halo_get): own mailbox and flags, the peers' mappings, message counters
+    bool p2p = false;
+    size_t slot_elems = 0;
+    real* mbox = nullptr; unsigned long long* flags = nullptr; unsigned* done = nullptr;     // done[0]: put, done[1]: get
+    std::vector<real*> peer_mbox; std::vector<unsigned long long*> peer_flags;
+    std::vector<unsigned long long> seq_send, seq_recv;     // per peer rank
     std::map<std::string, HaloGroupPlan> plans[2];
 };
 

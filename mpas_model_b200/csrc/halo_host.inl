@@ -71,6 +71,13 @@ static void halo_free_plans(HaloState& hs) {
 }
 static void halo_destroy(HaloState& hs) {
     halo_free_plans(hs);
+    for (size_t r = 0; r < hs.peer_mbox.size(); r++) {
+        if (hs.peer_mbox[r] && (int)r != hs.rank) cudaIpcCloseMemHandle(hs.peer_mbox[r]);
+        if (hs.peer_flags[r] && (int)r != hs.rank) cudaIpcCloseMemHandle(hs.peer_flags[r]);
+    }
+    if (hs.mbox) cudaFree(hs.mbox);
+    if (hs.flags) cudaFree(hs.flags);
+    if (hs.done) cudaFree(hs.done);
     if (hs.comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy((ncclComm_t)hs.comm); hs.comm = nullptr; }
 }
 
@@ -121,7 +128,8 @@ static int halo_build_plan(H* h, const GroupDef& gd, HaloGroupPlan& P) {
     std::vector<HaloSeg> pack, unpack;
     std::vector<int> idx_s, idx_r;
     size_t soff = 0, roff = 0;
-    for (int peer : peers) {
+    for (size_t pi = 0; pi < peers.size(); pi++) {
+        const int peer = peers[pi];
         P.send_off.push_back(soff); P.recv_off.push_back(roff);
         for (const GroupField& gf : gd.fields) {
             FieldRec* f = find_field(h, gf.name); if (!f) return 1;
@@ -140,13 +148,13 @@ static int halo_build_plan(H* h, const GroupDef& gd, HaloGroupPlan& P) {
                     if (!(gf.layers & (1 << l))) continue;
                     const int li = ni * K.n_layers + l;
                     if (K.n_send[li]) {
-                        HaloSeg s; s.field = base + p * plane; s.idx_off = (int)idx_s.size(); s.count = K.n_send[li]; s.width = width; s.buf_off = soff; s.stride = stride;
+                        HaloSeg s; s.field = base + p * plane; s.idx_off = (int)idx_s.size(); s.count = K.n_send[li]; s.width = width; s.peer = (int)pi; s.buf_off = soff; s.stride = stride;
                         idx_s.insert(idx_s.end(), K.h_send.begin() + K.send_off[li], K.h_send.begin() + K.send_off[li + 1]);
                         pack.push_back(s); soff += (size_t)s.count * width;
                         P.max_seg = std::max(P.max_seg, (size_t)s.count * width);
                     }
                     if (K.n_recv[li]) {
-                        HaloSeg s; s.field = base + p * plane; s.idx_off = (int)idx_r.size(); s.count = K.n_recv[li]; s.width = width; s.buf_off = roff; s.stride = stride;
+                        HaloSeg s; s.field = base + p * plane; s.idx_off = (int)idx_r.size(); s.count = K.n_recv[li]; s.width = width; s.peer = (int)pi; s.buf_off = roff; s.stride = stride;
                         idx_r.insert(idx_r.end(), K.h_recv.begin() + K.recv_off[li], K.h_recv.begin() + K.recv_off[li + 1]);
                         unpack.push_back(s); roff += (size_t)s.count * width;
                         P.max_seg = std::max(P.max_seg, (size_t)s.count * width);
@@ -179,9 +187,31 @@ static int halo_exchange(H* h, const char* group, cudaStream_t stream) {
     }
     HaloGroupPlan& P = it->second;
     if (P.peers.empty()) return 0;
+    const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((P.max_seg + 255) / 256, 64));
+    if (hs.p2p) {
+        // one put kernel and one get kernel; no library call, no intermediate buffers
+        if ((int)P.peers.size() > P2P_MAXP) { h->err = "p2p exchange: more than 8 neighbours"; return 1; }
+        P2PPeers pp; memset(&pp, 0, sizeof(pp));
+        pp.n = (int)P.peers.size();
+        for (int p = 0; p < pp.n; p++) {
+            const int q = P.peers[p];
+            if (P.send_cnt[p] > hs.slot_elems || P.recv_cnt[p] > hs.slot_elems) { h->err = "p2p exchange: message larger than the mailbox slot"; return 1; }
+            pp.seq_send[p] = P.send_cnt[p] ? ++hs.seq_send[q] : 0;
+            pp.seq_recv[p] = P.recv_cnt[p] ? ++hs.seq_recv[q] : 0;
+            pp.remote[p] = hs.peer_mbox[q] + ((size_t)hs.rank * 2 + (pp.seq_send[p] & 1)) * hs.slot_elems;
+            pp.local[p] = hs.mbox + ((size_t)q * 2 + (pp.seq_recv[p] & 1)) * hs.slot_elems;
+            pp.remote_arrived[p] = hs.peer_flags[q] + hs.rank;
+            pp.remote_consumed[p] = hs.peer_flags[q] + hs.world + hs.rank;
+            pp.local_arrived[p] = hs.flags + q;
+            pp.local_consumed[p] = hs.flags + hs.world + q;
+            pp.send_off[p] = P.send_off[p]; pp.recv_off[p] = P.recv_off[p];
+        }
+        if (P.n_pack) { k_halo_put<<<dim3(gx, std::min(P.n_pack, 256)), 256, 0, stream>>>(P.d_pack, P.d_idx_send, P.n_pack, pp, hs.done); h->launches++; }
+        if (P.n_unpack) { k_halo_get<<<dim3(gx, std::min(P.n_unpack, 256)), 256, 0, stream>>>(P.d_unpack, P.d_idx_recv, P.n_unpack, pp, hs.done + 1); h->launches++; }
+        return 0;
+    }
     if (!hs.comm) { h->err = "halo lists are set but mpasb_comm_init was not called"; return 1; }
     NcclApi* a = nccl_api();
-    const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((P.max_seg + 255) / 256, 64));
     if (P.n_pack) { k_halo_pack<<<dim3(gx, std::min(P.n_pack, 256)), 256, 0, stream>>>(P.d_pack, P.d_idx_send, P.d_sendbuf, P.n_pack); h->launches++; }
     a->GroupStart();
     for (size_t p = 0; p < P.peers.size(); p++) {
@@ -191,6 +221,58 @@ static int halo_exchange(H* h, const char* group, cudaStream_t stream) {
     ncclResult_t r = a->GroupEnd();
     if (r != ncclSuccess) { h->err = std::string("nccl: ") + a->GetErrorString(r); return 1; }
     if (P.n_unpack) { k_halo_unpack<<<dim3(gx, std::min(P.n_unpack, 256)), 256, 0, stream>>>(P.d_unpack, P.d_idx_recv, P.d_recvbuf, P.n_unpack); h->launches++; }
+    return 0;
+}
+
+// ---- CUDA-IPC peer-to-peer set-up: (1) every rank reports its largest message, (2) allocates mailbox + flags for the
+// largest one over all ranks and exports two IPC handles, (3) maps the handles of all ranks.
+extern "C" long mpasb_p2p_max_message(mpasb_handle h) {
+    cudaSetDevice(h->device);
+    HaloState& hs = h->halo;
+    size_t mx = 0;
+    for (const GroupDef& gd : group_table()) {
+        auto& plans = hs.plans[hs.parity];
+        auto it = plans.find(gd.name);
+        if (it == plans.end()) {
+            HaloGroupPlan P;
+            if (halo_build_plan(h, gd, P)) return -1;
+            it = plans.emplace(gd.name, P).first;
+        }
+        for (size_t p = 0; p < it->second.peers.size(); p++) mx = std::max(mx, std::max(it->second.send_cnt[p], it->second.recv_cnt[p]));
+    }
+    return (long)mx;
+}
+extern "C" int mpasb_p2p_prepare(mpasb_handle h, long slot_elems, void* out_handles128) {
+    cudaSetDevice(h->device);
+    HaloState& hs = h->halo;
+    if (hs.world < 2 || hs.world > P2P_MAXP + 1 || slot_elems <= 0) { h->err = "mpasb_p2p_prepare: needs 2..9 ranks (mpasb_comm_init first) and a positive slot"; return 1; }
+    hs.slot_elems = ((size_t)slot_elems + 1) / 2 * 2;                  // keeps every slot 16-byte aligned
+    const size_t mbytes = (size_t)hs.world * 2 * hs.slot_elems * sizeof(real), fbytes = (size_t)2 * hs.world * sizeof(unsigned long long);
+    CUDA_OK(cudaMalloc(&hs.mbox, mbytes)); CUDA_OK(cudaMalloc(&hs.flags, fbytes)); CUDA_OK(cudaMalloc(&hs.done, 2 * sizeof(unsigned)));
+    CUDA_OK(cudaMemset(hs.mbox, 0, mbytes)); CUDA_OK(cudaMemset(hs.flags, 0, fbytes)); CUDA_OK(cudaMemset(hs.done, 0, 2 * sizeof(unsigned)));
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hm, hf;
+    CUDA_OK(cudaIpcGetMemHandle(&hm, hs.mbox)); CUDA_OK(cudaIpcGetMemHandle(&hf, hs.flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two handles fill 128 bytes");
+    memcpy(out_handles128, &hm, 64); memcpy((char*)out_handles128 + 64, &hf, 64);
+    return 0;
+}
+extern "C" int mpasb_p2p_open(mpasb_handle h, const void* all_handles /* world x 128 bytes, rank order */) {
+    cudaSetDevice(h->device);
+    HaloState& hs = h->halo;
+    if (!hs.mbox) { h->err = "mpasb_p2p_open before mpasb_p2p_prepare"; return 1; }
+    hs.peer_mbox.assign(hs.world, nullptr); hs.peer_flags.assign(hs.world, nullptr);
+    hs.seq_send.assign(hs.world, 0); hs.seq_recv.assign(hs.world, 0);
+    for (int r = 0; r < hs.world; r++) {
+        if (r == hs.rank) { hs.peer_mbox[r] = hs.mbox; hs.peer_flags[r] = hs.flags; continue; }
+        cudaIpcMemHandle_t hm, hf;
+        memcpy(&hm, (const char*)all_handles + (size_t)r * 128, 64); memcpy(&hf, (const char*)all_handles + (size_t)r * 128 + 64, 64);
+        void* pm = nullptr; void* pf = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&pm, hm, cudaIpcMemLazyEnablePeerAccess));
+        CUDA_OK(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        hs.peer_mbox[r] = (real*)pm; hs.peer_flags[r] = (unsigned long long*)pf;
+    }
+    hs.p2p = true;
     return 0;
 }
 

@@ -292,7 +292,7 @@ __global__ void k_int_to_zero_based(int* __restrict__ dst, const int* __restrict
 // One launch packs every (field, list element, level) of one exchange group.  seg[] describes
 // contiguous runs of the send buffer: run r moves `count` columns of field `fld` listed in
 // idx[idx_off : idx_off+count] to buf[buf_off + j*width + k], width = levels moved per column.
-struct HaloSeg { real* field; int idx_off; int count; int width; size_t buf_off; int stride; };
+struct HaloSeg { real* field; int idx_off; int count; int width; int peer; size_t buf_off; int stride; };     // peer: index into the plan's peer list
 __global__ void k_halo_pack(const HaloSeg* __restrict__ seg, const int* __restrict__ idx, real* __restrict__ buf, int nseg) {
     for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
         const HaloSeg g = seg[s];
@@ -300,6 +300,82 @@ __global__ void k_halo_pack(const HaloSeg* __restrict__ seg, const int* __restri
         for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
             const int j = (int)(t / g.width), k = (int)(t % g.width);
             buf[g.buf_off + t] = g.field[(size_t)idx[g.idx_off + j] * g.stride + k];
+        }
+    }
+}
+
+// ---- the same exchange without NCCL: stores straight into the neighbour's mailbox over NVLink (CUDA IPC peer memory) ----
+// Every rank owns a mailbox [source rank][2 buffers][slot] and a flag array {arrived[source], consumed[destination]} of
+// 64-bit message counters; both are mapped into every peer with cudaIpcOpenMemHandle.  k_halo_put packs the send lists
+// directly into the peers' mailboxes (buffer = message number & 1), and its last block publishes the message number in
+// each peer's arrived[] after a system-scope fence.  k_halo_get waits for arrived[], unpacks from the local mailbox
+// (ld.global.cg: the lines were written by another GPU) and its last block publishes consumed[] to the senders, which
+// is what a sender checks before it reuses a buffer two messages later.
+#define P2P_MAXP 8
+struct P2PPeers {
+    int n;
+    real* remote[P2P_MAXP];                          // start of my message in peer p's mailbox
+    const real* local[P2P_MAXP];                     // start of peer p's message in my mailbox
+    unsigned long long* remote_arrived[P2P_MAXP];    // peer p's arrived[my rank]
+    unsigned long long* remote_consumed[P2P_MAXP];   // peer p's consumed[my rank]
+    const unsigned long long* local_arrived[P2P_MAXP];   // my arrived[p]
+    const unsigned long long* local_consumed[P2P_MAXP];  // my consumed[p]
+    unsigned long long seq_send[P2P_MAXP], seq_recv[P2P_MAXP];   // 0: nothing to send / receive in this exchange
+    size_t send_off[P2P_MAXP], recv_off[P2P_MAXP];   // start of the peer's part in the plan's contiguous layout (elements)
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__global__ void k_halo_put(const HaloSeg* __restrict__ seg, const int* __restrict__ idx, int nseg, const P2PPeers pp, unsigned* done) {
+    for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+        const HaloSeg g = seg[s];
+        const int p = g.peer;
+        if (threadIdx.x == 0 && pp.seq_send[p] > 2)            // the buffer last held message seq - 2: wait until it was unpacked
+            while (ld_acquire_sys(pp.local_consumed[p]) < pp.seq_send[p] - 2) { }
+        __syncthreads();
+        real* dst = pp.remote[p] + (g.buf_off - pp.send_off[p]);
+        const size_t total = (size_t)g.count * g.width;
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+            const int j = (int)(t / g.width), k = (int)(t % g.width);
+            dst[t] = g.field[(size_t)idx[g.idx_off + j] * g.stride + k];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {               // last block: every store of the grid is visible system-wide
+            *done = 0;
+            __threadfence_system();
+            for (int p = 0; p < pp.n; p++) if (pp.seq_send[p]) st_release_sys(pp.remote_arrived[p], pp.seq_send[p]);
+        }
+    }
+}
+__global__ void k_halo_get(const HaloSeg* __restrict__ seg, const int* __restrict__ idx, int nseg, const P2PPeers pp, unsigned* done) {
+    for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+        const HaloSeg g = seg[s];
+        const int p = g.peer;
+        if (threadIdx.x == 0) while (ld_acquire_sys(pp.local_arrived[p]) < pp.seq_recv[p]) { }
+        __syncthreads();
+        const real* src = pp.local[p] + (g.buf_off - pp.recv_off[p]);
+        const size_t total = (size_t)g.count * g.width;
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+            const int j = (int)(t / g.width), k = (int)(t % g.width);
+            g.field[(size_t)idx[g.idx_off + j] * g.stride + k] = __ldcg(src + t);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {               // last block: the mailbox buffers of this exchange are free again
+            *done = 0;
+            for (int p = 0; p < pp.n; p++) if (pp.seq_recv[p]) st_release_sys(pp.remote_consumed[p], pp.seq_recv[p]);
         }
     }
 }

@@ -252,6 +252,23 @@ class Dycore(Backend):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.lib.mpasb_comm_init(self._h, C.c_int(rank), C.c_int(world_size), buf), "comm_init")
 
+    def p2p_init(self, dist):
+        """Switch the halo exchanges of this handle to direct NVLink stores (CUDA IPC); ``dist`` is the host process
+        group used to agree on the mailbox size and to all-gather the IPC handles."""
+        self.lib.mpasb_p2p_max_message.restype = C.c_long
+        n = int(self.lib.mpasb_p2p_max_message(self._h))
+        if n < 0:
+            self._check(1, "p2p_max_message")
+        sizes = [None] * dist.get_world_size()
+        dist.all_gather_object(sizes, n)
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mpasb_p2p_prepare(self._h, C.c_long(max(max(sizes), 2)), buf), "p2p_prepare")
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, buf.raw)
+        allh = C.create_string_buffer(b"".join(handles), 128 * len(handles))
+        self._check(self.lib.mpasb_p2p_open(self._h, allh), "p2p_open")
+        dist.barrier()
+
     def nccl_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)
         if self.lib.mpasb_get_nccl_unique_id(buf) != 0:
