@@ -356,6 +356,9 @@ def main():
     if rank != 0:
         return
     line = line_common(args, n_cells, n_lev, dt, world)
+    if world > 1:
+        line["config"]["halo_exchange"] = ("CUDA-IPC put/get kernels over NVLink" if getattr(g, "p2p_on", False) else "pack -> NCCL send/recv -> unpack") \
+            + ("" if os.environ.get("MPASB_NO_OVERLAP") else ", 3 of the exchange groups overlapped with compute on a priority stream")
     if args.precision == "single":
         line["dtype"] = "f32"
         line["config"]["workload"] = line["config"]["workload"].replace("fp64", "fp32 (PRECISION=single build)")

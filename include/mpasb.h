@@ -144,10 +144,12 @@ int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HAL
  *   n = mpasb_p2p_max_message(h)                      largest message of this rank, in reals
  *   mpasb_p2p_prepare(h, max over ranks of n, out)    allocates mailbox + flags, writes two 64-byte IPC handles
  *   mpasb_p2p_open(h, handles of all ranks)           world x 128 bytes in rank order (host all-gather)
+ *   mpasb_p2p_enable(h, 1)                            once EVERY rank succeeded so far (otherwise all stay on NCCL)
  * From then on every exchange of the handle is one put kernel and one get kernel. */
 long mpasb_p2p_max_message(mpasb_handle h);
 int  mpasb_p2p_prepare(mpasb_handle h, long slot_elems, void* out_handles128);
 int  mpasb_p2p_open(mpasb_handle h, const void* all_handles);
+int  mpasb_p2p_enable(mpasb_handle h, int on);
 
 /* 1 if every kernel keeps the reference's operation order without FMA contraction (results bit-identical to
  * the fp64 CPU arithmetic; the only build at present), 0 for a relaxed build */

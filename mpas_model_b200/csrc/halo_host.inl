@@ -272,7 +272,13 @@ extern "C" int mpasb_p2p_open(mpasb_handle h, const void* all_handles /* world x
         CUDA_OK(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
         hs.peer_mbox[r] = (real*)pm; hs.peer_flags[r] = (unsigned long long*)pf;
     }
-    hs.p2p = true;
+    return 0;
+}
+// collective decision of the host: switch the peer-to-peer path on only when every rank mapped every peer
+extern "C" int mpasb_p2p_enable(mpasb_handle h, int on) {
+    HaloState& hs = h->halo;
+    if (on && (hs.peer_mbox.empty() || !hs.mbox)) { h->err = "mpasb_p2p_enable before mpasb_p2p_open"; return 1; }
+    hs.p2p = on != 0;
     return 0;
 }
 

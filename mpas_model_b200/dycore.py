@@ -252,22 +252,36 @@ class Dycore(Backend):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.lib.mpasb_comm_init(self._h, C.c_int(rank), C.c_int(world_size), buf), "comm_init")
 
-    def p2p_init(self, dist):
+    def p2p_init(self, dist) -> bool:
         """Switch the halo exchanges of this handle to direct NVLink stores (CUDA IPC); ``dist`` is the host process
-        group used to agree on the mailbox size and to all-gather the IPC handles."""
+        group used to agree on the mailbox size and to all-gather the IPC handles.  The switch is collective: if any
+        rank cannot export or map the buffers, every rank stays on NCCL send/recv.  Returns whether it is on."""
+        world = dist.get_world_size()
+
+        def all_ok(ok):
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok))
+            return all(flags)
+
         self.lib.mpasb_p2p_max_message.restype = C.c_long
         n = int(self.lib.mpasb_p2p_max_message(self._h))
-        if n < 0:
-            self._check(1, "p2p_max_message")
-        sizes = [None] * dist.get_world_size()
+        sizes = [None] * world
         dist.all_gather_object(sizes, n)
+        if min(sizes) < 0:
+            return False
         buf = C.create_string_buffer(128)
-        self._check(self.lib.mpasb_p2p_prepare(self._h, C.c_long(max(max(sizes), 2)), buf), "p2p_prepare")
-        handles = [None] * dist.get_world_size()
+        rc = self.lib.mpasb_p2p_prepare(self._h, C.c_long(max(max(sizes), 2)), buf)
+        if not all_ok(rc == 0):
+            return False
+        handles = [None] * world
         dist.all_gather_object(handles, buf.raw)
-        allh = C.create_string_buffer(b"".join(handles), 128 * len(handles))
-        self._check(self.lib.mpasb_p2p_open(self._h, allh), "p2p_open")
+        allh = C.create_string_buffer(b"".join(handles), 128 * world)
+        rc = self.lib.mpasb_p2p_open(self._h, allh)
+        if not all_ok(rc == 0):
+            return False
+        self._check(self.lib.mpasb_p2p_enable(self._h, C.c_int(1)), "p2p_enable")
         dist.barrier()
+        return True
 
     def nccl_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)

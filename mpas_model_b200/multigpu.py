@@ -126,8 +126,9 @@ def setup_rank(n_cells, n_levels, num_scalars, rank, world, device, precision="d
     uid = [g.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     g.comm_init(rank, world, uid[0])
+    g.p2p_on = False
     if os.environ.get("MPASB_P2P", "1") != "0" and 2 <= world <= 9:
-        g.p2p_init(dist)              # exchanges by direct NVLink stores (CUDA IPC) instead of NCCL send/recv
+        g.p2p_on = g.p2p_init(dist)   # exchanges by direct NVLink stores (CUDA IPC) instead of NCCL send/recv
     dt = cfg["config_dt"]
     g.exchange_halo_group("initialization:u")                       # mpas_atm_core.F:250
     g.atm_init_coupled_diagnostics()
