@@ -13,6 +13,7 @@ static const std::vector<GroupDef>& group_table() {
         {"dynamics:theta_m,scalars,pressure_p,rtheta_p", {{"theta_m", 1, 0, 3}, {"scalars", 1, 0, 3}, {"pressure_p", 1, 0, 3}, {"rtheta_p", 1, 0, 3}}},
         {"dynamics:rw_p,ru_p,rho_pp,rtheta_pp", {{"rw_p", 1, 0, 1}, {"ru_p", 1, 1, 2}, {"rho_pp", 1, 0, 3}, {"rtheta_pp", 1, 0, 2}}},
         {"dynamics:w,pv_edge,rho_edge", {{"w", 2, 0, 3}, {"pv_edge", 1, 1, 3}, {"rho_edge", 1, 1, 3}}},
+        {"dynamics:w,pv_edge,rho_edge,scalars", {{"w", 2, 0, 3}, {"pv_edge", 1, 1, 3}, {"rho_edge", 1, 1, 3}, {"scalars", 2, 0, 3}}},
         {"dynamics:theta_m,pressure_p,rtheta_p", {{"theta_m", 2, 0, 3}, {"pressure_p", 1, 0, 3}, {"rtheta_p", 1, 0, 3}}},
         {"dynamics:exner", {{"exner", 1, 0, 3}}},
         {"dynamics:tend_u", {{"tend_u", 1, 1, 1}}},

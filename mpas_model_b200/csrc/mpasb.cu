@@ -736,7 +736,12 @@ static int srk3(H* h, real dt) {
         rk_sub_timestep[1] = rk_sub_timestep[2] = rk_sub_timestep[3] = dt_dynamics / (real)number_of_sub_steps;
         number_sub_steps[1] = std::max(1, number_of_sub_steps / 2); number_sub_steps[2] = std::max(1, number_of_sub_steps / 2); number_sub_steps[3] = number_of_sub_steps;
     } else { h->err = "config_time_integration_order must be 2 or 3"; return 1; }
-    if (c.config_scalar_advection && !c.config_split_dynamics_transport) { h->err = "unsplit scalar transport is not implemented"; return 1; }
+    // config_split_dynamics_transport = false: the scalars are advanced inside the dynamics RK loop (TI:1404-1407)
+    const bool coupled_transport = c.config_scalar_advection && !c.config_split_dynamics_transport;
+    auto advance_scalars_stage = [&](int rk_step, real dt_rk) -> int {        // advance_scalars, TI:1730-1927
+        if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) { advance_scalars(h, dt_rk, rk_step); return 0; }
+        return advance_scalars_mono(h, dt_rk);
+    };
 
     if (exchange(h, "dynamics:theta_m,scalars,pressure_p,rtheta_p")) return 1;
     rk_integration_setup(h);
@@ -761,10 +766,12 @@ static int srk3(H* h, real dt) {
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
             if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, true)) return 1;   // starts u_3 (TI:1371)
             comm_wait(h);
+            if (coupled_transport && advance_scalars_stage(rk_step, rk_timestep[rk_step])) return 1;
             compute_solve_diagnostics(h, dt, 2, rk_step);
             // TI:1424.  Stages 1 and 2: the next kernels (vertical coefficients, first cell kernel of the tendencies) read none
             // of the three fields, so the exchange overlaps them; after stage 3 the substep roll copies w and must wait
-            if (rk_step < 3 ? exchange_async(h, "dynamics:w,pv_edge,rho_edge") : exchange(h, "dynamics:w,pv_edge,rho_edge")) return 1;
+            const char* grp = coupled_transport ? "dynamics:w,pv_edge,rho_edge,scalars" : "dynamics:w,pv_edge,rho_edge";      // TI:1463-1473
+            if (rk_step < 3 ? exchange_async(h, grp) : exchange(h, grp)) return 1;
         }
         if (dynamics_substep < dynamics_split)
             if (exchange(h, "dynamics:theta_m,pressure_p,rtheta_p")) return 1;
@@ -774,8 +781,7 @@ static int srk3(H* h, real dt) {
         rk_timestep[1] = dt / 3.; rk_timestep[2] = dt / 2.; rk_timestep[3] = dt;
         if (c.config_time_integration_order == 2) rk_timestep[1] = dt / 2.;
         for (int rk_step = 1; rk_step <= 3; rk_step++) {
-            if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) advance_scalars(h, rk_timestep[rk_step], rk_step);
-            else if (advance_scalars_mono(h, rk_timestep[rk_step])) return 1;
+            if (advance_scalars_stage(rk_step, rk_timestep[rk_step])) return 1;
             if (rk_step < 3) if (exchange(h, "dynamics:scalars")) return 1;
         }
     }

@@ -39,6 +39,8 @@ GROUPS = {
     "dynamics:rw_p,ru_p,rho_pp,rtheta_pp": (("rw_p", 1, "cells", (1,)), ("ru_p", 1, "edges", (2,)),
                                             ("rho_pp", 1, "cells", (1, 2)), ("rtheta_pp", 1, "cells", (2,))),
     "dynamics:w,pv_edge,rho_edge": (("w", 2, "cells", (1, 2)), ("pv_edge", 1, "edges", (1, 2)), ("rho_edge", 1, "edges", (1, 2))),
+    "dynamics:w,pv_edge,rho_edge,scalars": (("w", 2, "cells", (1, 2)), ("pv_edge", 1, "edges", (1, 2)), ("rho_edge", 1, "edges", (1, 2)),
+                                            ("scalars", 2, "cells", (1, 2))),
     "dynamics:theta_m,pressure_p,rtheta_p": (("theta_m", 2, "cells", (1, 2)), ("pressure_p", 1, "cells", (1, 2)),
                                              ("rtheta_p", 1, "cells", (1, 2))),
     "dynamics:exner": (("exner", 1, "cells", (1, 2)),),
@@ -207,6 +209,19 @@ def srk3_host_exchange(b, cfg, dt, xch):
         rk_t = [dt_dyn / 2.0, dt_dyn / 2.0, dt_dyn]
         rk_s = [dt_dyn / float(nss)] * 3
         n_sub = [max(1, nss // 2), max(1, nss // 2), nss]
+    coupled = cfg["config_scalar_advection"] and not cfg["config_split_dynamics_transport"]
+
+    def advance_scalars(rk, dt_rk):                                        # advance_scalars, TI:1730-1927
+        if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
+            b.k("advance_scalars", dt_rk, rk)
+        else:
+            b.k("advance_scalars_mono_pre", dt_rk)
+            xch("dynamics:scalars_old")                                    # TI:4155
+            for s in range(b.dims.num_scalars):
+                b.k("advance_scalars_mono_a", dt_rk, s)
+                xch("dynamics:scale")                                      # TI:4568
+                b.k("advance_scalars_mono_b", dt_rk, s)
+
     for n in ("tend_ru_physics", "tend_rtheta_physics", "tend_rho_physics"):
         b.set_array(n, np.zeros(b.shape(n)))
     xch("dynamics:theta_m,scalars,pressure_p,rtheta_p")                    # TI:1066
@@ -229,22 +244,18 @@ def srk3_host_exchange(b, cfg, dt, xch):
             xch("dynamics:rw_p,ru_p,rho_pp,rtheta_pp")                     # TI:1322
             b.k("recover_large_step_variables", rk_t[rk - 1], n_sub[rk - 1], rk)
             xch("dynamics:u_3")                                            # TI:1398
+            if coupled:
+                advance_scalars(rk, rk_t[rk - 1])                          # TI:1404-1407
             b.k("compute_solve_diagnostics", float(dt), rk)
-            xch("dynamics:w,pv_edge,rho_edge")                             # TI:1472
+            xch("dynamics:w,pv_edge,rho_edge,scalars" if coupled else "dynamics:w,pv_edge,rho_edge")     # TI:1463-1473
         if ds < split:
             xch("dynamics:theta_m,pressure_p,rtheta_p")                    # TI:1493
         b.k("rk_dynamics_substep_finish", ds, split)
+    if not cfg["config_scalar_advection"] or coupled:
+        return
     rk_t = [dt / 2.0 if order == 2 else dt / 3.0, dt / 2.0, float(dt)]
     for rk in (1, 2, 3):
-        if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
-            b.k("advance_scalars", rk_t[rk - 1], rk)
-        else:
-            b.k("advance_scalars_mono_pre", rk_t[rk - 1])
-            xch("dynamics:scalars_old")                                    # TI:4155
-            for s in range(b.dims.num_scalars):
-                b.k("advance_scalars_mono_a", rk_t[rk - 1], s)
-                xch("dynamics:scale")                                      # TI:4568
-                b.k("advance_scalars_mono_b", rk_t[rk - 1], s)
+        advance_scalars(rk, rk_t[rk - 1])
         if rk < 3:
             xch("dynamics:scalars")                                        # TI:1588-1590
 

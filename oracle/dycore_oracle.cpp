@@ -1558,6 +1558,7 @@ static const std::vector<Group>& halo_groups() {
         {"dynamics:rw_p,ru_p,rho_pp,rtheta_pp", {{"rw_p", 1, 0, 1}, {"ru_p", 1, 1, 2}, {"rho_pp", 1, 0, 3}, {"rtheta_pp", 1, 0, 2}}},
         {"dynamics:u_3", {{"u", 2, 1, 4}}},
         {"dynamics:w,pv_edge,rho_edge", {{"w", 2, 0, 3}, {"pv_edge", 1, 1, 3}, {"rho_edge", 1, 1, 3}}},
+        {"dynamics:w,pv_edge,rho_edge,scalars", {{"w", 2, 0, 3}, {"pv_edge", 1, 1, 3}, {"rho_edge", 1, 1, 3}, {"scalars", 2, 0, 3}}},
         {"dynamics:theta_m,pressure_p,rtheta_p", {{"theta_m", 2, 0, 3}, {"pressure_p", 1, 0, 3}, {"rtheta_p", 1, 0, 3}}},
         {"dynamics:scalars_old", {{"scalars", 1, 0, 3}}},
         {"dynamics:scale", {{"scale_arr", 1, 0, 3}}},
@@ -1600,6 +1601,22 @@ static void exchange_halo_group(Domain& dom, const char* name) {
 
 // ============================================================ TI:803-1725
 #define FOR_BLOCKS for (Block* bp : dom.blocks)
+// advance_scalars (TI:1730-1927): plain RK stage, or the monotonic routine with its two exchange points on stage 3
+static void advance_scalars(Domain& dom, int rk_step, real dt_rk) {
+    const mpasb_config& c = dom.blocks[0]->c;
+    if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) {
+        FOR_BLOCKS atm_advance_scalars(*bp, dt_rk, rk_step);
+    } else {
+        FOR_BLOCKS mono_pre_update(*bp, dt_rk);
+        exchange_halo_group(dom, "dynamics:scalars_old");
+        FOR_BLOCKS mono_rho_zz_int(*bp, dt_rk);
+        for (int iScalar = 1; iScalar <= dom.blocks[0]->d.num_scalars; iScalar++) {
+            FOR_BLOCKS mono_scalar_phase1(*bp, dt_rk, iScalar);
+            exchange_halo_group(dom, "dynamics:scale");
+            FOR_BLOCKS mono_scalar_phase2(*bp, dt_rk, iScalar);
+        }
+    }
+}
 static void atm_srk3(Domain& dom, real dt) {
     const mpasb_config& c = dom.blocks[0]->c;
     FOR_BLOCKS {   // TI:967-991, 1091-1093
@@ -1646,11 +1663,10 @@ static void atm_srk3(Domain& dom, real dt) {
             exchange_halo_group(dom, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp");
             FOR_BLOCKS atm_recover_large_step_variables(*bp, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step);
             exchange_halo_group(dom, "dynamics:u_3");
-            if (c.config_scalar_advection && !c.config_split_dynamics_transport) {
-                fprintf(stderr, "oracle: unsplit transport not restated\n"); abort();
-            }
+            const bool coupled_transport = c.config_scalar_advection && !c.config_split_dynamics_transport;
+            if (coupled_transport) advance_scalars(dom, rk_step, rk_timestep[rk_step]);                  // TI:1404-1407
             FOR_BLOCKS atm_compute_solve_diagnostics(*bp, dt, 2, rk_step);
-            exchange_halo_group(dom, "dynamics:w,pv_edge,rho_edge");
+            exchange_halo_group(dom, coupled_transport ? "dynamics:w,pv_edge,rho_edge,scalars" : "dynamics:w,pv_edge,rho_edge");   // TI:1463-1473
         }
         if (dynamics_substep < dynamics_split) exchange_halo_group(dom, "dynamics:theta_m,pressure_p,rtheta_p");
         FOR_BLOCKS atm_rk_dynamics_substep_finish(*bp, dynamics_substep, dynamics_split);
@@ -1659,18 +1675,7 @@ static void atm_srk3(Domain& dom, real dt) {
         rk_timestep[1] = dt / 3.; rk_timestep[2] = dt / 2.; rk_timestep[3] = dt;
         if (c.config_time_integration_order == 2) rk_timestep[1] = dt / 2.;
         for (int rk_step = 1; rk_step <= 3; rk_step++) {
-            if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) {
-                FOR_BLOCKS atm_advance_scalars(*bp, rk_timestep[rk_step], rk_step);
-            } else {
-                FOR_BLOCKS mono_pre_update(*bp, rk_timestep[rk_step]);
-                exchange_halo_group(dom, "dynamics:scalars_old");
-                FOR_BLOCKS mono_rho_zz_int(*bp, rk_timestep[rk_step]);
-                for (int iScalar = 1; iScalar <= dom.blocks[0]->d.num_scalars; iScalar++) {
-                    FOR_BLOCKS mono_scalar_phase1(*bp, rk_timestep[rk_step], iScalar);
-                    exchange_halo_group(dom, "dynamics:scale");
-                    FOR_BLOCKS mono_scalar_phase2(*bp, rk_timestep[rk_step], iScalar);
-                }
-            }
+            advance_scalars(dom, rk_step, rk_timestep[rk_step]);
             if (rk_step < 3) exchange_halo_group(dom, "dynamics:scalars");
         }
     }

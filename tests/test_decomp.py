@@ -115,8 +115,13 @@ def test_halo_known_answer(parts):
             assert np.array_equal(a[:n], want[:n]), (r, name)
 
 
-def test_four_blocks_equal_one_block_bit_for_bit(parts):
+COUPLED = dict(config_split_dynamics_transport=False, config_number_of_sub_steps=6)     # scalars inside the dynamics RK loop
+
+
+@pytest.mark.parametrize("overrides", [{}, COUPLED], ids=["split_transport", "coupled_transport"])
+def test_four_blocks_equal_one_block_bit_for_bit(parts, overrides):
     d, cfg, part, blocks, ex = parts
+    cfg = dict(cfg, **overrides)
     dt = cfg["config_dt"]
     one = orc.OracleDycore(d, cfg)
     one.atm_init_coupled_diagnostics(); one.atm_init_solve_diagnostics(dt)

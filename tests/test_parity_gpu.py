@@ -177,6 +177,10 @@ VARIANTS = {
     "rayleigh_u_and_cam_damping": dict(config_rayleigh_damp_u=True, config_number_rayleigh_damp_u_levels=4,
                                        config_mpas_cam_coef=2.0, config_number_cam_damping_levels=3),
     "no_apvm_not_monotonic": dict(config_apvm_upwinding=0.0, config_monotonic=False, config_epssm=0.2, config_smdiv=0.2),
+    # config_split_dynamics_transport = false: scalars advanced inside the dynamics RK loop (TI:1404-1407), 6 acoustic sub-steps
+    "coupled_transport": dict(config_split_dynamics_transport=False, config_number_of_sub_steps=6),
+    "coupled_transport_order3": dict(config_split_dynamics_transport=False, config_number_of_sub_steps=6,
+                                     config_time_integration_order=3, config_monotonic=False),
     "generic_kernels": dict(),          # MPASB_GENERIC_KERNELS=1: the one-thread-per-(level, column) family
 }
 

@@ -60,6 +60,14 @@ def srk3_stepwise(backends, cfg, dt, after=None):
         rk_t = [dt_dyn / 2.0, dt_dyn / 2.0, dt_dyn]
         rk_s = [dt_dyn / float(nss)] * 3
         n_sub = [max(1, nss // 2), max(1, nss // 2), nss]
+    coupled = cfg["config_scalar_advection"] and not cfg["config_split_dynamics_transport"]
+
+    def advance_scalars(rk, dt_rk):
+        if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
+            call("advance_scalars", dt_rk, rk)
+        else:
+            call("advance_scalars_mono", dt_rk)
+
     for b in backends:                      # TI:1091-1093 (no physics)
         for n in ("tend_ru_physics", "tend_rtheta_physics", "tend_rho_physics"):
             b.set_array(n, np.zeros(b.shape(n)))
@@ -76,14 +84,14 @@ def srk3_stepwise(backends, cfg, dt, after=None):
                 call("advance_acoustic_step", rk_s[rk - 1], ss)
                 call("divergence_damping_3d", rk_s[rk - 1])
             call("recover_large_step_variables", rk_t[rk - 1], n_sub[rk - 1], rk)
+            if coupled:                                  # config_split_dynamics_transport = false, TI:1404-1407
+                advance_scalars(rk, rk_t[rk - 1])
             call("compute_solve_diagnostics", float(dt), rk)
         call("rk_dynamics_substep_finish", ds, split)
-    rk_t = [dt / 2.0 if cfg["config_time_integration_order"] == 2 else dt / 3.0, dt / 2.0, float(dt)]
-    for rk in (1, 2, 3):
-        if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
-            call("advance_scalars", rk_t[rk - 1], rk)
-        else:
-            call("advance_scalars_mono", rk_t[rk - 1])
+    if cfg["config_scalar_advection"] and not coupled:
+        rk_t = [dt / 2.0 if cfg["config_time_integration_order"] == 2 else dt / 3.0, dt / 2.0, float(dt)]
+        for rk in (1, 2, 3):
+            advance_scalars(rk, rk_t[rk - 1])
     for b in backends:                      # TI:1596-1611
         b.mpas_reconstruct(2, False)
     if after:
