@@ -150,7 +150,10 @@ def reference_arm(args, rank, world):
     whole-mesh rate on the same cores is the block rate / N."""
     if rank != 0:
         return
+    from oracle import oracle as orc
     from oracle.oracle import OracleDycore
+    n_threads = int(os.environ.get("MPASB_REF_THREADS", os.cpu_count()))
+    orc.set_threads(n_threads)                    # torchrun forces OMP_NUM_THREADS=1 into its ranks; the baseline uses every core
     n_cells, n_lev = workload_for(args)
     if args.gpus > 1:
         from mpas_model_b200 import multigpu as mg
@@ -177,7 +180,7 @@ def reference_arm(args, rank, world):
     el = time.time() - t0
     sps = frac * steps / el                       # whole-mesh steps/s
     v = n_cells * sps                             # cell-column updates/s (the line's unit)
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+    cores = n_threads
     line = line_common(args, n_cells, n_lev, dt, args.gpus)
     line["config"]["implementation"] = "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build"
     line.update({
@@ -342,7 +345,10 @@ def main():
     # ---------------- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as orc
         from oracle.oracle import OracleDycore
+        n_threads = int(os.environ.get("MPASB_REF_THREADS", os.cpu_count()))
+        orc.set_threads(n_threads)
         o = OracleDycore(d, cfg)
         o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
         o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
@@ -350,7 +356,7 @@ def main():
         while n < 3 or (time.time() - t0 < 10.0 and n < 20):
             o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); n += 1
         el = time.time() - t0
-        cpu = {"value": n_cells * n / el, "unit": "cell-columns/s", "steps_per_s": n / el, "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count())),
+        cpu = {"value": n_cells * n / el, "unit": "cell-columns/s", "steps_per_s": n / el, "cores": n_threads,
                "kind": "port", "sample": f"{n} full atm_srk3 steps of the same workload (C++/OpenMP restatement, not the Fortran build)"}
 
     if rank != 0:

@@ -38,6 +38,16 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads of the oracle from here on (omp_set_num_threads of the libgomp it is linked against).  torchrun
+    exports OMP_NUM_THREADS=1 into every rank, which would turn the multi-core CPU baseline into a single-core one."""
+    lib()
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(max(1, int(n))))
+    except OSError:
+        pass
+
+
 class OracleDycore(Backend):
     def __init__(self, block: dict, cfg: dict, rank: int = 0):
         self.lib = lib()
