@@ -861,15 +861,17 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev 
 // lanes hit distinct banks -- the serial recurrence costs one warp-instruction per level for 32 columns instead of
 // one per column.  Phase 3: each warp finishes its columns (Rayleigh damping, wwAvg, rho_pp, rtheta_pp).
 // Operation order inside every column is the reference's: bit-identical results.
+// Tiling measured on B200 (x1.40962 x 55): 32 columns / 8 warps / 2 blocks per SM (128 registers) 154 us; 16 columns / 4 warps with
+// 4 blocks (128 registers) 150 us, 3 blocks (167 registers: more loads in flight per warp) 144 us, 2 blocks (207 registers) 176 us.
 #ifndef AC3_COLS
-#define AC3_COLS 32                     // columns per block = lanes of the sweeping warp
+#define AC3_COLS 16                     // columns per block = lanes of the sweeping warp
 #endif
 #ifndef AC3_MINB
-#define AC3_MINB 2
+#define AC3_MINB 3
 #endif
 #define AC3_ARRAYS 6                    // rw (rhs / solution), a_tri, alpha_tri, gamma_tri, ts, rs
 #ifndef AC3_WARPS
-#define AC3_WARPS 8                     // warps per block: AC3_COLS / AC3_WARPS columns per warp (8 measured faster than 16)
+#define AC3_WARPS 4                     // warps per block: AC3_COLS / AC3_WARPS columns per warp
 #endif
 __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
     extern __shared__ __align__(16) real sm3[];
@@ -1200,7 +1202,10 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
 // Phase 3: the warps write alpha_tri and gamma_tri.  Operation order inside a column is the reference's.
 #define VIC_COLS 32
 #define VIC_WARPS 8
-__global__ void __launch_bounds__(VIC_WARPS * 32) k3_vert_imp_coefs(const Dev D, real dtseps, real c2, real rcv) {
+#ifndef MB_VIC
+#define MB_VIC 3
+#endif
+__global__ void __launch_bounds__(VIC_WARPS * 32, MB_VIC) k3_vert_imp_coefs(const Dev D, real dtseps, real c2, real rcv) {
     extern __shared__ __align__(16) real smv[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
