@@ -1200,8 +1200,12 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
 // Phase 2: ONE warp runs the LU recurrence alpha = 1/(b - a*gamma), gamma = c*alpha (TI:2352-2355) of all VIC_COLS
 // columns at once, lane = column, rows of odd stride in shared memory (alpha/gamma overwrite b/c).
 // Phase 3: the warps write alpha_tri and gamma_tri.  Operation order inside a column is the reference's.
+#ifndef VIC_COLS
 #define VIC_COLS 32
+#endif
+#ifndef VIC_WARPS
 #define VIC_WARPS 8
+#endif
 #ifndef MB_VIC
 #define MB_VIC 3
 #endif
