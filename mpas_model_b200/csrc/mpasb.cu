@@ -55,6 +55,7 @@ struct mpasb_handle_s {
     bool physics_tend_dirty = true; // tend_*_physics must be zeroed before the next step (TI:1091-1093, no physics)
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool profile = false;
+    bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
     // stencil-union tiles of the TMA-staged advective flux kernel (k4_dt_edge_flux): host copies of the lists they
     // are derived from, and the derived device tables
@@ -367,8 +368,7 @@ static void compute_vert_imp_coefs(H* h, real dts) {   // TI:2225-2366
     const real c2 = cp * rcv;
     if (h->colwarp) {
         const size_t smem3 = (size_t)3 * VIC_COLS * (h->D.LDK | 1) * sizeof(real);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k3_vert_imp_coefs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
+        if (!h->smem_attr_vic) { cudaFuncSetAttribute(k3_vert_imp_coefs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); h->smem_attr_vic = true; }
         KScope ks_(h, "k:k3_vert_imp_coefs");
         k3_vert_imp_coefs<<<(unsigned)((h->D.nCellsSolve + VIC_COLS - 1) / VIC_COLS), VIC_WARPS * 32, smem3, h->stream>>>(h->D, dtseps, c2, rcv);
         h->launches++;
@@ -523,8 +523,7 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
         if (small_step == 1) h->ru_p_pending = true;
         else LAUNCHW(k2_acoustic_edge, h->D.nEdges, h->D, dts, c2);
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        if (!h->smem_attr_ac) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); h->smem_attr_ac = true; }
         KScope ks_(h, "k:k3_acoustic_cell");
         k3_acoustic_cell<<<(unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS), AC3_WARPS * 32, smem3, h->stream>>>(h->D, dts, small_step, epssm, resm);
         h->launches++;
