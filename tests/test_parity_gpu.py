@@ -206,6 +206,25 @@ def test_namelist_variants(tiny_case, variant, monkeypatch):
     g.close(); o.close()
 
 
+def test_tall_columns_use_the_generic_family():
+    """nVertLevels + 1 > 64: a column no longer fits one warp's level pairs, so every routine runs its generic
+    one-thread-per-(level, column) kernel (and the segment copies, reconstruction and summary run with LDK = 68)."""
+    from mpas_model_b200.case import make_case
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d, cfg = make_case(642, 66, num_scalars=2)
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    for _ in range(2):
+        o.atm_srk3(dt); g.atm_srk3(dt)
+        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+    worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE + ("uReconstructZonal",)}
+    assert max(worst.values()) <= 10 * TOL_STEP, worst
+    assert np.allclose(g.summarize_timestep(), o.summarize_timestep(), rtol=1e-10, atol=0)
+    g.close(); o.close()
+
+
 def test_ten_steps_and_invariants(pair):
     d, cfg, o, g = pair
     o.load_block(d); g.load_block(d)
