@@ -135,15 +135,36 @@ def _pad_rows(a, fill):
     return np.concatenate([a, pad])
 
 
-def generate(n_cells: int = 2562, lloyd_iters: int = 12, reorder: str = "morton") -> dict:
+def _delaunay_on_sphere(p):
+    """Spherical Delaunay triangulation = facets of the convex hull, oriented counter-clockwise seen from outside."""
+    from scipy.spatial import ConvexHull
+    tri = ConvexHull(p).simplices.astype(np.int64)
+    a, b, c = p[tri[:, 0]], p[tri[:, 1]], p[tri[:, 2]]
+    flip = np.einsum("ij,ij->i", np.cross(b - a, c - a), a + b + c) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    return tri
+
+
+def generate(n_cells: int = 2562, lloyd_iters: int = 12, reorder: str = "morton", jitter: float = 0.0, seed: int = 0) -> dict:
     """Build the ``x1.<n_cells>`` mesh.  Returns a dict of numpy arrays named as
-    in the MPAS grid file, 0-based connectivity, garbage slot included."""
+    in the MPAS grid file, 0-based connectivity, garbage slot included.
+
+    ``jitter`` > 0 (a fraction of the nominal cell spacing) displaces the generators at random and re-triangulates:
+    an irregular Voronoi mesh with 5-, 6-, 7- (and occasionally 8-) sided cells like the reference's variable-resolution
+    meshes, used by the tests to exercise the paths that a pentagon/hexagon-only mesh never takes (``maxEdges`` > 6)."""
     if n_cells not in LEVEL_OF:
         raise ValueError(f"n_cells must be 10*4^n+2, got {n_cells}")
     p, tri = _icosahedron()
     for _ in range(LEVEL_OF[n_cells]):
         p, tri = _subdivide(p, tri)
     p = _lloyd(p, tri, lloyd_iters)
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        spacing = np.sqrt(2.0 * (4.0 * np.pi / p.shape[0]) / np.sqrt(3.0))
+        p = _normalize(p + jitter * spacing * rng.uniform(-1.0, 1.0, p.shape))
+        tri = _delaunay_on_sphere(p)
+    MAX_EDGES = max(6, int(np.bincount(tri.reshape(-1)).max()))      # shadows the module constant: widest cell of this mesh
+    MAX_EDGES2 = 2 * MAX_EDGES
 
     nC = p.shape[0]
     if reorder == "morton":

@@ -141,3 +141,27 @@ def test_four_blocks_equal_one_block_bit_for_bit(parts, overrides):
                                 ("theta_m", "cells", "cell_bounds"), ("scalars", "cells", "cell_bounds")):
             n = L[key][0]
             assert np.array_equal(o.get_array(name)[:n], one.get_array(name)[L[kind][:n]]), (r, name)
+
+
+def test_irregular_mesh_blocks_equal_one_block():
+    """Variable cell degree (maxEdges = 7) through the decomposition: three blocks = one block, bit for bit."""
+    from mpas_model_b200.case import make_case
+    d, cfg = make_case(2562, 10, num_scalars=1, jitter=0.2)
+    assert d["maxEdges"] == 7
+    part = decomp.partition_rcb(d, 3)
+    blocks, ex = decomp.decompose_case(d, cfg, part)
+    dt = cfg["config_dt"]
+    one = orc.OracleDycore(d, cfg)
+    one.atm_init_coupled_diagnostics(); one.atm_init_solve_diagnostics(dt)
+    os_ = _mk_oracles(blocks, ex, cfg)
+    orc.exchange(os_, "initialization:u")
+    for o in os_:
+        o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+    orc.exchange(os_, "initialization:pv_edge,ru,rw")
+    one.atm_srk3(dt); orc.step(os_, dt)
+    for o, r in zip(os_, sorted(blocks)):
+        L = blocks[r]["lists"]
+        for name, kind, key in (("u", "edges", "edge_bounds"), ("w", "cells", "cell_bounds"), ("theta_m", "cells", "cell_bounds"),
+                                ("scalars", "cells", "cell_bounds")):
+            n = L[key][0]
+            assert np.array_equal(o.get_array(name, 2)[:n], one.get_array(name, 2)[L[kind][:n]]), (r, name)
