@@ -36,12 +36,40 @@ def _init(o, g, dt):
 def test_set_get_roundtrip(pair):
     d, cfg, o, g = pair
     rng = np.random.default_rng(0)
-    for name in ("u", "w", "scalars", "zb_cell", "scale_arr", "weightsOnEdge", "horiz_flux_arr", "fzm"):
+    for name in ("u", "w", "scalars", "zb_cell", "scale_arr", "weightsOnEdge", "horiz_flux_arr", "fzm", "coeffs_reconstruct", "latCell"):
         a = rng.standard_normal(g.shape(name))
         g.set_array(name, a)
         assert np.array_equal(g.get_array(name), a), name
         g.set_array(name, np.zeros(g.shape(name)))
     g.load_block(d)
+
+
+def test_error_convention(pair, tiny_case):
+    """every entry point returns 0 or a nonzero code with a message; nothing aborts.  The regional
+    path is refused at creation (config_apply_lbcs), unknown keys / wrong sizes / wrong time levels at the call."""
+    import ctypes as C
+    from mpas_model_b200.dycore import Dycore, make_config, make_dims
+    d, cfg, o, g = pair
+    lib, h = g.lib, g._h
+    buf = np.zeros(g.shape("u"))
+    ptr = buf.ctypes.data_as(C.c_void_p)
+    assert lib.mpasb_set_field(h, b"no_such_field", C.c_int(1), ptr, C.c_long(buf.size)) != 0
+    assert b"no_such_field" in lib.mpasb_last_error(h)
+    assert lib.mpasb_set_field(h, b"u", C.c_int(1), ptr, C.c_long(buf.size - 1)) != 0          # wrong element count
+    assert lib.mpasb_set_field(h, b"u", C.c_int(3), ptr, C.c_long(buf.size)) != 0              # no such time level
+    assert lib.mpasb_get_field(h, b"ru", C.c_int(2), ptr, C.c_long(buf.size)) != 0             # ru has one level
+    assert lib.mpasb_exchange_halo_group(h, b"dynamics:tend_u") == 0                           # single block: no-op
+    with pytest.raises(RuntimeError):
+        g.summarize_timestep_fetch()
+    dt, cfg_t = tiny_case
+    with pytest.raises(RuntimeError):
+        Dycore(dt, dict(cfg_t, config_apply_lbcs=True))
+    bad = Dycore(dt, dict(cfg_t, config_time_integration_order=4))
+    with pytest.raises(RuntimeError, match="config_time_integration_order"):
+        bad.atm_srk3(cfg_t["config_dt"])
+    bad.close()
+    g.load_block(d)          # the handle is still usable after every refused call
+    g.atm_init_coupled_diagnostics()
 
 
 def test_init_routines(pair):
@@ -233,6 +261,36 @@ def test_namelist_variants(tiny_case, variant, monkeypatch):
     worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
     assert max(worst.values()) <= 10 * TOL_STEP, (variant, worst)
     g.close(); o.close()
+
+
+def test_mesh_scaling_and_diabatic_tendency(tiny_case):
+    """Inputs that are trivial in the quasi-uniform JW case (meshScalingDel2/4 = 1, rt_diabatic_tend = 0) made
+    non-trivial, so that the kernels' use of them is actually compared: smooth variable mesh scaling as on a
+    variable-resolution mesh (mpas_atm_core.F:1091-1148) and a microphysics heating rate (TI:6134-6197)."""
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d0, cfg = tiny_case
+    d = dict(d0)
+    nC, nE = d["nCells"], d["nEdges"]
+    d["meshScalingDel2"] = np.concatenate([1.0 + 0.4 * np.sin(3.0 * d["latEdge"][:nE]), [1.0]])
+    d["meshScalingDel4"] = np.concatenate([1.0 + 0.4 * np.cos(2.0 * d["lonEdge"][:nE]), [1.0]])
+    heat = 1.0e-4 * np.cos(d["latCell"][:nC])[:, None] * np.sin(np.pi * (np.arange(d["nVertLevels"]) + 0.5) / d["nVertLevels"])[None, :]
+    d["rt_diabatic_tend"] = np.concatenate([heat, np.zeros((1, d["nVertLevels"]))])
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    ref = OracleDycore(d0, cfg)
+    _init(ref, ref, dt)
+    for _ in range(2):
+        o.atm_srk3(dt); g.atm_srk3(dt); ref.atm_srk3(dt)
+        for b in (o, g, ref):
+            b.mpas_pool_shift_time_levels()
+    worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
+    assert max(worst.values()) <= 10 * TOL_STEP, worst
+    # and the modified inputs do change the answer (the comparison above is not vacuous)
+    assert rel_l2(o.get_array("theta_m", 1), ref.get_array("theta_m", 1)) > 1e-7
+    assert rel_l2(o.get_array("u", 1), ref.get_array("u", 1)) > 1e-9
+    g.close(); o.close(); ref.close()
 
 
 def test_tall_columns_use_the_generic_family():
