@@ -165,3 +165,46 @@ def test_irregular_mesh_blocks_equal_one_block():
                                 ("scalars", "cells", "cell_bounds")):
             n = L[key][0]
             assert np.array_equal(o.get_array(name, 2)[:n], one.get_array(name, 2)[L[kind][:n]]), (r, name)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_arbitrary_partition_vectors(tiny_case, seed):
+    """The decomposition takes any cell -> block vector (the reference reads METIS files, mpas_block_decomp.F:101-137), not only
+    the coordinate bisection used for the benchmarks: blocks made of scattered patches, with every other block as neighbour,
+    still give the single-block result bit for bit, and the halo known-answer pattern holds."""
+    d, cfg = tiny_case
+    rng = np.random.default_rng(seed)
+    nC = d["nCells"]
+    # patches: a few random seed cells per block, every cell joins the block of its nearest seed
+    seeds = rng.choice(nC, size=9, replace=False)
+    xyz = np.stack([d["xCell"][:nC], d["yCell"][:nC], d["zCell"][:nC]], 1)
+    part = (np.argmax(xyz @ xyz[seeds].T, axis=1) % 3).astype(np.int64)
+    assert len(np.unique(part)) == 3
+    blocks, ex = decomp.decompose_case(d, cfg, part)
+    os_ = _mk_oracles(blocks, ex, cfg)
+    nl = d["nVertLevels"]
+    for o, r in zip(os_, sorted(blocks)):
+        b = blocks[r]
+        a = np.repeat(b["indexToCellID"].astype(np.float64)[:, None], nl, axis=1)
+        a[b["nCellsSolve"]:] = -1.0
+        o.set_array("theta_m", a, 1)
+    orc.exchange(os_, "dynamics:theta_m,scalars,pressure_p,rtheta_p")
+    for o, r in zip(os_, sorted(blocks)):
+        b = blocks[r]
+        want = np.repeat(b["indexToCellID"].astype(np.float64)[:, None], nl, axis=1)
+        assert np.array_equal(o.get_array("theta_m")[: b["nCells"]], want[: b["nCells"]]), r
+        o.load_block(b)
+    dt = cfg["config_dt"]
+    one = orc.OracleDycore(d, cfg)
+    one.atm_init_coupled_diagnostics(); one.atm_init_solve_diagnostics(dt)
+    orc.exchange(os_, "initialization:u")
+    for o in os_:
+        o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+    orc.exchange(os_, "initialization:pv_edge,ru,rw")
+    one.atm_srk3(dt); orc.step(os_, dt)
+    for o, r in zip(os_, sorted(blocks)):
+        L = blocks[r]["lists"]
+        for name, kind, key in (("u", "edges", "edge_bounds"), ("w", "cells", "cell_bounds"), ("rho_zz", "cells", "cell_bounds"),
+                                ("theta_m", "cells", "cell_bounds"), ("scalars", "cells", "cell_bounds")):
+            n = L[key][0]
+            assert np.array_equal(o.get_array(name, 2)[:n], one.get_array(name, 2)[L[kind][:n]]), (r, name)
