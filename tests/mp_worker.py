@@ -5,6 +5,7 @@ mode "oracle": every rank owns one block in a CPU oracle instance; halo exchange
 mode "gpu":    every rank owns one block on its own GPU; exchanges go through the library
                (pack kernel -> NCCL send/recv -> unpack kernel).
 Rank 0 gathers the owned elements of every rank and writes them to <out>.npz."""
+import json
 import os
 import sys
 
@@ -31,6 +32,7 @@ def main():
         dist.broadcast_object_list(box, src=0)
         rec = mg.load_block(box[0], rank)
         block, cfg, ex = rec["block"], rec["cfg"], rec["ex"]
+        cfg = dict(cfg, **json.loads(os.environ.get("MPASB_TEST_CFG", "{}")))      # namelist overrides of the test
         g = OracleDycore(block, cfg, rank=rank)
         hx = mg.HostExchanger(dist, rank, ex)
         xch = lambda group: hx.exchange(g, group)

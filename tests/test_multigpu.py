@@ -22,8 +22,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _launch(mode, world, n_cells, n_lev, n_scal, n_steps, out, tmp_path):
-    env = dict(os.environ, MPASB_CACHE=str(tmp_path), OMP_NUM_THREADS="2")
+def _launch(mode, world, n_cells, n_lev, n_scal, n_steps, out, tmp_path, overrides=None):
+    import json
+    env = dict(os.environ, MPASB_CACHE=str(tmp_path), OMP_NUM_THREADS="2", MPASB_TEST_CFG=json.dumps(overrides or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "mp_worker.py"), mode, str(n_cells), str(n_lev), str(n_scal), str(n_steps), out]
@@ -31,10 +32,11 @@ def _launch(mode, world, n_cells, n_lev, n_scal, n_steps, out, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
 
-def _single_block_oracle(n_cells, n_lev, n_scal, n_steps):
+def _single_block_oracle(n_cells, n_lev, n_scal, n_steps, overrides=None):
     from mpas_model_b200.case import make_case
     from oracle.oracle import OracleDycore
     d, cfg = make_case(n_cells, n_lev, num_scalars=n_scal)
+    cfg = dict(cfg, **(overrides or {}))
     o = OracleDycore(d, cfg)
     dt = cfg["config_dt"]
     o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
@@ -43,10 +45,12 @@ def _single_block_oracle(n_cells, n_lev, n_scal, n_steps):
     return d, {n: o.get_array(n) for n in STATE}
 
 
-def test_two_ranks_gloo_equal_one_block_bit_for_bit(tmp_path):
+@pytest.mark.parametrize("overrides", [None, dict(config_split_dynamics_transport=False, config_number_of_sub_steps=6)],
+                         ids=["split_transport", "coupled_transport"])
+def test_two_ranks_gloo_equal_one_block_bit_for_bit(tmp_path, overrides):
     out = str(tmp_path / "gloo2.npz")
-    _launch("oracle", 2, 642, 10, 2, 2, out, tmp_path)
-    d, ref = _single_block_oracle(642, 10, 2, 2)
+    _launch("oracle", 2, 642, 10, 2, 2, out, tmp_path, overrides)
+    d, ref = _single_block_oracle(642, 10, 2, 2, overrides)
     got = np.load(out)
     for n in STATE:
         cnt = got[n].shape[0]
