@@ -153,14 +153,6 @@ __global__ void k_zb_flags(const Dev D) {
     for (size_t j = 0; j < n; j++) any |= (a[j] != 0.0) | (b[j] != 0.0);
     D.zb_any[i] = any;
 }
-__global__ void k_add_into(real* __restrict__ y, const real* __restrict__ x, size_t n) {       // y = x + y
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) y[t] = x[t] + y[t];
-}
-__global__ void k_scale_from(real* __restrict__ y, const real* __restrict__ x, real s, size_t n) {   // y = x * s
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) y[t] = x[t] * s;
-}
 // One launch for a whole list of element-wise column copies/accumulations (atm_rk_integration_setup, TI:1930-2039, and
 // atm_rk_dynamics_substep_finish, TI:7013-7191): blockIdx.y selects the segment, blockIdx.x strides over its
 // 16-byte element pairs.  op 0: d = s;  1: d = s + d;  2: d = s, then s = d * scale;  3: d = s + d, then s = d * scale.
@@ -192,10 +184,6 @@ __global__ void __launch_bounds__(256) k_segments(const SegList L) {
             v2 q; q.x = r.x * L.scale; q.y = r.y * L.scale; s[t] = q;
         }
     }
-}
-__global__ void k_fill(real* __restrict__ y, real v, size_t n) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) y[t] = v;
 }
 
 // ------------------------------------------------------------------ summarize_timestep  TI:8286-8319
