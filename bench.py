@@ -88,7 +88,6 @@ KERNEL_MODEL_C = {
     # acoustic cell solve: 1 E (ru_p or tend_u) + 21 C read, 5 C written on a later small step (29 C); the first
     # small step of a stage does not read rho_pp, rtheta_pp, rw_p, wwAvg (25 C); 9 first + 3 later per step
     "k:k3_acoustic_cell": (9 * 25.0 + 3 * 29.0) / 12,
-    "k:k2_acoustic_cell": (9 * 25.0 + 3 * 29.0) / 12,
     "k:k_acoustic_cell": 29.0,
     # edge tendency: rk 1 reads 5 E + 8 C + 1 V and writes 3 E (34 C); rk 2,3 read 5 E + 3 C, write 1 E (21 C)
     "k:k2_dt_edge_b": (3 * 34.0 + 6 * 21.0) / 9,

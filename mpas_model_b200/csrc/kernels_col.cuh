@@ -26,9 +26,6 @@
 #define CW_FULL 0xffffffffu
 #define CW_WARPS 8                      // warps (= columns) per block
 #define CW_THREADS (CW_WARPS * 32)
-#ifndef CW_MINB
-#define CW_MINB 2                       // resident blocks per SM the register allocation aims for
-#endif
 
 // resident blocks per SM each kernel's register allocation aims for (1 = no constraint); tuned on B200, DESIGN.md §4
 #ifndef MB_EDGE_B
@@ -471,118 +468,8 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
     ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
 }
 
-// ------------------------------------------------------------------ atm_advance_acoustic_step_work, cell part  TI:2824-2973
-// One warp per cell.  Right-hand sides are assembled by all lanes; lane 0 then runs the two
-// tridiagonal sweeps (TI:2922-2930) out of the warp's shared-memory slab in the reference's order,
-// while the operands of the post-solve damping step are already in flight.
-#define AC_STRIDE 66
-__global__ void __launch_bounds__(CW_THREADS, CW_MINB) k2_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
-    __shared__ __align__(16) real s_rw[CW_WARPS][AC_STRIDE], s_a[CW_WARPS][AC_STRIDE], s_al[CW_WARPS][AC_STRIDE], s_ga[CW_WARPS][AC_STRIDE];
-    CW_SETUP(D.nCells)
-    const bool first = small_step == 1;
-    const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
-    // old values of the perturbation variables (zero on the first small step, TI:2850-2860)
-    r2 rtheta_pp = mk2(0.0, 0.0);
-    if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
-    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); return; }
-    const int ne = D.nEdgesOnCell[i];
-    const real invArea = D.invAreaCell[i];
-    const int le = min(lane, ne - 1);
-    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
-    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
-    const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
-    r2 rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
-    if (!first) {
-        rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
-        wwAvg = sel(k_le_nl, LD(D.wwAvg, i), 0.0);
-        rho_pp = sel(k_lt_nl, LD(D.rho_pp, i), 0.0);
-    }
-    const r2 tend_rho = LD(D.tend_rho, i), tend_theta = LD(D.tend_theta, i), tend_w = LD(D.tend_w, i);
-    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
-    const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
-    const r2 zz = LD(D.zz, i);
-    const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
-    r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
-#define AC_EDGE(E)                                                                                          \
-    {                                                                                                       \
-        const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                    \
-        const r2 flux = BC(my_f, (E)) * LD(D.ru_p, iEdge) * invArea;                                        \
-        const r2 th = LD(D.theta_m, cell2) + LD(D.theta_m, cell1);                                          \
-        rs = selb((E) < ne, rs - flux, rs);                                                                 \
-        ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                      \
-    }
-#pragma unroll
-    for (int e = 0; e < CW_NE; e++) AC_EDGE(e)
-    for (int e = CW_NE; e < ne; e++) AC_EDGE(e)
-#undef AC_EDGE
-    // operands of the implicit Rayleigh damping step (TI:2936-2942): requested before the solve
-    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
-    const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
-    const r2 rw_p1 = dn1(rw_p);
-    const r2 coftz1 = dn1(coftz);
-    rs = rho_pp + dts * tend_rho + rs
-         - cofrz * resm * (rw_p1 - rw_p);
-    ts = rtheta_pp + dts * tend_theta + ts
-         - resm * rdzw * (coftz1 * rw_p1
-                          - coftz * rw_p);
-    rs = sel(k_lt_nl, rs, 0.0); ts = sel(k_lt_nl, ts, 0.0);
-    wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 - epssm) * rw_p, wwAvg);
-    const r2 zzm = up1(zz);
-    {
-        const r2 tsm = up1(ts), rsm = up1(rs), rtm = up1(rtheta_pp), rhm = up1(rho_pp), cofwtm = up1(cofwt);
-        const r2 r = rw_p + dts * tend_w
-                     - cofwz * ((zz * ts
-                                 - zzm * tsm)
-                                + resm * (zz * rtheta_pp
-                                          - zzm * rtm))
-                     - cofwr * ((rs + rsm)
-                                + resm * (rho_pp + rhm))
-                     + cofwt * (ts + resm * rtheta_pp)
-                     + cofwtm * (tsm + resm * rtm);
-        const r2 rhs = sel(k_mid, r, rw_p);
-        if (act) {
-            *reinterpret_cast<r2*>(&s_rw[wib][k0]) = rhs; *reinterpret_cast<r2*>(&s_a[wib][k0]) = a_tri;
-            *reinterpret_cast<r2*>(&s_al[wib][k0]) = al_tri; *reinterpret_cast<r2*>(&s_ga[wib][k0]) = ga_tri;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) {
-        real* rwv = s_rw[wib];
-        const real* av = s_a[wib]; const real* alv = s_al[wib]; const real* gav = s_ga[wib];
-        real prev = rwv[0];
-#pragma unroll 4
-        for (int kk = 1; kk < nl; kk++) {
-            prev = (rwv[kk] - av[kk] * prev) * alv[kk];
-            rwv[kk] = prev;
-        }
-        real next = rwv[nl];
-#pragma unroll 4
-        for (int kk = nl - 1; kk >= 0; kk--) {
-            next = rwv[kk] - gav[kk] * next;
-            rwv[kk] = next;
-        }
-    }
-    __syncwarp();
-    r2 r = *reinterpret_cast<const r2*>(&s_rw[wib][kc]);
-    {   // implicit Rayleigh damping on w, TI:2936-2942
-        const r2 dw = rw_save - rw_now;
-        const r2 rd = (r + dw - dts * dss *
-                       (fm * zz + fp * zzm)
-                       * (fm * rho + fp * up1(rho))
-                       * w_now) / (1.0 + dts * dss)
-                      - dw;
-        r = sel(k_mid, rd, r);
-        wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 + epssm) * r, wwAvg);
-    }
-    r = sel(k_le_nl, r, 0.0);
-    const r2 r1 = dn1(r);
-    ST(D.rtheta_pp_old, i, rtheta_pp);
-    ST(D.rw_p, i, r);
-    ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
-    ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
-    ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1
-                                                  - coftz * r), 0.0));
-}
+// (an earlier one-warp-per-cell version of the acoustic cell step, with lane 0 sweeping the column out of shared memory --
+//  741 dynamic instructions per column in the sweep against 34 in the block-tiled k3_acoustic_cell below -- was removed)
 
 // ------------------------------------------------------------------ atm_set_smlstep_pert_variables_work  TI:2427-2508
 // zb_cell/zb3_cell are [cell][edge slot][LDK]; requires maxEdges >= CW_NE (slots beyond nEdgesOnCell exist and are skipped)
