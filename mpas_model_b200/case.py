@@ -8,16 +8,18 @@ from . import init_block, jw_init, mesh
 
 
 def make_case(n_cells: int, n_levels: int, dt: float | None = None, init_case: int = 2,
-              num_scalars: int = 1, lloyd_iters: int = 12, jitter: float = 0.0, **cfg_overrides):
+              num_scalars: int = 1, lloyd_iters: int = 12, jitter: float = 0.0, derive: bool = True, **cfg_overrides):
     """Returns (block, cfg).  ``dt`` defaults to the reference's rule of thumb
-    of 6 s per km of nominal grid distance."""
+    of 6 s per km of nominal grid distance.  ``derive=False`` leaves out the init-time derived
+    fields (``init_block``): a case that is only going to be decomposed gets them per block."""
     m = mesh.generate(n_cells, lloyd_iters=lloyd_iters, jitter=jitter)
     d = jw_init.init_atm_case_jw(m, n_levels, init_case=init_case, num_scalars=num_scalars)
     if dt is None:
         dt = 6.0 * round(d["nominalMinDc"] / 1000.0)
     cfg = init_block.default_config(d["nominalMinDc"], dt)
     cfg.update(cfg_overrides)
-    init_block.init_block(d, cfg)
+    if derive:
+        init_block.init_block(d, cfg)
     if num_scalars > 1:
         add_passive_tracers(d)
     return d, cfg

@@ -73,12 +73,12 @@ def prepare_blocks(n_cells, n_levels, num_scalars, world, tag=""):
     prefix = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.part.{world}{tag}")
     if all(os.path.exists(f"{prefix}.{r}.pkl") for r in range(world)):
         return prefix
-    gpath = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.global.pkl")
+    gpath = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.global.raw.pkl")
     if os.path.exists(gpath):                                   # the global case is shared by every partition count
         with open(gpath, "rb") as f:
             d, cfg = pickle.load(f)
     else:
-        d, cfg = make_case(n_cells, n_levels, num_scalars=num_scalars)
+        d, cfg = make_case(n_cells, n_levels, num_scalars=num_scalars, derive=False)     # derived fields are computed per block
         if n_cells <= 200000:                                   # 4 GB at x1.163842; not worth 17 GB at x1.655362
             with open(gpath + ".tmp", "wb") as f:
                 pickle.dump((d, cfg), f, protocol=4)
