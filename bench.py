@@ -259,7 +259,9 @@ def main():
     for _ in range(args.warmup):
         g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:                                  # one nvidia-smi poller per job is enough (the line reports rank 0's GPU)
+        sampler.start()
     l0 = g.kernel_launch_count()
     g.timer_start()
     for _ in range(args.steps):
@@ -313,7 +315,7 @@ def main():
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": n_cells / e2e_s, "unit": "cell-columns/s", "steps_per_s": 1.0 / e2e_s, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": 1e3 * e2e_s}
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- per-kernel timing (CUDA events on the launching stream) for the roofline object
     barrier()
