@@ -97,3 +97,26 @@ def test_init_file_round_trip_and_step(tmp_path):
         o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt); o.atm_srk3(dt)
     for name in ("u", "w", "rho_zz", "theta_m", "scalars"):
         assert np.array_equal(o1.get_array(name, 2), o2.get_array(name, 2)), name
+
+
+def test_compare_tool_against_a_restart_file(tmp_path):
+    """tools/compare_with_reference_output.py, the one-command pin against a real MPAS run: here the 'reference' restart
+    file is written from the oracle's own state after two steps, so the comparison must come out exactly zero."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "cmp_tool", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "compare_with_reference_output.py"))
+    tool = importlib.util.module_from_spec(spec); spec.loader.exec_module(tool)
+    init = str(tmp_path / "x1.642.init.nc")
+    tool.main(["write-init", init, "--cells", "642", "--levels", "10"])
+    d, cfg, b = tool.run_from_init(init, 2)
+    nC, nE, nz = d["nCells"], d["nEdges"], d["nVertLevels"]
+    fields = {"u": ncio.Var(("Time", "nEdges", "nVertLevels"), b.get_array("u", 1)[:nE][None]),
+              "w": ncio.Var(("Time", "nCells", "nVertLevelsP1"), b.get_array("w", 1)[:nC][None]),
+              "rho_zz": ncio.Var(("Time", "nCells", "nVertLevels"), b.get_array("rho_zz", 1)[:nC][None]),
+              "theta_m": ncio.Var(("Time", "nCells", "nVertLevels"), b.get_array("theta_m", 1)[:nC][None]),
+              "qv": ncio.Var(("Time", "nCells", "nVertLevels"), b.get_array("scalars", 1)[:nC, :, 0][None])}
+    rst = str(tmp_path / "restart.nc")
+    ncio.write(rst, {"Time": 0, "nCells": nC, "nEdges": nE, "nVertLevels": nz, "nVertLevelsP1": nz + 1}, {}, fields, version=5, unlimited="Time")
+    assert tool.main(["compare", init, rst, "--steps", "2"]) == 0.0
+    assert tool.main(["compare", init, rst, "--steps", "1"]) > 1e-6          # and it does notice a different state
