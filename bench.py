@@ -100,11 +100,14 @@ KERNEL_MODEL_C = {
 }
 
 
+NCU_STEP_CSV = os.path.join("profiles", "r1_ncu_step_metrics.csv")
+
+
 def kernel_traffic(kernel, n_cells, n_lev, rb):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one step in the
     committed ncu capture profiles/r1_ncu_step_metrics.csv (tools/ncu_step_metrics.sh: x1.40962 x 55 levels, fp64).
     Only valid for that workload; None otherwise."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_step_metrics.csv")
+    path = os.path.join(ROOT, NCU_STEP_CSV)
     if not (os.path.exists(path) and (n_cells, n_lev, rb) == (40962, 55, 8)):
         return None
     import csv
@@ -137,16 +140,20 @@ def line_common(args, n_cells, n_lev, dt, world):
                                    "`value` is the one BASELINE throughput figure that is comparable across N: cell-column "
                                    "updates/s = nCells x steps/s; steps_per_s and sdpd are reported beside it",
                    "l2": "no flush: every step streams the block's fields (>= 3.5 GB at 40962 cells x 55 levels), >> 126 MB L2",
-                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"},
+                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)",
+                   "timed_region": "K x (atm_srk3 + mpas_pool_shift_time_levels), fields resident; excluded: mesh/state generation, "
+                                   "upload, init-time diagnostics, the min/max summary (taken once after the loop), H2D/D2H (those are in e2e)"},
+        # outside `config` so that both arms print the same config object
+        "implementation": "B200 CUDA library (libmpasb.so) through the C ABI" if args.impl != "reference"
+                          else "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build",
     }
 
 
 def reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The Fortran build is
     impossible in this image (no Fortran compiler/MPI/NetCDF), so this times the C++ restatement
-    (oracle/, OpenMP over the same cell/edge ranges) on the box's host cores.  For N > 1 workloads
-    the sample is ONE block of the N-block decomposition (1/N of the mesh plus its halo); the
-    whole-mesh rate on the same cores is the block rate / N."""
+    (oracle/, OpenMP over the same cell/edge ranges) on the box's host cores, on the same workload
+    and decomposition as the GPU arm."""
     if rank != 0:
         return
     from oracle import oracle as orc
@@ -154,38 +161,68 @@ def reference_arm(args, rank, world):
     n_threads = int(os.environ.get("MPASB_REF_THREADS", os.cpu_count()))
     orc.set_threads(n_threads)                    # torchrun forces OMP_NUM_THREADS=1 into its ranks; the baseline uses every core
     n_cells, n_lev = workload_for(args)
+    blocks = None
+    extrapolated = False
     if args.gpus > 1:
+        # the N-block decomposition itself, every block in this process in lock step with in-process halo exchanges
+        # (the oracle's "virtual ranks") -- the whole mesh is stepped, nothing is extrapolated.  Only the 8-block
+        # x1.655362 case (55 GB of oracle state, minutes per step) falls back to ONE block x 1/N, labelled as such.
         from mpas_model_b200 import multigpu as mg
-        rec = mg.load_block(mg.prepare_blocks(n_cells, n_lev, args.scalars, args.gpus), 0)
-        d, cfg = rec["block"], rec["cfg"]
-        frac = 1.0 / args.gpus
-        sample_what = f"block 0 of {args.gpus} ({d['nCellsSolve']} owned cells + halo; halo values frozen), rate scaled by 1/{args.gpus}"
+        prefix = mg.prepare_blocks(n_cells, n_lev, args.scalars, args.gpus)
+        whole = args.gpus <= 4 or os.environ.get("MPASB_REF_WHOLE_MESH")
+        ranks = range(args.gpus) if whole else range(1)
+        blocks = []
+        for r in ranks:
+            rec = mg.load_block(prefix, r)
+            ob = OracleDycore(rec["block"], rec["cfg"], rank=r)
+            for kind, k in mg.KINDS:
+                ob.set_halo_lists(k, rec["ex"][kind])
+            blocks.append(ob)
+            cfg = rec["cfg"]
+        frac = 1.0 if whole else 1.0 / args.gpus
+        extrapolated = not whole
+        sample_what = (f"all {args.gpus} blocks of the decomposition in lock step (in-process halo exchanges)" if whole else
+                       f"EXTRAPOLATED: block 0 of {args.gpus} only ({rec['block']['nCellsSolve']} owned cells + halo, halo values frozen), rate scaled by 1/{args.gpus}")
     else:
         from mpas_model_b200.case import make_case
         d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
         frac = 1.0
         sample_what = "the whole mesh"
+        blocks = [OracleDycore(d, cfg)]
     dt = cfg["config_dt"]
-    o = OracleDycore(d, cfg)
-    o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
-    t0 = time.time(); o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); t1 = time.time() - t0
+    multi = len(blocks) > 1
+
+    def one_step():
+        if multi:
+            orc.step(blocks, dt)
+        else:
+            blocks[0].atm_srk3(dt)
+        for b in blocks:
+            b.mpas_pool_shift_time_levels()
+
+    if multi:
+        orc.exchange(blocks, "initialization:u")
+    for b in blocks:
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+    if multi:
+        orc.exchange(blocks, "initialization:pv_edge,ru,rw")
+    t0 = time.time(); one_step(); t1 = time.time() - t0
     warm = max(0, min(args.warmup - 1, int(20.0 / max(t1, 1e-3))))
     for _ in range(warm):
-        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+        one_step()
     steps = max(1, min(args.steps, int(100.0 / max(t1, 1e-3))))
     t0 = time.time()
     for _ in range(steps):
-        o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+        one_step()
     el = time.time() - t0
     sps = frac * steps / el                       # whole-mesh steps/s
     v = n_cells * sps                             # cell-column updates/s (the line's unit)
     cores = n_threads
     line = line_common(args, n_cells, n_lev, dt, args.gpus)
-    line["config"]["implementation"] = "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build"
     line.update({
         "impl": "reference", "value": v, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 / sps,
         "cpu_baseline": {"value": v, "unit": "cell-columns/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full atm_srk3 steps on {sample_what}"},
+                         "sample": f"{steps} full atm_srk3 steps on {sample_what}", "extrapolated": extrapolated},
         "e2e": {"value": v, "unit": "cell-columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": sps, "sdpd": dt * sps, "cell_columns_per_s": v,
     })
@@ -195,7 +232,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=0, help="override the mesh (10*4^n+2 cells)")
@@ -256,16 +293,22 @@ def main():
         return float(t[0])
 
     # ---------------- device-resident throughput
-    for _ in range(args.warmup):
+    STATE = ("u", "w", "rho_zz", "theta_m", "scalars")
+    snap = {}                                      # GPU state after warm-up step 1 and after the last warm-up step (parity check below)
+    for k in range(1, args.warmup + 1):
         g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
+        if world == 1 and not args.no_cpu_baseline and k in (1, args.warmup):
+            snap[k] = {n: g.get_array(n, 1).astype(np.float64) for n in STATE}
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:                                  # one nvidia-smi poller per job is enough (the line reports rank 0's GPU)
         sampler.start()
     l0 = g.kernel_launch_count()
     g.timer_start()
-    for _ in range(args.steps):
-        g.atm_srk3(dt); g.mpas_pool_shift_time_levels()
+    for k in range(args.steps):
+        g.atm_srk3(dt)
+        if k + 1 < args.steps:
+            g.mpas_pool_shift_time_levels()
     ms = g.timer_stop()
     barrier()
     launches = int(sum_over_ranks(g.kernel_launch_count() - l0))
@@ -277,7 +320,8 @@ def main():
         t = torch.tensor([-mm[0], mm[1], -mm[2], mm[3]], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)              # the reference's mpas_dmpar_min/max_real (TI:8300-8318)
         mm = (-float(t[0]), float(t[1]), -float(t[2]), float(t[3]))
-    minmax = mm
+    minmax = mm                                     # of the state the LAST timed step produced (time level 2, before the shift)
+    g.mpas_pool_shift_time_levels()
 
     # ---------------- end to end through the C ABI with pinned host buffers (every rank moves its own block)
     e2e = None
@@ -338,25 +382,47 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom_name[2:], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
                 "traffic": kernel_traffic(dom_name[2:], n_cells, n_lev, rb) if world == 1 else None,
+                "traffic_source": f"replayed from the committed ncu capture {NCU_STEP_CSV} (dram__bytes_read.sum + dram__bytes_write.sum per "
+                                  "launch, averaged over the launches of one step of this workload); not measured in this run",
                 "avg_launch_us": dom_us, "share_of_step": dom_ms / ksum,
                 "algorithmic_bytes_per_launch": (model_c * C) if model_c else None, "peak_source": peak_src}
     B_step = model_bytes_per_step(n_cells, n_lev, args.scalars, rb)
     step_gbs = B_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---------------- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only)
+    # ---------------- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only); the same oracle
+    # run is the parity check of this very bench run: GPU state after warm-up steps 1 and W against the oracle's
     cpu = None
+    parity = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as orc
         from oracle.oracle import OracleDycore
         n_threads = int(os.environ.get("MPASB_REF_THREADS", os.cpu_count()))
         orc.set_threads(n_threads)
-        o = OracleDycore(d, cfg)
+        o = OracleDycore(d, cfg, precision=args.precision)
         o.atm_init_coupled_diagnostics(); o.atm_init_solve_diagnostics(dt)
+
+        def rel_l2_all(k):
+            out = {}
+            for nme in STATE:
+                a, r = snap[k][nme], o.get_array(nme, 1).astype(np.float64)
+                out[nme] = float(np.linalg.norm((a - r).ravel()) / max(np.linalg.norm(r.ravel()), 1e-300))
+            return out
+
         o.atm_srk3(dt); o.mpas_pool_shift_time_levels()
+        parity = {"against": "CPU oracle (oracle/, same precision) stepped from the same initial state",
+                  "after_steps": {}}
+        if 1 in snap:
+            parity["after_steps"]["1"] = rel_l2_all(1)
         t0 = time.time(); n = 0
-        while n < 3 or (time.time() - t0 < 10.0 and n < 20):
+        while n < 3 or (time.time() - t0 < 10.0 and n < 20) or (n + 1 < args.warmup <= 12):
             o.atm_srk3(dt); o.mpas_pool_shift_time_levels(); n += 1
+            if n + 1 == args.warmup and args.warmup in snap and args.warmup > 1:
+                t1 = time.time()
+                parity["after_steps"][str(args.warmup)] = rel_l2_all(args.warmup)
+                t0 += time.time() - t1              # the comparison is not part of the CPU timing
         el = time.time() - t0
+        parity["parity_rel_l2"] = max(parity["after_steps"]["1"].values()) if "1" in parity["after_steps"] else None
+        parity["bar"] = "1e-11 after one RK3 step (fp64); fp32: compared with the fp32 restatement"
         cpu = {"value": n_cells * n / el, "unit": "cell-columns/s", "steps_per_s": n / el, "cores": n_threads,
                "kind": "port", "sample": f"{n} full atm_srk3 steps of the same workload (C++/OpenMP restatement, not the Fortran build)"}
 
@@ -364,7 +430,7 @@ def main():
         return
     line = line_common(args, n_cells, n_lev, dt, world)
     if world > 1:
-        line["config"]["halo_exchange"] = ("CUDA-IPC put/get kernels over NVLink" if getattr(g, "p2p_on", False) else "pack -> NCCL send/recv -> unpack") \
+        line["halo_exchange"] = ("CUDA-IPC put/get kernels over NVLink" if getattr(g, "p2p_on", False) else "pack -> NCCL send/recv -> unpack") \
             + ("" if os.environ.get("MPASB_NO_OVERLAP") else ", 3 of the exchange groups overlapped with compute on a priority stream")
     if args.precision == "single":
         line["dtype"] = "f32"
@@ -374,7 +440,8 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs,
                           "frac_of_measured_peak": step_gbs / (peak * world), "frac_of_nominal_8TBs": step_gbs / (8000.0 * world)},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity": parity,
+        "parity_rel_l2": parity["parity_rel_l2"] if parity else None,
         "steps_per_s": steps_per_s, "sdpd": dt * steps_per_s, "cell_columns_per_s": value,
         "minmax_w_u": list(minmax),
         "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:14]},

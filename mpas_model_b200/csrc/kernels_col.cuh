@@ -121,8 +121,8 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
     const int LDK = D.LDK, nl = D.nl;                                                         \
     if (i >= (ncols)) return;                                                                 \
     Lv lv; lv.k0 = 2 * lane;                                                                  \
-    const int k0 = lv.k0; const bool act = k0 < LDK; (void)nl;                                \
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;                             \
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
 #define LD(p, col) ld2((p), (unsigned)(col) * uLDK + kc)
 #define ST(p, col, v) st2((p), (unsigned)(col) * uLDK + kc, act, (v))
 #define BC(v, src) __shfl_sync(CW_FULL, (v), (src))
@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
     const int4 hdr = tile_hdr[tile];                        // (runs, staged columns, active-edge mask); runs < 0: gather from global memory
     const int nt = hdr.x;
     Lv lv; lv.k0 = 2 * lane;
-    const int k0 = lv.k0; const bool act = k0 < LDK;
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const unsigned bar = smem_u32(&ef_bar);
     if (nt > 0) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, (unsigned)(hdr.y * 2 * LDK * sizeof(real))); }
@@ -772,8 +772,8 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
     real* s_ts = s_ga + AC3_COLS * S;
     real* s_rs = s_ts + AC3_COLS * S;
     Lv lv; lv.k0 = 2 * lane;
-    const int k0 = lv.k0; const bool act = k0 < LDK;
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const bool first = small_step == 1;
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
     const int base = blockIdx.x * AC3_COLS;
@@ -1105,8 +1105,8 @@ __global__ void __launch_bounds__(VIC_WARPS * 32, MB_VIC) k3_vert_imp_coefs(cons
     real* s_b = s_a + VIC_COLS * S;
     real* s_c = s_b + VIC_COLS * S;
     Lv lv; lv.k0 = 2 * lane;
-    const int k0 = lv.k0; const bool act = k0 < LDK;
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, LDK - 2);
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
     const int base = blockIdx.x * VIC_COLS;
     const r2 fzm = LD(D.fzm, 0), fzp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0), rdzu = LD(D.rdzu, 0);

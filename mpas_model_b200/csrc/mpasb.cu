@@ -127,7 +127,8 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     Dev& D = h->D;
     D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
     D.nCellsSolve = dims->nCellsSolve; D.nEdgesSolve = dims->nEdgesSolve; D.nVerticesSolve = dims->nVerticesSolve;
-    D.nl = dims->nVertLevels; D.LDK = (dims->nVertLevels + 1 + 1) / 2 * 2;
+    D.nl = dims->nVertLevels; D.LDKA = (dims->nVertLevels + 1 + 1) / 2 * 2; D.LDK = D.LDKA;
+    if (const char* al = getenv("MPASB_LDK_ALIGN")) { const int a = std::max(2, atoi(al)) / 2 * 2; D.LDK = (D.LDKA + a - 1) / a * a; }
     D.maxEdges = dims->maxEdges; D.maxEdges2 = dims->maxEdges2; D.num_scalars = dims->num_scalars;
     D.index_qv = dims->index_qv - 1; D.moist_start = dims->moist_start - 1; D.moist_end = dims->moist_end - 1;
     D.cellPlane = (size_t)(dims->nCells + 1) * D.LDK; D.edgePlane = (size_t)(dims->nEdges + 1) * D.LDK;

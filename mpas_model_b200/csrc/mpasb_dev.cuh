@@ -28,7 +28,8 @@ struct Dev {
     // dimensions (0-based counts; garbage column index == n)
     int nCells, nEdges, nVertices, nCellsSolve, nEdgesSolve, nVerticesSolve;
     int nl;            // nVertLevels
-    int LDK;           // padded level stride
+    int LDK;           // column pitch in reals (>= LDKA; MPASB_LDK_ALIGN rounds it up, e.g. to whole 128-byte lines)
+    int LDKA;          // active width: nVertLevels+1 rounded up to an even count; rows [LDKA, LDK) are never touched
     int maxEdges, maxEdges2, num_scalars;
     int index_qv, moist_start, moist_end;      // 0-based
     size_t cellPlane, edgePlane;               // (n+1)*LDK, stride between scalar planes

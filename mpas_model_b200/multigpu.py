@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import os
 import pickle
-import tempfile
 import time
 
 import numpy as np
@@ -61,19 +60,39 @@ GROUPS = {
 
 # ---------------------------------------------------------------------------------- bootstrap
 def _cache_dir():
-    p = os.environ.get("MPASB_CACHE", os.path.join(tempfile.gettempdir(), "mpasb_cases"))
-    os.makedirs(p, exist_ok=True)
+    """Per-user, mode-0700 directory for the prepared blocks (they are pickles: never read one from a directory another
+    user could have written).  MPASB_CACHE overrides the location, not the ownership check."""
+    p = os.environ.get("MPASB_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "mpasb_cases")
+    os.makedirs(p, mode=0o700, exist_ok=True)
+    st = os.stat(p)
+    if st.st_uid != os.getuid() or (st.st_mode & 0o022):
+        raise RuntimeError(f"{p}: block cache must be owned by the current user and not group/world-writable")
     return p
+
+
+def _source_key(n_cells, n_levels, num_scalars):
+    """Hash of everything a prepared block depends on: the generating sources and the default namelist, so that an edit
+    to the mesh generator, the JW initialisation, the init-time derivations or the decomposition never reuses stale blocks."""
+    import hashlib
+    from . import case, decomp as dc, init_block, jw_init, mesh, reconstruct
+    hsh = hashlib.sha256()
+    for mod in (case, dc, init_block, jw_init, mesh, reconstruct):
+        with open(mod.__file__, "rb") as f:
+            hsh.update(f.read())
+    hsh.update(repr(sorted(init_block.default_config(1.0, 1.0).items())).encode())
+    hsh.update(f"{n_cells}.{n_levels}.{num_scalars}".encode())
+    return hsh.hexdigest()[:12]
 
 
 def prepare_blocks(n_cells, n_levels, num_scalars, world, tag=""):
     """Rank-0 work: global case -> partition -> one pickle per rank.  Returns the path prefix.
     The pickles are reused by later runs of the same (mesh, levels, scalars, world)."""
     from .case import make_case
-    prefix = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.part.{world}{tag}")
+    key = _source_key(n_cells, n_levels, num_scalars)
+    prefix = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.{key}.part.{world}{tag}")
     if all(os.path.exists(f"{prefix}.{r}.pkl") for r in range(world)):
         return prefix
-    gpath = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.global.raw.pkl")
+    gpath = os.path.join(_cache_dir(), f"x1.{n_cells}.L{n_levels}.S{num_scalars}.{key}.global.raw.pkl")
     if os.path.exists(gpath):                                   # the global case is shared by every partition count
         with open(gpath, "rb") as f:
             d, cfg = pickle.load(f)

@@ -22,7 +22,42 @@
 #include <algorithm>
 #include "../include/mpasb.h"
 
+// RKIND: PRECISION=double, or PRECISION=single when built -DORACLE_SINGLE -fsingle-precision-constant (every
+// un-suffixed literal is then a float, as the reference's default-kind literals are in its single build:
+// reference Makefile:861-873, src/framework/mpas_kind_types.F:22-28)
+#ifdef ORACLE_SINGLE
+typedef float real;
+#else
 typedef double real;
+#endif
+
+// the namelist in RKIND (mpasb_config carries doubles across the ABI whatever the build precision)
+struct OCfg {
+    int config_time_integration_order, config_number_of_sub_steps, config_dynamics_split_steps, config_split_dynamics_transport,
+        config_scalar_advection, config_monotonic, config_positive_definite, config_horiz_mixing, config_mix_full,
+        config_rayleigh_damp_u, config_number_rayleigh_damp_u_levels, config_number_cam_damping_levels, config_apply_lbcs,
+        config_print_global_minmax_vel;
+    real config_epssm, config_smdiv, config_len_disp, config_coef_3rd_order, config_visc4_2dsmag, config_smagorinsky_coef,
+         config_del4u_div_factor, config_h_mom_eddy_visc2, config_h_mom_eddy_visc4, config_v_mom_eddy_visc2,
+         config_h_theta_eddy_visc2, config_h_theta_eddy_visc4, config_v_theta_eddy_visc2, config_apvm_upwinding,
+         config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days, cf1, cf2, cf3, sphere_radius;
+    int on_a_sphere;
+    OCfg() {}
+    explicit OCfg(const mpasb_config& c) {
+#define CI(n) n = c.n;
+#define CR(n) n = (real)c.n;
+        CI(config_time_integration_order) CI(config_number_of_sub_steps) CI(config_dynamics_split_steps) CI(config_split_dynamics_transport)
+        CI(config_scalar_advection) CI(config_monotonic) CI(config_positive_definite) CI(config_horiz_mixing) CI(config_mix_full)
+        CI(config_rayleigh_damp_u) CI(config_number_rayleigh_damp_u_levels) CI(config_number_cam_damping_levels) CI(config_apply_lbcs)
+        CI(config_print_global_minmax_vel) CI(on_a_sphere)
+        CR(config_epssm) CR(config_smdiv) CR(config_len_disp) CR(config_coef_3rd_order) CR(config_visc4_2dsmag) CR(config_smagorinsky_coef)
+        CR(config_del4u_div_factor) CR(config_h_mom_eddy_visc2) CR(config_h_mom_eddy_visc4) CR(config_v_mom_eddy_visc2)
+        CR(config_h_theta_eddy_visc2) CR(config_h_theta_eddy_visc4) CR(config_v_theta_eddy_visc2) CR(config_apvm_upwinding)
+        CR(config_mpas_cam_coef) CR(config_rayleigh_damp_u_timescale_days) CR(cf1) CR(cf2) CR(cf3) CR(sphere_radius)
+#undef CI
+#undef CR
+    }
+};
 
 // src/framework/mpas_constants.F:43-56
 static const real gravity = 9.80616, rgas = 287.0, cp = 7.0 * 287.0 / 2.0, rv = 461.6;
@@ -55,7 +90,7 @@ struct HaloList {      // one (neighbour, layer) pair of a kind (cell/edge/verte
 
 struct Block {
     mpasb_dims d;
-    mpasb_config c;
+    OCfg c;
     std::map<std::string, std::vector<real>> rf;
     std::map<std::string, std::vector<int>> nf;
     std::map<std::string, const FieldDef*> defs;
@@ -839,7 +874,7 @@ static void atm_compute_dyn_tend(Block& b, int rk_step, real dt) {
     const int nVertLevels = b.d.nVertLevels, vertexDegree = b.d.vertexDegree;
     const int cellStart = 1, cellEnd = b.d.nCells, edgeStart = 1, edgeEnd = b.d.nEdges, vertexStart = 1, vertexEnd = b.d.nVertices;
     const int cellSolveStart = 1, cellSolveEnd = b.d.nCellsSolve, edgeSolveStart = 1, edgeSolveEnd = b.d.nEdgesSolve;
-    const mpasb_config& c = b.c;
+    const OCfg& c = b.c;
     A1 dvEdge = b.r1("dvEdge"), dcEdge = b.r1("dcEdge"), invDcEdge = b.r1("invDcEdge"), invDvEdge = b.r1("invDvEdge"),
        invAreaCell = b.r1("invAreaCell"), invAreaTriangle = b.r1("invAreaTriangle"),
        meshScalingDel2 = b.r1("meshScalingDel2"), meshScalingDel4 = b.r1("meshScalingDel4"), angleEdge = b.r1("angleEdge");
@@ -1603,7 +1638,7 @@ static void exchange_halo_group(Domain& dom, const char* name) {
 #define FOR_BLOCKS for (Block* bp : dom.blocks)
 // advance_scalars (TI:1730-1927): plain RK stage, or the monotonic routine with its two exchange points on stage 3
 static void advance_scalars(Domain& dom, int rk_step, real dt_rk) {
-    const mpasb_config& c = dom.blocks[0]->c;
+    const OCfg& c = dom.blocks[0]->c;
     if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) {
         FOR_BLOCKS atm_advance_scalars(*bp, dt_rk, rk_step);
     } else {
@@ -1618,7 +1653,7 @@ static void advance_scalars(Domain& dom, int rk_step, real dt_rk) {
     }
 }
 static void atm_srk3(Domain& dom, real dt) {
-    const mpasb_config& c = dom.blocks[0]->c;
+    const OCfg& c = dom.blocks[0]->c;
     FOR_BLOCKS {   // TI:967-991, 1091-1093
         Block& b = *bp;
         std::fill(b.rf["qtot"].begin(), b.rf["qtot"].end(), 0.0);
@@ -1686,28 +1721,29 @@ static void atm_srk3(Domain& dom, real dt) {
 extern "C" {
 void* oracle_create(const mpasb_dims* d, const mpasb_config* c, int rank) {
     Block* b = new Block();
-    b->d = *d; b->c = *c; b->rank = rank;
+    b->d = *d; b->c = OCfg(*c); b->rank = rank;
     b->init();
     return b;
 }
 void oracle_destroy(void* h) { delete (Block*)h; }
+int oracle_real_bytes(void) { return (int)sizeof(real); }
 long oracle_field_count(void* h, const char* name) {
     Block* b = (Block*)h;
     auto it = b->defs.find(name);
     return it == b->defs.end() ? -1 : b->count(it->second);
 }
-int oracle_set_field(void* h, const char* name, int lev, const double* src, long n) {
+int oracle_set_field(void* h, const char* name, int lev, const real* src, long n) {
     Block* b = (Block*)h;
     auto it = b->rf.find(Block::key(name, lev));
     if (it == b->rf.end() || (long)it->second.size() != n) return 1;
-    memcpy(it->second.data(), src, n * sizeof(double));
+    memcpy(it->second.data(), src, n * sizeof(real));
     return 0;
 }
-int oracle_get_field(void* h, const char* name, int lev, double* dst, long n) {
+int oracle_get_field(void* h, const char* name, int lev, real* dst, long n) {
     Block* b = (Block*)h;
     auto it = b->rf.find(Block::key(name, lev));
     if (it == b->rf.end() || (long)it->second.size() != n) return 1;
-    memcpy(dst, it->second.data(), n * sizeof(double));
+    memcpy(dst, it->second.data(), n * sizeof(real));
     return 0;
 }
 int oracle_set_field_int(void* h, const char* name, const int* src, long n) {   // 1-based, like the ABI
@@ -1742,7 +1778,7 @@ void oracle_exchange(void** hs, int n, const char* group) { Domain d = make_doma
 void oracle_minmax(void* h, double out[4]) {      // TI:8286-8319: reductions start from 0, owned elements only
     Block* b = (Block*)h;
     A2 w = b->r2("w", 2), u = b->r2("u", 2);
-    double wmin = 0, wmax = 0, umin = 0, umax = 0;
+    real wmin = 0, wmax = 0, umin = 0, umax = 0;
     for (int i = 1; i <= b->d.nCellsSolve; i++) for (int k = 1; k <= b->d.nVertLevels; k++) { wmin = std::min(wmin, w(k, i)); wmax = std::max(wmax, w(k, i)); }
     for (int i = 1; i <= b->d.nEdgesSolve; i++) for (int k = 1; k <= b->d.nVertLevels; k++) { umin = std::min(umin, u(k, i)); umax = std::max(umax, u(k, i)); }
     out[0] = wmin; out[1] = wmax; out[2] = umin; out[3] = umax;

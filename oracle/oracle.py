@@ -16,26 +16,28 @@ from mpas_model_b200.dycore import Backend, make_config, make_dims
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
+LIB_PATH_SINGLE = os.path.join(_HERE, "liboracle_sp.so")      # PRECISION=single restatement (RKIND = float)
 
 
 def build(force=False):
     src = os.path.join(_HERE, "dycore_oracle.cpp")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    if force or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src) for p in (LIB_PATH, LIB_PATH_SINGLE)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB_PATH
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(precision="double"):
+    if precision not in _libs:
         build()
-        _lib = C.CDLL(LIB_PATH)
-        _lib.oracle_create.restype = C.c_void_p
-        _lib.oracle_field_count.restype = C.c_long
-    return _lib
+        l = C.CDLL(LIB_PATH_SINGLE if precision == "single" else LIB_PATH)
+        l.oracle_create.restype = C.c_void_p
+        l.oracle_field_count.restype = C.c_long
+        assert l.oracle_real_bytes() == (4 if precision == "single" else 8)
+        _libs[precision] = l
+    return _libs[precision]
 
 
 def set_threads(n: int) -> None:
@@ -49,8 +51,11 @@ def set_threads(n: int) -> None:
 
 
 class OracleDycore(Backend):
-    def __init__(self, block: dict, cfg: dict, rank: int = 0):
-        self.lib = lib()
+    def __init__(self, block: dict, cfg: dict, rank: int = 0, precision: str = "double"):
+        self.lib = lib(precision)
+        self.precision = precision
+        if precision == "single":
+            self.rdtype, self.creal = np.float32, C.c_float
         self.dims = make_dims(block)
         self.config = make_config(cfg, block)
         self._h = C.c_void_p(self.lib.oracle_create(C.byref(self.dims), C.byref(self.config), C.c_int(rank)))
@@ -109,9 +114,9 @@ class OracleDycore(Backend):
 def step(blocks, dt):
     """atm_srk3 over N in-process blocks ("virtual ranks") in lock step."""
     arr = (C.c_void_p * len(blocks))(*[b._h for b in blocks])
-    lib().oracle_step(arr, C.c_int(len(blocks)), C.c_double(dt))
+    blocks[0].lib.oracle_step(arr, C.c_int(len(blocks)), C.c_double(dt))
 
 
 def exchange(blocks, group):
     arr = (C.c_void_p * len(blocks))(*[b._h for b in blocks])
-    lib().oracle_exchange(arr, C.c_int(len(blocks)), group.encode())
+    blocks[0].lib.oracle_exchange(arr, C.c_int(len(blocks)), group.encode())

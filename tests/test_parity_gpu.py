@@ -81,7 +81,7 @@ def test_init_routines(pair):
     assert not bad, bad
 
 
-def _walk_routines(d, cfg, o, g):
+def _walk_routines(d, cfg, o, g, tol_pow=TOL_ROUTINE):
     """Walk atm_srk3 routine by routine.  After each routine the CUDA fields are compared
     with the oracle's and then overwritten by them, so every routine is judged on
     bit-identical inputs (otherwise the 1-ulp pow() difference in exner is amplified
@@ -100,7 +100,7 @@ def _walk_routines(d, cfg, o, g):
         if not g.strict_arithmetic():
             assert worst[1] <= TOL_ROUTINE_FAST, (label, worst)
         elif uses_pow:
-            assert worst[1] <= TOL_ROUTINE, (label, worst)
+            assert worst[1] <= tol_pow, (label, worst)
         else:
             assert worst[1] == 0.0, (label, worst)          # bit for bit
         sync_all(o, g)
@@ -139,6 +139,81 @@ def test_irregular_mesh_with_heptagons():
         o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
     worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
     assert max(worst.values()) <= 10 * TOL_STEP, worst
+    g.close(); o.close()
+
+
+def _one_step_worst(d, cfg, n_steps=1, monkeypatch=None):
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    for _ in range(n_steps):
+        o.atm_srk3(dt); g.atm_srk3(dt)
+        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+    worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
+    mm = (o.summarize_timestep(), g.summarize_timestep())
+    g.close(); o.close()
+    return worst, mm
+
+
+def test_55_levels_every_routine_and_one_step():
+    """The level count every BASELINE.json GPU configuration is quoted on: nVertLevels = 55 is ODD, so
+    LDK = nVertLevels + 1 = 56 has no pad row and 28 of a warp's 32 level pairs are active -- a different
+    code shape from the even 26/10-level cases (one pad row).  x1.10242 (BASELINE config 0's mesh) x 55 levels:
+    every routine on identical inputs, then one full step within the north-star bar."""
+    from mpas_model_b200.case import make_case
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d, cfg = make_case(10242, 55, num_scalars=2)
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    report = _walk_routines(d, cfg, o, g)
+    if g.strict_arithmetic():
+        assert sum(1 for _, w in report if w[1] == 0.0) >= len(report) - 4
+    g.close(); o.close()
+    worst, mm = _one_step_worst(d, cfg)
+    assert max(worst.values()) <= TOL_STEP, worst
+    assert np.allclose(mm[0], mm[1], rtol=1e-12, atol=0), mm
+
+
+def test_bench_configuration_one_step():
+    """BASELINE.json configs[1], the workload bench.py's N = 1 line is measured on: x1.40962, 55 levels, fp64,
+    dt = 720 s, reference-default namelist.  One RK3 step against the oracle within the north-star bar."""
+    from mpas_model_b200.case import make_case
+    d, cfg = make_case(40962, 55, num_scalars=1)
+    assert cfg["config_dt"] == 720.0
+    worst, mm = _one_step_worst(d, cfg)
+    print("x1.40962 x 55 one step rel-L2 vs oracle:", worst)
+    assert max(worst.values()) <= TOL_STEP, worst
+    assert np.allclose(mm[0], mm[1], rtol=1e-12, atol=0), mm
+
+
+def test_21_scalars_55_levels():
+    """The shape of BASELINE.json configs[4]: qv + 20 passive tracers through the monotonic transport, 55 levels
+    (on x1.2562 so that the oracle finishes in seconds).  Two steps within the bar, every tracer monotone and
+    its mass conserved to round-off."""
+    from mpas_model_b200.case import make_case
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d, cfg = make_case(2562, 55, num_scalars=21)
+    o, g = OracleDycore(d, cfg), Dycore(d, cfg)
+    dt = cfg["config_dt"]
+    _init(o, g, dt)
+    nC = d["nCells"]
+    vol = d["areaCell"][:nC, None] / d["rdzw"][None, :]
+    q0 = g.get_array("scalars", 1)[:nC].copy()
+    m0 = (g.get_array("rho_zz", 1)[:nC, :, None] * q0 * vol[..., None]).sum(axis=(0, 1))
+    for _ in range(2):
+        o.atm_srk3(dt); g.atm_srk3(dt)
+        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+    worst = {n: float(rel_l2(g.get_array(n, 1), o.get_array(n, 1))) for n in STATE}
+    assert max(worst.values()) <= 10 * TOL_STEP, worst
+    q = g.get_array("scalars", 1)[:nC]
+    m1 = (g.get_array("rho_zz", 1)[:nC, :, None] * q * vol[..., None]).sum(axis=(0, 1))
+    assert q.min() >= 0.0
+    for s in range(1, 21):
+        assert q[..., s].max() <= q0[..., s].max() * (1 + 1e-12) and q[..., s].min() >= q0[..., s].min() * (1 - 1e-12), s
+        assert abs(m1[s] - m0[s]) <= 1e-12 * abs(m0[s]), (s, m0[s], m1[s])
     g.close(); o.close()
 
 
@@ -352,26 +427,44 @@ def test_one_simulated_day(pair):
 
 
 def test_single_precision_build(small_case):
-    """PRECISION=single build (libmpasb_sp.so, RKIND = float) against the fp64 oracle: north-star bar 1e-4 after one
-    simulated day.  The same kernels, compiled with real = float; inputs are rounded to float at upload."""
+    """PRECISION=single build (libmpasb_sp.so, RKIND = float) against BOTH oracles.
+
+    (a) fp32 oracle (liboracle_sp.so: the same restatement with RKIND = float and every literal a float, as the
+        reference's single build has them): every routine on identical inputs is bit-identical except the powf()
+        routines, and one full step agrees to a few ulps.
+    (b) fp64 oracle, one simulated day: north-star bar 1e-4 on u, rho_zz, theta_m and the moist scalar.  w is a residual
+        of cancelling terms of size 1e-3 m/s in this case: the reference's OWN single-precision arithmetic (the fp32
+        oracle) is 4e-3 away from its fp64 arithmetic after a day, so no fp32 implementation can hold 1e-4 on it;
+        the library is required to be as close to fp64 as the fp32 restatement is (factor 2)."""
     from mpas_model_b200.dycore import Dycore
     from oracle.oracle import OracleDycore
     d, cfg = small_case
     dt = cfg["config_dt"]
     o = OracleDycore(d, cfg)
+    os_ = OracleDycore(d, cfg, precision="single")
     g = Dycore(d, cfg, precision="single")
-    assert g.rdtype == np.float32 and not np.isnan(g.get_array("zz")).any()
-    _init(o, g, dt)
-    report = {}
+    assert g.rdtype == np.float32 and os_.rdtype == np.float32 and not np.isnan(g.get_array("zz")).any()
+    report = _walk_routines(d, cfg, os_, g, tol_pow=2e-6)
+    assert sum(1 for _, w in report if w[1] == 0.0) >= len(report) - 4
+    os_.load_block(d); g.load_block(d)
+    for b in (o, os_, g):
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+    rep64, rep32, ora32 = {}, {}, {}
     n_steps = int(np.ceil(86400.0 / dt))
     for step in range(1, n_steps + 1):
-        o.atm_srk3(dt); g.atm_srk3(dt)
-        o.mpas_pool_shift_time_levels(); g.mpas_pool_shift_time_levels()
+        for b in (o, os_, g):
+            b.atm_srk3(dt); b.mpas_pool_shift_time_levels()
         if step in (1, n_steps):
-            report[step] = {n: float(rel_l2(g.get_array(n, 1).astype(np.float64), o.get_array(n, 1))) for n in STATE}
-    print("single-precision build vs fp64 oracle, rel-L2 after 1 step and after one day:", report)
-    for n in ("u", "rho_zz", "theta_m"):
-        assert report[n_steps][n] <= 1e-4, (n, report[n_steps][n])
-    # w (|w| ~ 1e-3 m/s, a residual of cancelling terms) and the all-zero qv carry no such guarantee in fp32
-    assert report[n_steps]["w"] <= 0.5
-    g.close()
+            ga = {n: g.get_array(n, 1).astype(np.float64) for n in STATE}
+            rep64[step] = {n: float(rel_l2(ga[n], o.get_array(n, 1))) for n in STATE}
+            rep32[step] = {n: float(rel_l2(ga[n], os_.get_array(n, 1).astype(np.float64))) for n in STATE}
+            ora32[step] = {n: float(rel_l2(os_.get_array(n, 1).astype(np.float64), o.get_array(n, 1))) for n in STATE}
+    print("single build vs fp64 oracle:", rep64)
+    print("single build vs fp32 oracle:", rep32)
+    print("fp32 oracle vs fp64 oracle :", ora32)
+    for n in STATE:
+        assert rep32[1][n] <= 5e-6 or (n == "w" and rep32[1][n] <= 1e-3), (n, rep32[1][n])     # one step, same precision
+    for n in ("u", "rho_zz", "theta_m", "scalars"):
+        assert rep64[n_steps][n] <= 1e-4, (n, rep64[n_steps][n])
+    assert rep64[n_steps]["w"] <= 2.0 * ora32[n_steps]["w"] + 1e-4, (rep64[n_steps]["w"], ora32[n_steps]["w"])
+    g.close(); o.close(); os_.close()
