@@ -167,7 +167,7 @@ __global__ void k_recover_cell1(const Dev D, real dt, real invNs, int rk_step, r
             AT(D.rtheta_p, i, k) = rtheta_p;
             AT(D.theta_m_2, i, k) = (rtheta_p + rtb) / rho_zz;
             const real zzk = AT(D.zz, i, k);
-            const real ex = pow(zzk * (rgas_p0) * (rtheta_p + rtb), rcv);
+            const real ex = pow_cr(zzk * (rgas_p0) * (rtheta_p + rtb), rcv);
             AT(D.exner, i, k) = ex;
             AT(D.pressure_p, i, k) = zzk * RGAS * (ex * rtheta_p + rtb
                                                     * (ex - AT(D.exner_base, i, k)));

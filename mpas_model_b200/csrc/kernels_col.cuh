@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const De
         rtheta_p = LD(D.rtheta_p_save, i) + LD(D.rtheta_pp, i)
                    - dt * rho_zz * LD(D.rt_diabatic_tend, i);
         const r2 arg = zz * (rgas_p0) * (rtheta_p + rtb);
-        const r2 ex = mk2(pow(arg.x, rcv), pow(arg.y, rcv));
+        const r2 ex = mk2(pow_cr(arg.x, rcv), pow_cr(arg.y, rcv));
         ST(D.exner, i, sel(k_lt_nl, ex, 0.0));
         ST(D.pressure_p, i, sel(k_lt_nl, zz * RGAS * (ex * rtheta_p + rtb
                                                        * (ex - LD(D.exner_base, i))), 0.0));

@@ -106,8 +106,8 @@ __global__ void k_initcd_cell1(const Dev D, real rvord, real rcv, real rgas_p0) 
     const real rho_p = rho_zz - rb;
     const real rtb = tb * rb;
     const real rtp = theta_m * rho_p + rb * (theta_m - tb);
-    const real ex = pow(zzk * (rgas_p0) * (rtp + rtb), rcv);
-    const real exb = pow(zzk * (rgas_p0) * (rtb), rcv);
+    const real ex = pow_cr(zzk * (rgas_p0) * (rtp + rtb), rcv);
+    const real exb = pow_cr(zzk * (rgas_p0) * (rtb), rcv);
     AT(D.rho_p, i, k) = rho_p;
     AT(D.rtheta_base, i, k) = rtb;
     AT(D.rtheta_p, i, k) = rtp;

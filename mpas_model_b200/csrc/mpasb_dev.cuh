@@ -8,6 +8,8 @@
 // Connectivity is 0-based on the device.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
+#include "pow_cr.cuh"
 
 // RKIND: PRECISION=double (default) or PRECISION=single (-DMPASB_SINGLE, reference Makefile: PRECISION=single)
 #ifdef MPASB_SINGLE

@@ -4,13 +4,15 @@
 // mpas_model_b200/csrc: only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load it.  The product never does.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
-// logs for the dycore arithmetic and cannot be compiled in
-// this image (no Fortran compiler / MPI / NetCDF), so this restatement is pinned
-// only by self-consistency (1-vs-N block bit equality, conservation, steady
-// state) and by being a literal, loop-for-loop transcription of
-//   /root/reference/src/core_atmosphere/dynamics/mpas_atm_time_integration.F  ("TI")
-// with 1-based indexing kept so that each loop can be read against the cited lines.
+// PARITY PIN: the reference ships no golden vectors or logs for the dycore arithmetic and this
+// image has no Fortran compiler, so the pin is the reference's own SOURCE TEXT: oracle/f2cpp.py transliterates
+//   /root/reference/src/core_atmosphere/dynamics/mpas_atm_time_integration.F  ("TI": every *_work routine of the step,
+//   their wrappers, the pool-based routines) and src/framework/mpas_constants.F
+// statement by statement into C++ at build time (oracle/_ref/, never committed), and tests/test_reference_pin.py requires
+// this hand-written restatement to equal it BIT FOR BIT -- every routine on identical inputs, every scratch array,
+// six non-default namelists, an irregular mesh, the single-precision build, and free-running steps.  What that pin
+// does not cover is stated in DESIGN.md §2 (gfortran's code generation itself; the routines outside TI).
+// This file keeps 1-based indexing so that each loop can be read against the cited lines.
 // Compile with -ffp-contract=off (mirrors -Mnofma, reference Makefile:160).
 #include <cmath>
 #include <cstdio>

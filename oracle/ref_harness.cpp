@@ -1,0 +1,130 @@
+// ref_harness.cpp -- C entry points around the reference's own dycore routines, transliterated from Fortran to C++
+// by oracle/f2cpp.py into oracle/_ref/ti_ref.inc (generated at build time from /root/reference, never committed).
+//
+// TEST INFRASTRUCTURE ONLY: loaded by tests/test_reference_pin.py (through oracle/ref.py) to pin the hand-written oracle
+// against the reference's own statements.  Hand-written here: the pool plumbing and, per entry point, the ONE call that
+// atm_srk3 makes to the routine (mpas_atm_time_integration.F line cited), with the index ranges an MPI-only run has
+// (nThreads = 1: cellThreadStart = 1, cellThreadEnd = nCells, cellSolveThreadEnd = nCellsSolve, ...;
+// mpas_atm_threading.F:114-125).  No arithmetic of the model is restated in this file.
+#include "f2cpp_rt.h"
+#include "_ref/ti_ref.inc"
+
+struct RefBlock {
+    std::map<std::string, int> dims;
+    std::map<std::string, CfgVal> cfgs;
+    Pool state, diag, mesh, tend, tend_physics, configs, halo_scratch, dimensions;
+    std::map<std::string, PoolEntry> module_arrays;
+    BlockT block;
+    std::string exchange_log;
+    RefBlock() {
+        Pool* ps[] = {&state, &diag, &mesh, &tend, &tend_physics, &configs, &halo_scratch, &dimensions};
+        const char* names[] = {"state", "diag", "mesh", "tend", "tend_physics", "configs", "halo_scratch", "dimensions"};
+        for (int i = 0; i < 8; i++) { ps[i]->name = names[i]; ps[i]->dims = &dims; ps[i]->cfgs = &cfgs; }
+    }
+    Pool* pool(const std::string& n) {
+        if (n == "state") return &state; if (n == "diag") return &diag; if (n == "mesh") return &mesh; if (n == "tend") return &tend;
+        if (n == "tend_physics") return &tend_physics; if (n == "halo_scratch") return &halo_scratch; return nullptr;
+    }
+};
+
+template <class T> static void bind_mod(FArr<T>& a, const PoolEntry& e) {
+    a.p = (T*)e.p[0]; a.rank = e.rank;
+    for (int d = 0; d < 3; d++) { a.lo[d] = 1; a.n[d] = e.n[d]; }
+}
+
+// module variables of atm_time_integration / mpas_atm_dimensions are globals of the generated code: load this block's
+static void activate(RefBlock* b) {
+    nvertlevels = b->dims.at("nVertLevels"); maxedges = b->dims.at("maxEdges"); maxedges2 = b->dims.at("maxEdges2");
+    num_scalars = b->dims.at("num_scalars");
+    config_apply_lbcs = b->cfgs.at("config_apply_lbcs").i != 0;                       // TI:773-775
+    struct { const char* n; FArr<real>* a; } tab[] = {
+        {"tend_ru_physics", &tend_ru_physics}, {"tend_rtheta_physics", &tend_rtheta_physics}, {"tend_rho_physics", &tend_rho_physics},
+        {"qtot", &qtot}, {"delsq_theta", &delsq_theta}, {"delsq_w", &delsq_w}, {"delsq_divergence", &delsq_divergence},
+        {"delsq_u", &delsq_u}, {"delsq_vorticity", &delsq_vorticity}, {"dpdz", &dpdz}, {"horiz_flux_array", &horiz_flux_array},
+        {"scalar_old_arr", &scalar_old_arr}, {"scalar_new_arr", &scalar_new_arr}, {"s_max_arr", &s_max_arr}, {"s_min_arr", &s_min_arr},
+        {"flux_array", &flux_array}, {"flux_upwind_tmp_arr", &flux_upwind_tmp_arr}, {"flux_tmp_arr", &flux_tmp_arr},
+        {"wdtn_arr", &wdtn_arr}, {"rho_zz_int", &rho_zz_int}, {"ke_vertex", &ke_vertex}, {"ke_edge", &ke_edge}};
+    for (auto& t : tab) {
+        auto it = b->module_arrays.find(t.n);
+        if (it == b->module_arrays.end()) { fprintf(stderr, "ref_harness: module array %s not bound\n", t.n); abort(); }
+        bind_mod(*t.a, it->second);
+    }
+    bind_mod(bdymaskedge, b->module_arrays.at("bdyMaskEdge"));
+}
+
+extern "C" {
+void* ref_create(void) { return new RefBlock(); }
+void ref_destroy(void* h) { delete (RefBlock*)h; }
+int ref_real_bytes(void) { return (int)sizeof(real); }
+void ref_set_dim(void* h, const char* name, int v) { ((RefBlock*)h)->dims[name] = v; }
+void ref_set_cfg_real(void* h, const char* name, double v) { CfgVal c; c.kind = 0; c.r = v; ((RefBlock*)h)->cfgs[name] = c; }
+void ref_set_cfg_int(void* h, const char* name, int v) { CfgVal c; c.kind = 1; c.i = v; ((RefBlock*)h)->cfgs[name] = c; }
+void ref_set_cfg_str(void* h, const char* name, const char* v) { CfgVal c; c.kind = 3; c.s = v; ((RefBlock*)h)->cfgs[name] = c; }
+// pool == "module": a module variable of atm_time_integration
+int ref_bind_array(void* h, const char* pool, const char* key, int lev, void* ptr, int is_int, int rank, long n0, long n1, long n2) {
+    RefBlock* b = (RefBlock*)h;
+    std::map<std::string, PoolEntry>* m = nullptr;
+    if (std::string(pool) == "module") m = &b->module_arrays;
+    else { Pool* p = b->pool(pool); if (!p) return 1; m = &p->arrays; }
+    PoolEntry& e = (*m)[key];
+    e.p[lev - 1] = ptr; e.is_int = is_int != 0; e.rank = rank; e.n[0] = n0; e.n[1] = n1; e.n[2] = n2;
+    return 0;
+}
+const char* ref_exchange_log(void* h) { return ((RefBlock*)h)->exchange_log.c_str(); }
+
+// One routine of the step.  ia / ra: the integer and real arguments in the order of the oracle's entry points.
+int ref_call(void* h, const char* routine, const int* ia, const double* ra) {
+    RefBlock* b = (RefBlock*)h;
+    activate(b);
+    const std::string r = routine;
+    const int nCells = b->dims.at("nCells"), nEdges = b->dims.at("nEdges"), nVertices = b->dims.at("nVertices");
+    const int nCellsSolve = b->dims.at("nCellsSolve"), nEdgesSolve = b->dims.at("nEdgesSolve"), nVerticesSolve = b->dims.at("nVerticesSolve");
+    const int nVertLevels = b->dims.at("nVertLevels");
+    // a single block exchanges nothing; the group names the reference asks for are recorded for the test
+    ExchFn xch = [b](const std::string& g) { b->exchange_log += g + ";"; };
+#define CELLS 1, nCells
+#define VERTS 1, nVertices
+#define EDGES 1, nEdges
+#define CELLS_SOLVE 1, nCellsSolve
+#define VERTS_SOLVE 1, nVerticesSolve
+#define EDGES_SOLVE 1, nEdgesSolve
+    if (r == "rk_integration_setup")                          // TI:1083
+        atm_rk_integration_setup(b->state, b->diag, nVertLevels, b->dims.at("num_scalars"), CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "compute_moist_coefficients")               // TI:1102
+        atm_compute_moist_coefficients(b->dimensions, b->state, b->diag, b->mesh, CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "compute_vert_imp_coefs")                   // TI:1117
+        atm_compute_vert_imp_coefs(b->state, b->mesh, b->diag, b->configs, nVertLevels, (real)ra[0], CELLS, EDGES, CELLS_SOLVE, EDGES_SOLVE);
+    else if (r == "compute_dyn_tend")                         // TI:1173
+        atm_compute_dyn_tend(b->tend, b->tend_physics, b->state, b->diag, b->mesh, b->configs, nVertLevels, ia[0], (real)ra[0],
+                             CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "set_smlstep_pert_variables")               // TI:1212
+        atm_set_smlstep_pert_variables(b->tend, b->mesh, CELLS_SOLVE);
+    else if (r == "advance_acoustic_step")                    // TI:1285
+        atm_advance_acoustic_step(b->state, b->diag, b->tend, b->mesh, b->configs, nCells, nVertLevels, (real)ra[0], ia[0],
+                                  CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "divergence_damping_3d")                    // TI:1310
+        atm_divergence_damping_3d(b->state, b->diag, b->mesh, b->configs, (real)ra[0], EDGES);
+    else if (r == "recover_large_step_variables")             // TI:1328
+        atm_recover_large_step_variables(b->state, b->diag, b->tend, b->mesh, b->configs, (real)ra[0], ia[0], ia[1],
+                                         CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "compute_solve_diagnostics")                // TI:1451 (time level 2, rk_step given)
+        atm_compute_solve_diagnostics((real)ra[0], b->state, 2, b->diag, b->mesh, b->configs, CELLS, VERTS, EDGES, Opt<int>(ia[0]));
+    else if (r == "init_solve_diagnostics")                   // mpas_atm_core.F:515-527 (time level 1, no rk_step)
+        atm_compute_solve_diagnostics((real)ra[0], b->state, 1, b->diag, b->mesh, b->configs, CELLS, VERTS, EDGES);
+    else if (r == "init_coupled_diagnostics")                 // mpas_atm_core.F:509
+        atm_init_coupled_diagnostics(b->state, 1, b->diag, b->mesh, b->configs, CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "rk_dynamics_substep_finish")               // TI:1502
+        atm_rk_dynamics_substep_finish(b->state, b->diag, nVertLevels, ia[0], ia[1], CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
+    else if (r == "advance_scalars")                          // advance_scalars, TI:1846: horiz_flux_array, advance_density = config_split_dynamics_transport
+        atm_advance_scalars("scalars", b->tend, b->state, b->diag, b->mesh, b->configs, (real)ra[0], EDGES, CELLS_SOLVE,
+                            horiz_flux_array, ia[0], b->cfgs.at("config_time_integration_order").i,
+                            Opt<bool>(b->cfgs.at("config_split_dynamics_transport").i != 0));
+    else if (r == "advance_scalars_mono")                     // advance_scalars, TI:1897
+        atm_advance_scalars_mono("scalars", b->block, b->tend, b->state, b->diag, b->mesh, b->halo_scratch, b->configs, (real)ra[0],
+                                 CELLS, EDGES, CELLS_SOLVE, scalar_old_arr, scalar_new_arr, s_max_arr, s_min_arr, wdtn_arr,
+                                 flux_array, flux_upwind_tmp_arr, flux_tmp_arr, xch,
+                                 Opt<bool>(b->cfgs.at("config_split_dynamics_transport").i != 0), rho_zz_int);
+    else { fprintf(stderr, "ref_call: unknown routine %s\n", routine); return 1; }
+    return 0;
+}
+}

@@ -40,7 +40,7 @@ def compare_all(ref, test, names=None):
     return out
 
 
-def srk3_stepwise(backends, cfg, dt, after=None):
+def srk3_stepwise(backends, cfg, dt, after=None, reconstruct=True):
     """atm_srk3 (mpas_atm_time_integration.F:803-1725) driven one *_work routine at a
     time on each backend; ``after(label)`` is called after every routine."""
     def call(routine, *args):
@@ -92,6 +92,8 @@ def srk3_stepwise(backends, cfg, dt, after=None):
         rk_t = [dt / 2.0 if cfg["config_time_integration_order"] == 2 else dt / 3.0, dt / 2.0, float(dt)]
         for rk in (1, 2, 3):
             advance_scalars(rk, rk_t[rk - 1])
+    if not reconstruct:
+        return
     for b in backends:                      # TI:1596-1611
         b.mpas_reconstruct(2, False)
     if after:
