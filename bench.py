@@ -97,6 +97,12 @@ KERNEL_MODEL_C = {
     "k:k_dt_cell_f": 22.0,
     "k:k2_dt_edge_flux": 11.0,       # ru (E), w, theta_m read; 2 E written
     "k:k2_recover_cell2": 19.0,      # zb_cell + zb3_cell (12 C), ru (E), rho_zz, w r/w
+    # relaxed-arithmetic path: the column solve as a warp-level scan (same operands as k3_acoustic_cell), the cell-centred
+    # flux sweep (ru: E, w, theta_m read; 2 C written) and the cell tendency without the two per-edge flux arrays
+    "k:k6_acoustic_cell": (9 * 25.0 + 3 * 29.0) / 12,
+    "k:k5_flux_cell": 7.0,
+    "k:k2_dt_cell_f<true>": 14.0,
+    "k:k2_dt_cell_f<false>": 24.0,
 }
 
 

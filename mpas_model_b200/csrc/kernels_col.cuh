@@ -289,11 +289,123 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
     }
 }
 
+// ---- cell-centred flux sweep (relaxed arithmetic): horizontal flux divergence of w and theta_m, TI:5713-5757, 5956-5991 ----
+// One warp per owned cell c.  The reference evaluates, for each of the 6 edges of c, flux_e = ru_e * sum_j (adv_coefs_j
+// +/- adv_coefs_3rd_j) q(cell_j) over the 10-cell stencil of the edge; the stencils of the 6 edges of one cell cover only 19
+// distinct cells (c, its ring n_0..n_5, the second ring m_0..m_11), and on a hexagonal neighbourhood WHICH of them an edge
+// uses is known statically: {c, n_0..n_5, m_{2i-1}, m_{2i}, m_{2i+1}} for edge i (tables built and checked on the host,
+// build_flux_rings in mpasb.cu).  So the 7 inner columns of w and theta_m are loaded once and stay in registers, the outer
+// ring as well, and every stencil sum is register arithmetic: 38 gathered columns per cell
+// instead of 60 (per-edge kernel) or 120 (reference loop nest), and no per-edge flux arrays (12 C less HBM traffic per call).
+// Each edge flux is computed by both adjacent cells, as in the reference.  Arithmetic differs from the strict path only by
+// association: F4 = sum a_j q_j and F3 = sum b_j q_j are accumulated separately with fma() and combined as F4 +/- F3.
+// The 2 x 60 weights of the cell are staged in shared memory by the warp and read back as warp-uniform LDS.128 pairs.
+// Irregular cells (pentagons, heptagons and their neighbours; ~0.2 % of an icosahedral mesh) walk advCellsForEdge.
+#define FX_RING 20                      // ints per cell: n_0..n_5, m_0..m_11, regular flag, pad
+#define FX_WTS 128                      // reals per cell: a[6][10] at 0, b[6][10] at 64
+#define FX_WARPS 4
+#ifndef FX_MINB
+#define FX_MINB 2
+#endif
+__device__ __forceinline__ r2 fma2(real a, r2 q, r2 acc) { return mk2(fma(a, q.x, acc.x), fma(a, q.y, acc.y)); }
+__global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev D) {
+    __shared__ __align__(16) real s_wts[FX_WARPS][FX_WTS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * FX_WARPS + wib;
+    const int LDK = D.LDK, nl = D.nl;
+    if (i >= D.nCellsSolve) return;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const int my_ring = D.fx_ring[(unsigned)i * FX_RING + min(lane, FX_RING - 1)];
+    const int regular = BC(my_ring, 18);
+    r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
+    if (regular) {
+        const int le = min(lane, 5);
+        const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+        const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+        {   // stage the weights: FX_WTS reals per cell = 4 per lane
+            const real* __restrict__ src = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
+            const r2 a = *reinterpret_cast<const r2*>(src), b = *reinterpret_cast<const r2*>(src + 2);
+            *reinterpret_cast<r2*>(&s_wts[wib][4 * lane]) = a; *reinterpret_cast<r2*>(&s_wts[wib][4 * lane + 2]) = b;
+        }
+        // all 19 columns of both fields and the 6 edge columns are requested before any of them is used: one exposed memory
+        // latency per cell (the kernel runs at 2 blocks x 4 warps per SM with ~230 registers per thread for exactly this)
+        const r2 wc = LD(D.w_2, i), tc = LD(D.theta_m_2, i);
+        r2 wn[6], tn[6], wm[12], tm[12], ru6[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) { const int c = BC(my_ring, q); wn[q] = LD(D.w_2, c); tn[q] = LD(D.theta_m_2, c); }
+#pragma unroll
+        for (int q = 0; q < 12; q++) { const int c = BC(my_ring, 6 + q); wm[q] = LD(D.w_2, c); tm[q] = LD(D.theta_m_2, c); }
+#pragma unroll
+        for (int q = 0; q < 6; q++) ru6[q] = LD(D.ru, BC(my_e, q));
+        __syncwarp();
+        const real* __restrict__ W = s_wts[wib];
+#pragma unroll
+        for (int e = 0; e < 6; e++) {
+            const r2 wa = wm[(2 * e + 11) % 12], ta = tm[(2 * e + 11) % 12], wb = wm[2 * e], tb = tm[2 * e],
+                     wd = wm[(2 * e + 1) % 12], td = tm[(2 * e + 1) % 12];
+            const r2 ruk = ru6[e];
+            const real sg = BC(my_sgn, e);
+            const real* __restrict__ A = W + e * 10;
+            const real* __restrict__ B = W + FX_WTS / 2 + e * 10;
+            const r2 a01 = *reinterpret_cast<const r2*>(A), a23 = *reinterpret_cast<const r2*>(A + 2), a45 = *reinterpret_cast<const r2*>(A + 4),
+                     a67 = *reinterpret_cast<const r2*>(A + 6), a89 = *reinterpret_cast<const r2*>(A + 8);
+            const r2 b01 = *reinterpret_cast<const r2*>(B), b23 = *reinterpret_cast<const r2*>(B + 2), b45 = *reinterpret_cast<const r2*>(B + 4),
+                     b67 = *reinterpret_cast<const r2*>(B + 6), b89 = *reinterpret_cast<const r2*>(B + 8);
+            r2 f4w = wc * a01.x, f3w = wc * b01.x, f4t = tc * a01.x, f3t = tc * b01.x;
+#define FX_TERM(AW, BW, QW, QT) { f4w = fma2((AW), (QW), f4w); f3w = fma2((BW), (QW), f3w); f4t = fma2((AW), (QT), f4t); f3t = fma2((BW), (QT), f3t); }
+            FX_TERM(a01.y, b01.y, wn[0], tn[0]) FX_TERM(a23.x, b23.x, wn[1], tn[1]) FX_TERM(a23.y, b23.y, wn[2], tn[2])
+            FX_TERM(a45.x, b45.x, wn[3], tn[3]) FX_TERM(a45.y, b45.y, wn[4], tn[4]) FX_TERM(a67.x, b67.x, wn[5], tn[5])
+            FX_TERM(a67.y, b67.y, wa, ta) FX_TERM(a89.x, b89.x, wb, tb) FX_TERM(a89.y, b89.y, wd, td)
+#undef FX_TERM
+            const r2 ruw = fm * ruk + fp * up1(ruk);               // ru at w levels
+            const b2 pw = nonneg_sign(ruw), pt = nonneg_sign(ruk);
+            const r2 fxw = ruw * sel(pw, f4w + f3w, f4w - f3w);
+            const r2 fxt = ruk * sel(pt, f4t + f3t, f4t - f3t);
+            tw = tw - sg * fxw;
+            tt = tt - sg * fxt;
+        }
+    } else {
+        // the reference's loop nest over the edges of the cell and their advCellsForEdge lists
+        const int ne = D.nEdgesOnCell[i];
+        for (int e = 0; e < ne; e++) {
+            const int iEdge = D.edgesOnCell[(unsigned)i * D.maxEdges + e];
+            const real sg = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + e];
+            const int nadv = D.nAdvCellsForEdge[iEdge];
+            int my_c = 0; real my_a = 0.0, my_b = 0.0;
+            if (lane < nadv) {
+                my_c = D.advCellsForEdge[(unsigned)iEdge * 15 + lane];
+                my_a = D.adv_coefs[(unsigned)iEdge * 15 + lane]; my_b = D.adv_coefs_3rd[(unsigned)iEdge * 15 + lane];
+            }
+            const r2 ruk = LD(D.ru, iEdge);
+            const r2 ruw = fm * ruk + fp * up1(ruk);
+            r2 f4w = mk2(0.0, 0.0), f3w = f4w, f4t = f4w, f3t = f4w;
+            for (int j = 0; j < nadv; j++) {
+                const int c = BC(my_c, j);
+                const real a = BC(my_a, j), b = BC(my_b, j);
+                const r2 w2 = LD(D.w_2, c), t2 = LD(D.theta_m_2, c);
+                f4w = fma2(a, w2, f4w); f3w = fma2(b, w2, f3w); f4t = fma2(a, t2, f4t); f3t = fma2(b, t2, f3t);
+            }
+            const b2 pw = nonneg_sign(ruw), pt = nonneg_sign(ruk);
+            tw = tw - sg * (ruw * sel(pw, f4w + f3w, f4w - f3w));
+            tt = tt - sg * (ruk * sel(pt, f4t + f3t, f4t - f3t));
+        }
+    }
+    ST(D.hdiv_w, i, sel(k_mid, tw, 0.0));
+    ST(D.hdiv_theta, i, sel(k_lt_nl, tt, 0.0));
+}
+
 // owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
 // Restrictions (the host falls back to k_dt_cell_f otherwise): v_mom_eddy_visc2 == v_theta_eddy_visc2 == 0.
 #ifndef CELLF_MINB
 #define CELLF_MINB 3
 #endif
+// HDIV: the horizontal flux divergences come ready-made from k5_flux_cell (relaxed arithmetic) instead of being summed
+// here from the per-edge fluxes of k2_dt_edge_flux
+template <bool HDIV>
 __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
@@ -317,9 +429,12 @@ __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev
         tw = selb((E) < ne, tw - sg * fxw, tw);                                                             \
         tt = selb((E) < ne, tt - sg * fxt, tt);                                                             \
     }
+    if (HDIV) { tw = LD(D.hdiv_w, i); tt = LD(D.hdiv_theta, i); }
+    else {
 #pragma unroll
-    for (int e = 0; e < CW_NE; e++) CELL_F_EDGE(e)
-    for (int e = CW_NE; e < ne; e++) CELL_F_EDGE(e)
+        for (int e = 0; e < CW_NE; e++) CELL_F_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) CELL_F_EDGE(e)
+    }
 #undef CELL_F_EDGE
     r2 twe = LD(D.tend_w_euler, i), tte = LD(D.tend_theta_euler, i);
     const r2 twe_in = twe;
@@ -921,6 +1036,129 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
         ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1
                                                       - coftz * r), 0.0));
     }
+}
+
+// ---- the same routine with the column solve done by the warp that owns the column (relaxed arithmetic) ----
+// The two sweeps of TI:2922-2930 are first-order linear recurrences, x_k = A_k x_{k-1} + B_k with A_k = -a_k alpha_k,
+// B_k = rhs_k alpha_k, and y_k = G_k y_{k+1} + x_k with G_k = -gamma_k.  Affine maps compose associatively, so each is a
+// parallel prefix over the levels: every lane composes its own level pair, five shuffle steps combine the 32 lanes, one more
+// shuffle hands each lane its neighbour's end value.  One warp then carries a column from its gathers to its stores with
+// everything in registers: no shared-memory tiles, no block-wide barriers between the phases, no operand read twice
+// (k3_acoustic_cell re-reads coftz, zz, rw_p, rtheta_pp after the solve), and occupancy is set by registers alone.
+// |A_k|, |G_k| < 1 (the system is diagonally dominant), so the re-associated products are as well conditioned as the serial
+// sweep; results agree with it to rounding (tests: TOL_ROUTINE_FAST per routine, 1e-11 per step).
+#ifndef AC6_MINB
+#define AC6_MINB 2
+#endif
+struct aff { real a, b; };          // x -> a * x + b
+__device__ __forceinline__ aff aff_after(aff later, aff earlier) { aff r; r.a = later.a * earlier.a; r.b = fma(later.a, earlier.b, later.b); return r; }
+__global__ void __launch_bounds__(CW_THREADS, AC6_MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    CW_SETUP(D.nCells)
+    const bool first = small_step == 1;
+    const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
+    r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
+    if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
+    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); return; }          // halo cells: TI:2827-2842 only
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    const bool my_is1 = my_c1 == i, my_is2 = my_c2 == i;
+    const int my_oth = my_is1 ? my_c2 : my_c1;
+    const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
+    const real invArea = D.invAreaCell[i];
+    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    if (!first) {
+        rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
+        rho_pp = sel(k_lt_nl, LD(D.rho_pp, i), 0.0);
+        wwAvg = sel(k_le_nl, LD(D.wwAvg, i), 0.0);
+    }
+    const r2 tend_rho = LD(D.tend_rho, i), tend_theta = LD(D.tend_theta, i), tend_w = LD(D.tend_w, i);
+    const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
+    const r2 zz = LD(D.zz, i);
+    const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
+    const r2 th_own = LD(D.theta_m, i);
+    r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
+#define AC6_EDGE(E)                                                                                         \
+    {                                                                                                       \
+        const int iEdge = BC(my_e, (E));                                                                    \
+        const bool is1 = BC(my_is1, (E)), is2 = BC(my_is2, (E));                                            \
+        const r2 th_o = LD(D.theta_m, BC(my_oth, (E)));                                                     \
+        const r2 ru_p = first ? dts * LD(D.tend_u, iEdge) : LD(D.ru_p, iEdge);   /* TI:2798-2806 */         \
+        const r2 flux = BC(my_f, (E)) * ru_p * invArea;                                                     \
+        const r2 th = selb(is2, th_own, th_o) + selb(is1, th_own, th_o);                                    \
+        rs = selb((E) < ne, rs - flux, rs);                                                                 \
+        ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                      \
+    }
+#pragma unroll
+    for (int e = 0; e < CW_NE; e++) AC6_EDGE(e)
+    for (int e = CW_NE; e < ne; e++) AC6_EDGE(e)
+#undef AC6_EDGE
+    // operands of the part after the solve: issued here so that they are in flight during the solve
+    const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const r2 rw_p1 = dn1(rw_p);
+    const r2 coftz1 = dn1(coftz);
+    rs = rho_pp + dts * tend_rho + rs - cofrz * resm * (rw_p1 - rw_p);
+    ts = rtheta_pp + dts * tend_theta + ts - resm * rdzw * (coftz1 * rw_p1 - coftz * rw_p);
+    rs = sel(k_lt_nl, rs, 0.0); ts = sel(k_lt_nl, ts, 0.0);
+    const r2 zzm = up1(zz);
+    const r2 tsm = up1(ts), rsm = up1(rs), rtm = up1(rtheta_pp), rhm = up1(rho_pp), cofwtm = up1(cofwt);
+    const r2 rr = rw_p + dts * tend_w
+                  - cofwz * ((zz * ts - zzm * tsm) + resm * (zz * rtheta_pp - zzm * rtm))
+                  - cofwr * ((rs + rsm) + resm * (rho_pp + rhm))
+                  + cofwt * (ts + resm * rtheta_pp)
+                  + cofwtm * (tsm + resm * rtm);
+    const r2 rhs = sel(k_le_nl, sel(k_mid, rr, rw_p), 0.0);
+    // ---- forward sweep: x_k = alpha_k (rhs_k - a_k x_{k-1}), k = 1 .. nl-1; x_0 = rhs_0, x_nl = rhs_nl
+    r2 x;
+    {
+        aff m0, m1;
+        m0.a = k_mid.x ? -(a_tri.x * al_tri.x) : (real)0.0; m0.b = k_mid.x ? rhs.x * al_tri.x : rhs.x;
+        m1.a = k_mid.y ? -(a_tri.y * al_tri.y) : (real)0.0; m1.b = k_mid.y ? rhs.y * al_tri.y : rhs.y;
+        aff m = aff_after(m1, m0);                              // x_{k0-1} -> x_{k0+1}
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            aff p; p.a = __shfl_up_sync(CW_FULL, m.a, d); p.b = __shfl_up_sync(CW_FULL, m.b, d);
+            if (lane >= d) m = aff_after(m, p);
+        }
+        real xprev = __shfl_up_sync(CW_FULL, m.b, 1);           // x_{k0-1}: the previous lane's upper level (lane 0: m0.a == 0)
+        if (lane == 0) xprev = 0.0;
+        x.x = fma(m0.a, xprev, m0.b);
+        x.y = m.b;
+    }
+    // ---- backward sweep: y_k = x_k - gamma_k y_{k+1}, k = nl-1 .. 0; y_nl = x_nl
+    r2 r;
+    {
+        aff m0, m1;
+        m0.a = k_lt_nl.x ? -ga_tri.x : (real)0.0; m0.b = x.x;
+        m1.a = k_lt_nl.y ? -ga_tri.y : (real)0.0; m1.b = x.y;
+        aff m = aff_after(m0, m1);                              // y_{k0+2} -> y_{k0}
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            aff p; p.a = __shfl_down_sync(CW_FULL, m.a, d); p.b = __shfl_down_sync(CW_FULL, m.b, d);
+            if (lane + d < 32) m = aff_after(m, p);
+        }
+        real ynext = __shfl_down_sync(CW_FULL, m.b, 1);         // y_{k0+2}
+        if (lane == 31) ynext = 0.0;
+        r.x = m.b;
+        r.y = fma(m1.a, ynext, m1.b);
+    }
+    // ---- damping, averages, back-substitution of rho_pp and rtheta_pp (TI:2936-2959)
+    wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 - epssm) * rw_p, wwAvg);
+    {
+        const r2 dw = rw_save - rw_now;
+        const r2 rd = (r + dw - dts * dss * (fm * zz + fp * zzm) * (fm * rho + fp * up1(rho)) * w_now) / (1.0 + dts * dss) - dw;
+        r = sel(k_mid, rd, r);
+        wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 + epssm) * r, wwAvg);
+    }
+    r = sel(k_le_nl, r, 0.0);
+    const r2 r1 = dn1(r);
+    ST(D.rtheta_pp_old, i, rtheta_pp);
+    ST(D.rw_p, i, r);
+    ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
+    ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
+    ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1 - coftz * r), 0.0));
 }
 
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075

@@ -40,6 +40,10 @@ struct Dev {
     int* zb_any;
     // per-edge 3rd/4th-order advective fluxes of w and theta_m (kernels_col.cuh: k2_dt_edge_flux -> k2_dt_cell_f)
     real* adv_flux_w; real* adv_flux_theta;
+    // cell-centred flux sweep of the relaxed-arithmetic path (kernels_col.cuh: k5_flux_cell -> k2_dt_cell_f): per owned cell
+    // the 18 cells of its two rings in canonical order + a regularity flag, the 2 x 60 stencil weights of its 6 edges in
+    // canonical slot order, and the horizontal flux divergences of w and theta_m it produces
+    int* fx_ring; real* fx_w; real* hdiv_w; real* hdiv_theta;
 };
 #undef F
 #undef FIELD_REAL

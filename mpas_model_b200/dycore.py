@@ -161,6 +161,7 @@ class Dycore(Backend):
         self.config = make_config(cfg, block)
         self.cfg = dict(cfg)
         self._h = C.c_void_p()
+        self._strict = bool(self.lib.mpasb_strict_arithmetic())      # MPASB_STRICT is read when the handle is created
         rc = self.lib.mpasb_create(C.byref(self.dims), C.byref(self.config), C.c_int(device), C.byref(self._h))
         if rc != 0:
             raise RuntimeError(f"mpasb_create failed ({rc}): no usable CUDA device or bad dimensions")
@@ -298,8 +299,9 @@ class Dycore(Backend):
         return ms.value
 
     def strict_arithmetic(self) -> bool:
-        """True if the library keeps the reference's operation order everywhere (bit-exact build)."""
-        return bool(self.lib.mpasb_strict_arithmetic())
+        """True if this handle keeps the reference's operation order everywhere (MPASB_STRICT=1 at creation: results are
+        bit-identical to the fp64 CPU arithmetic); False for the default, relaxed mode (re-associated stencil sums)."""
+        return self._strict
 
     def kernel_launch_count(self):
         return int(self.lib.mpasb_kernel_launch_count(self._h))

@@ -54,28 +54,58 @@ def _struct_members(text, name):
 
 
 def test_bindings_agree_with_the_header():
-    """The three descriptions of the boundary name the same things in the same order: include/mpasb.h, the ctypes
-    mirror (dycore.Dims / dycore.Config) and the Fortran ISO_C_BINDING block of INTEGRATION.md."""
+    """The descriptions of the boundary name the same things in the same order: include/mpasb.h, the ctypes mirror
+    (dycore.Dims / dycore.Config) and the committed Fortran shim (fortran/mpasb_binding.F90: ISO_C_BINDING interface of
+    EVERY exported symbol; fortran/mpas_atm_dynamics_b200.F: the replacement bodies of mpas_atm_dynamics_init /
+    _finalize / atm_timestep with every upload and download spelled out)."""
     from mpas_model_b200 import dycore
+    from mpas_model_b200.fields import FIELDS
     with open(os.path.join(ROOT, "include", "mpasb.h")) as f:
         header = f.read()
-    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
-        integ = f.read()
+    with open(os.path.join(ROOT, "fortran", "mpasb_binding.F90")) as f:
+        binding = f.read()
+    with open(os.path.join(ROOT, "fortran", "mpas_atm_dynamics_b200.F")) as f:
+        shim = f.read()
     dims, cfg = _struct_members(header, "mpasb_dims"), _struct_members(header, "mpasb_config")
     assert [n for n, _ in dycore.Dims._fields_] == dims
     assert [n for n, _ in dycore.Config._fields_] == cfg
     # Fortran derived types: same members, same order
     for tname, members in (("mpasb_dims", dims), ("mpasb_config", cfg)):
-        body = re.search(r"type, bind\(C\) :: " + tname + r"(.*?)end type", integ, re.S).group(1)
+        body = re.search(r"type, bind\(C\) :: " + tname + r"(.*?)end type", binding, re.S).group(1)
         body = re.sub(r"!.*", "", body)
         f_members = []
         for line in body.splitlines():
             if "::" in line:
                 f_members += [m.strip() for m in line.split("::", 1)[1].split(",") if m.strip()]
         assert f_members == members, tname
-    # every bound symbol exists in the header
-    bound = set(re.findall(r"bind\(C, name='(mpasb_[a-z_0-9]+)'\)", integ))
-    assert len(bound) >= 15 and bound <= set(_declared()), bound - set(_declared())
-    # and the symbols the replacement bodies call are bound or declared
-    used = set(re.findall(r"\b(mpasb_[a-z_0-9]+)\(", integ))
-    assert used <= set(_declared()) | {"mpasb_binding"}, used - set(_declared())
+    # every exported symbol is bound, nothing is bound that the header does not declare
+    bound = set(re.findall(r"bind\(C, name='(mpasb_[a-z_0-9]+)'\)", binding))
+    assert bound == set(_declared()), bound ^ set(_declared())
+    # both RKIND widths
+    assert "#ifdef SINGLE_PRECISION" in binding and "c_float" in binding and "c_double" in binding
+    # the replacement bodies only call bound symbols, keep the reference's entry-point names ...
+    used = set(re.findall(r"\b(mpasb_[a-z_0-9]+)\(", shim)) - {"mpasb_check", "mpasb_upload_state", "mpasb_download_for_output", "mpasb_c_to_f"}
+    assert used <= bound, used - bound
+    for name in ("subroutine mpas_atm_dynamics_init(domain)", "subroutine mpas_atm_dynamics_finalize(domain)",
+                 "subroutine atm_timestep(domain, dt, nowTime, itimestep, exchange_halo_group)"):
+        assert name in shim, name
+    # ... and spell out an upload for every mesh field of the table and for the prognostic state
+    uploaded = set(re.findall(r"call put_[ri]\d\(\w+, '(\w+)'", shim))
+    mesh_start = open(os.path.join(ROOT, "include", "mpasb_fields.def")).read().index("/* ---- mesh, real ---- */")
+    mesh_keys = set(re.findall(r"^F\((\w+),", open(os.path.join(ROOT, "include", "mpasb_fields.def")).read()[mesh_start:], re.M))
+    assert mesh_keys <= uploaded, mesh_keys - uploaded
+    assert {"u", "w", "rho_zz", "theta_m", "scalars", "ru", "rw", "rtheta_p", "rho_p", "exner", "pressure_p"} <= uploaded
+    downloaded = set(re.findall(r"call get_r\d\(\w+, '(\w+)'", shim))
+    assert {"u", "w", "rho_zz", "theta_m", "scalars", "uReconstructZonal", "theta", "pressure"} <= downloaded
+    assert (uploaded | downloaded) <= set(FIELDS), (uploaded | downloaded) - set(FIELDS)
+
+
+def test_fortran_shim_is_generated_from_the_header_and_the_field_table():
+    """fortran/*.F* are the output of tools/gen_fortran_shim.py: regenerating them changes nothing."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_fortran_shim", os.path.join(ROOT, "tools", "gen_fortran_shim.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    for name, text in {"mpasb_binding.F90": gen.wrap(gen.binding()), "mpas_atm_dynamics_b200.F": gen.wrap(gen.dynamics())}.items():
+        with open(os.path.join(ROOT, "fortran", name)) as f:
+            assert f.read() == text, name
