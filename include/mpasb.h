@@ -80,10 +80,25 @@ int  mpasb_set_field(mpasb_handle h, const char* name, int time_level, const mpa
 int  mpasb_get_field(mpasb_handle h, const char* name, int time_level, mpasb_real* dst, long count);
 int  mpasb_set_field_int(mpasb_handle h, const char* name, const int* src, long count);
 int  mpasb_field_count(mpasb_handle h, const char* name, long* count);   /* dense host element count */
+/* The same for a whole batch of real fields without stalling the host: all host->device (device->host) copies of a batch go
+ * back to back on a copy stream of their own, ordered against the compute stream by events, so that the upload of the next
+ * request, the step, and the download of the previous request overlap (PCIe is full duplex).  Host arrays should be pinned.
+ * Upload: the host arrays may be reused after mpasb_wait_uploads; download: they are valid after mpasb_wait_downloads.
+ * Device-side order is call order: set_fields_async; step; get_fields_async moves one request through. */
+int  mpasb_set_fields_async(mpasb_handle h, int n, const char* const* names, const int* time_levels, const mpasb_real* const* src, const long* counts);
+int  mpasb_get_fields_async(mpasb_handle h, int n, const char* const* names, const int* time_levels, mpasb_real* const* dst, const long* counts);
+int  mpasb_wait_uploads(mpasb_handle h);
+int  mpasb_wait_downloads(mpasb_handle h);
+/* ... all but the last `lag` batches (0 <= lag < 4): lets a host keep `lag` requests in flight */
+int  mpasb_wait_uploads_lag(mpasb_handle h, int lag);
+int  mpasb_wait_downloads_lag(mpasb_handle h, int lag);
 
 /* atm_srk3 (TI:803-1725): advance state level 1 -> level 2 by dt.  Followed by
  * mpasb_shift_time_levels == mpas_pool_shift_time_levels(state) (mpas_atm_core.F:808). */
 int  mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep);
+/* The physics tendencies tend_ru_physics, tend_rtheta_physics, tend_rho_physics (filled by physics_get_tend inside atm_srk3 in
+ * the reference, TI:1091-1093) are zero after mpasb_create and keep what mpasb_set_field uploads until this call. */
+int  mpasb_zero_physics_tendencies(mpasb_handle h);
 int  mpasb_shift_time_levels(mpasb_handle h);
 /* summarize_timestep (TI:7914-8357): out = {min w, max w, min u, max u} of level 2,
  * reductions start from 0 as in TI:8291-8292. */
@@ -101,6 +116,7 @@ int  mpasb_synchronize(mpasb_handle h);
  * atm_compute_solve_diagnostics without rk_step (mpas_atm_core.F:515-527). */
 int  mpasb_init_coupled_diagnostics(mpasb_handle h);
 int  mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt);
+int  mpasb_init_solve_diagnostics_async(mpasb_handle h, mpasb_real dt);   /* enqueued only: no host synchronisation */
 
 /* mpas_reconstruct (src/operators/mpas_vector_reconstruction.F:205-330): uReconstructX/Y/Z/Zonal/Meridional from u of
  * the given time level through the init-time field coeffs_reconstruct; mpasb_step already ends with the call of
@@ -151,8 +167,9 @@ int  mpasb_p2p_prepare(mpasb_handle h, long slot_elems, void* out_handles128);
 int  mpasb_p2p_open(mpasb_handle h, const void* all_handles);
 int  mpasb_p2p_enable(mpasb_handle h, int on);
 
-/* 1 if every kernel keeps the reference's operation order without FMA contraction (results bit-identical to
- * the fp64 CPU arithmetic; the only build at present), 0 for a relaxed build */
+/* 1 (MPASB_STRICT=1 in the environment): handles created from now on keep the reference's operation order everywhere, nothing
+ * contracted into FMAs: results bit-identical to the fp64 CPU arithmetic.  0 (default): the relaxed path (re-associated
+ * stencil sums, explicit fma, scan-based column solve) within the parity bars (rel-L2 <= 1e-11 after one step). */
 int  mpasb_strict_arithmetic(void);
 int  mpasb_real_bytes(void);     /* sizeof(mpasb_real) of this build: 8 (libmpasb.so) or 4 (libmpasb_sp.so) */
 

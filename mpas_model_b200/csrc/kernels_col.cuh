@@ -115,14 +115,19 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
     return flux4_2(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * abs2(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;
 }
 
+// One warp per column, walking columns g, g + G, g + 2G, ... (G = warps of the grid): launched with one warp per column the
+// loop runs once; launched with just the resident blocks (persistent warps, mpasb.cu: LAUNCHW) every warp also asks L2 for the
+// own-column operands of its NEXT column (CW_PF lists, cw_pf / cw_next) while it works on the current one.
 #define CW_SETUP(ncols)                                                                       \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
-    const int i = blockIdx.x * CW_WARPS + wib;                                                \
     const int LDK = D.LDK, nl = D.nl;                                                         \
-    if (i >= (ncols)) return;                                                                 \
     Lv lv; lv.k0 = 2 * lane;                                                                  \
     const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;                             \
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);                  \
+    const int cw_stride = gridDim.x * CW_WARPS, cw_n = (ncols);                               \
+    for (int i = blockIdx.x * CW_WARPS + wib; i < cw_n; i += cw_stride) {                     \
+        const int cw_next = i + cw_stride; const bool cw_pf = D.pf_next && cw_next < cw_n; (void)cw_next; (void)cw_pf;
+#define CW_END }
 #define LD(p, col) ld2((p), (unsigned)(col) * uLDK + kc)
 #define ST(p, col, v) st2((p), (unsigned)(col) * uLDK + kc, act, (v))
 #define BC(v, src) __shfl_sync(CW_FULL, (v), (src))
@@ -142,7 +147,7 @@ __device__ __forceinline__ void pf2(const real* p, unsigned off) { asm volatile(
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;           // only edges of owned cells are consumed
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;           // only edges of owned cells are consumed
     const int nadv = D.nAdvCellsForEdge[i];
     // one stencil entry per lane: cell index and the two possible weights adv_coefs +/- adv_coefs_3rd
     // (TI:5744-5750: coef + sign(ru) * coef_3rd with sign = +/-1)
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
     }
     ST(D.adv_flux_w, i, sel(lv.ge(1) && lv.lt(nl), ruw * fw, 0.0));
     ST(D.adv_flux_theta, i, sel(lv.lt(nl), ruk * ft, 0.0));
+    CW_END
 }
 
 // ---- the same per-edge flux with the stencil columns staged in shared memory by bulk copies (TMA) ----
@@ -311,28 +317,33 @@ __device__ __forceinline__ r2 fma2(real a, r2 q, r2 acc) { return mk2(fma(a, q.x
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev D) {
     __shared__ __align__(16) real s_wts[FX_WARPS][FX_WTS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * FX_WARPS + wib;
     const int LDK = D.LDK, nl = D.nl;
-    if (i >= D.nCellsSolve) return;
     Lv lv; lv.k0 = 2 * lane;
     const int k0 = lv.k0; const bool act = k0 < D.LDKA;
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
-    const int my_ring = D.fx_ring[(unsigned)i * FX_RING + min(lane, FX_RING - 1)];
+    // Persistent warps: warp g handles cells g, g + G, g + 2G, ...  The kernel is latency bound (two dependent memory round
+    // trips per cell: neighbourhood table -> columns), so the table row, the edge ids and the signs of the NEXT cell are
+    // fetched while the current cell's columns are in flight: one exposed round trip per cell instead of two.
+    const int G = gridDim.x * FX_WARPS;
+    const int le = min(lane, 5), lr = min(lane, FX_RING - 1);
+    int i = blockIdx.x * FX_WARPS + wib;
+    int my_ring = 0, my_e = 0; real my_sgn = 0.0;
+    if (i < D.nCellsSolve) {
+        my_ring = D.fx_ring[(unsigned)i * FX_RING + lr];
+        my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+        my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    }
+    for (; i < D.nCellsSolve; i += G) {
     const int regular = BC(my_ring, 18);
     r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
+    const int inext = i + G;
+    int nx_ring = 0, nx_e = 0; real nx_sgn = 0.0;
     if (regular) {
-        const int le = min(lane, 5);
-        const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
-        const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
-        {   // stage the weights: FX_WTS reals per cell = 4 per lane
-            const real* __restrict__ src = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
-            const r2 a = *reinterpret_cast<const r2*>(src), b = *reinterpret_cast<const r2*>(src + 2);
-            *reinterpret_cast<r2*>(&s_wts[wib][4 * lane]) = a; *reinterpret_cast<r2*>(&s_wts[wib][4 * lane + 2]) = b;
-        }
-        // all 19 columns of both fields and the 6 edge columns are requested before any of them is used: one exposed memory
-        // latency per cell (the kernel runs at 2 blocks x 4 warps per SM with ~230 registers per thread for exactly this)
+        const real* __restrict__ wsrc = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
+        const r2 wts_a = *reinterpret_cast<const r2*>(wsrc), wts_b = *reinterpret_cast<const r2*>(wsrc + 2);
+        // all 19 columns of both fields and the 6 edge columns are requested before any of them is used
         const r2 wc = LD(D.w_2, i), tc = LD(D.theta_m_2, i);
         r2 wn[6], tn[6], wm[12], tm[12], ru6[6];
 #pragma unroll
@@ -341,6 +352,13 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
         for (int q = 0; q < 12; q++) { const int c = BC(my_ring, 6 + q); wm[q] = LD(D.w_2, c); tm[q] = LD(D.theta_m_2, c); }
 #pragma unroll
         for (int q = 0; q < 6; q++) ru6[q] = LD(D.ru, BC(my_e, q));
+        if (inext < D.nCellsSolve) {                    // next cell's table row, edges, signs: in flight with the columns
+            nx_ring = D.fx_ring[(unsigned)inext * FX_RING + lr];
+            nx_e = D.edgesOnCell[(unsigned)inext * D.maxEdges + le];
+            nx_sgn = D.edgesOnCell_sign[(unsigned)inext * D.maxEdges + le];
+        }
+        __syncwarp();                                    // the previous cell's reads of s_wts are done
+        *reinterpret_cast<r2*>(&s_wts[wib][4 * lane]) = wts_a; *reinterpret_cast<r2*>(&s_wts[wib][4 * lane + 2]) = wts_b;
         __syncwarp();
         const real* __restrict__ W = s_wts[wib];
 #pragma unroll
@@ -369,6 +387,11 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
             tt = tt - sg * fxt;
         }
     } else {
+        if (inext < D.nCellsSolve) {
+            nx_ring = D.fx_ring[(unsigned)inext * FX_RING + lr];
+            nx_e = D.edgesOnCell[(unsigned)inext * D.maxEdges + le];
+            nx_sgn = D.edgesOnCell_sign[(unsigned)inext * D.maxEdges + le];
+        }
         // the reference's loop nest over the edges of the cell and their advCellsForEdge lists
         const int ne = D.nEdgesOnCell[i];
         for (int e = 0; e < ne; e++) {
@@ -396,6 +419,96 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
     }
     ST(D.hdiv_w, i, sel(k_mid, tw, 0.0));
     ST(D.hdiv_theta, i, sel(k_lt_nl, tt, 0.0));
+    my_ring = nx_ring; my_e = nx_e; my_sgn = nx_sgn;
+    }
+}
+
+// ---- the same sweep with ONE FIELD PER WARP (warp 2c: w of cell c, warp 2c + 1: theta_m): half the registers per thread, twice
+// the resident warps.  k5_flux_cell holds both fields' 19 columns (248 registers, 8 warps per SM) and is bound by the
+// latency of its own instruction stream at 1.8 warps per scheduler (ncu: issue slots 32 % busy, L1 data pipe 50 %, DRAM 16 %).
+#ifndef FX1_MINB
+#define FX1_MINB 2
+#endif
+__global__ void __launch_bounds__(CW_THREADS, FX1_MINB) k5s_flux_cell(const Dev D) {
+    __shared__ __align__(16) real s_wts[CW_WARPS][FX_WTS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * CW_WARPS + wib;
+    const int i = g >> 1, field = g & 1;
+    const int LDK = D.LDK, nl = D.nl;
+    if (i >= D.nCellsSolve) return;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
+    const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
+    const real* __restrict__ Q = field ? D.theta_m_2 : D.w_2;
+    real* OUT = field ? D.hdiv_theta : D.hdiv_w;
+    const int my_ring = D.fx_ring[(unsigned)i * FX_RING + min(lane, FX_RING - 1)];
+    const int regular = BC(my_ring, 18);
+    r2 acc = mk2(0.0, 0.0);
+    if (regular) {
+        const int le = min(lane, 5);
+        const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+        const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+        const real* __restrict__ wsrc = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
+        const r2 wts_a = *reinterpret_cast<const r2*>(wsrc), wts_b = *reinterpret_cast<const r2*>(wsrc + 2);
+        const r2 qc = LD(Q, i);
+        r2 qn[6], qm[12], ru6[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) qn[q] = LD(Q, BC(my_ring, q));
+#pragma unroll
+        for (int q = 0; q < 12; q++) qm[q] = LD(Q, BC(my_ring, 6 + q));
+#pragma unroll
+        for (int q = 0; q < 6; q++) ru6[q] = LD(D.ru, BC(my_e, q));
+        *reinterpret_cast<r2*>(&s_wts[wib][4 * lane]) = wts_a; *reinterpret_cast<r2*>(&s_wts[wib][4 * lane + 2]) = wts_b;
+        __syncwarp();
+        const real* __restrict__ W = s_wts[wib];
+        r2 fm = mk2(1.0, 1.0), fp = mk2(0.0, 0.0);
+        if (!field) { fm = LD(D.fzm, 0); fp = LD(D.fzp, 0); }
+#pragma unroll
+        for (int e = 0; e < 6; e++) {
+            const r2 qa = qm[(2 * e + 11) % 12], qb = qm[2 * e], qd = qm[(2 * e + 1) % 12];
+            const real sg = BC(my_sgn, e);
+            const real* __restrict__ A = W + e * 10;
+            const real* __restrict__ B = W + FX_WTS / 2 + e * 10;
+            const r2 a01 = *reinterpret_cast<const r2*>(A), a23 = *reinterpret_cast<const r2*>(A + 2), a45 = *reinterpret_cast<const r2*>(A + 4),
+                     a67 = *reinterpret_cast<const r2*>(A + 6), a89 = *reinterpret_cast<const r2*>(A + 8);
+            const r2 b01 = *reinterpret_cast<const r2*>(B), b23 = *reinterpret_cast<const r2*>(B + 2), b45 = *reinterpret_cast<const r2*>(B + 4),
+                     b67 = *reinterpret_cast<const r2*>(B + 6), b89 = *reinterpret_cast<const r2*>(B + 8);
+            r2 f4 = qc * a01.x, f3 = qc * b01.x;
+#define FX1_TERM(AW, BW, QQ) { f4 = fma2((AW), (QQ), f4); f3 = fma2((BW), (QQ), f3); }
+            FX1_TERM(a01.y, b01.y, qn[0]) FX1_TERM(a23.x, b23.x, qn[1]) FX1_TERM(a23.y, b23.y, qn[2])
+            FX1_TERM(a45.x, b45.x, qn[3]) FX1_TERM(a45.y, b45.y, qn[4]) FX1_TERM(a67.x, b67.x, qn[5])
+            FX1_TERM(a67.y, b67.y, qa) FX1_TERM(a89.x, b89.x, qb) FX1_TERM(a89.y, b89.y, qd)
+#undef FX1_TERM
+            const r2 ruk = ru6[e];
+            const r2 rue = field ? ruk : fm * ruk + fp * up1(ruk);     // theta_m: ru at mass levels; w: ru at w levels
+            const b2 pos = nonneg_sign(rue);
+            acc = acc - sg * (rue * sel(pos, f4 + f3, f4 - f3));
+        }
+    } else {
+        const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+        const int ne = D.nEdgesOnCell[i];
+        for (int e = 0; e < ne; e++) {
+            const int iEdge = D.edgesOnCell[(unsigned)i * D.maxEdges + e];
+            const real sg = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + e];
+            const int nadv = D.nAdvCellsForEdge[iEdge];
+            int my_c = 0; real my_a = 0.0, my_b = 0.0;
+            if (lane < nadv) {
+                my_c = D.advCellsForEdge[(unsigned)iEdge * 15 + lane];
+                my_a = D.adv_coefs[(unsigned)iEdge * 15 + lane]; my_b = D.adv_coefs_3rd[(unsigned)iEdge * 15 + lane];
+            }
+            const r2 ruk = LD(D.ru, iEdge);
+            const r2 rue = field ? ruk : fm * ruk + fp * up1(ruk);
+            r2 f4 = mk2(0.0, 0.0), f3 = f4;
+            for (int j = 0; j < nadv; j++) {
+                const r2 q2 = LD(Q, BC(my_c, j));
+                f4 = fma2(BC(my_a, j), q2, f4); f3 = fma2(BC(my_b, j), q2, f3);
+            }
+            const b2 pos = nonneg_sign(rue);
+            acc = acc - sg * (rue * sel(pos, f4 + f3, f4 - f3));
+        }
+    }
+    ST(OUT, i, field ? sel(k_lt_nl, acc, 0.0) : sel(k_mid, acc, 0.0));
 }
 
 // owned cells: tend_w (TI:5713-5757, 5838-5945) and tend_theta (TI:5956-6016, 6066-6126, 6134-6197).
@@ -520,6 +633,136 @@ __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev
     ST(D.tend_w, i, out_tend_w);
     ST(D.rthdynten, i, out_rthdynten);
     ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
+    CW_END
+}
+
+// ---- the same cell tendency for the relaxed path: horizontal flux divergences from k5_flux_cell, persistent warps ----
+// The kernel is a chain of dependent round trips (edgesOnCell -> cellsOnEdge -> gathered columns), i.e. latency bound at one
+// column per warp.  Here a warp walks cells g, g + G, ..., fetches the NEXT cell's connectivity while the current cell's
+// columns are in flight, and requests the own-column operands together with the gathers.
+struct CfConn { int ne, e, c1, c2; real sgn, dv, d4, idc, invArea; };
+__device__ __forceinline__ CfConn cf_conn(const Dev& D, int i, int lane, bool rk1) {
+    CfConn c;
+    c.ne = D.nEdgesOnCell[i];
+    const int le = min(lane, c.ne - 1);
+    c.e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    c.sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+    c.c1 = D.cellsOnEdge[2 * c.e]; c.c2 = D.cellsOnEdge[2 * c.e + 1];
+    c.dv = D.dvEdge[c.e];
+    c.d4 = 0.0; c.idc = 0.0;
+    if (rk1) { c.d4 = D.meshScalingDel4[c.e]; c.idc = D.invDcEdge[c.e]; }
+    c.invArea = D.invAreaCell[i];
+    return c;
+}
+#ifndef CF7_MINB
+#define CF7_MINB 2
+#endif
+__global__ void __launch_bounds__(CW_THREADS, CF7_MINB) k7_dt_cell_f(const Dev D, const DynTendArgs A) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
+    const bool rk1 = A.rk_step == 1;
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdzu = LD(D.rdzu, 0), rdzw = LD(D.rdzw, 0);
+    const b2 k_ge1 = lv.ge(1), k_lt_nl = lv.lt(nl);
+    const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
+    const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
+    const int G = gridDim.x * CW_WARPS;
+    int i = blockIdx.x * CW_WARPS + wib;
+    CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
+    if (i < D.nCellsSolve) cn = cf_conn(D, i, lane, rk1);
+    for (; i < D.nCellsSolve; i += G) {
+        const int ne = cn.ne, my_e = cn.e, my_c1 = cn.c1, my_c2 = cn.c2;
+        const real my_sgn = cn.sgn, my_dv = cn.dv, my_d4 = cn.d4, my_idc = cn.idc, invArea = cn.invArea;
+        // own-column operands: requested up front, together with the gathers below
+        r2 tw = LD(D.hdiv_w, i), tt = LD(D.hdiv_theta, i);
+        r2 twe = LD(D.tend_w_euler, i), tte = LD(D.tend_theta_euler, i);
+        const r2 rw = LD(D.rw, i), w = LD(D.w_2, i), t = LD(D.theta_m_2, i), ts = LD(D.theta_m, i), rws = LD(D.rw_save, i);
+        const r2 rho = LD(D.rho_zz_2, i), tend_rho = LD(D.tend_rho, i), rtdiab = LD(D.rt_diabatic_tend, i);
+        const r2 trp = LD(D.tend_rtheta_physics, i);
+        r2 pp = mk2(0.0, 0.0), dpdz = mk2(0.0, 0.0), cqw = mk2(0.0, 0.0);
+        if (rk1) { pp = LD(D.pressure_p, i); dpdz = LD(D.dpdz, i); cqw = LD(D.cqw, i); }
+        const r2 twe_in = twe;
+        if (!rk1) {               // perturbation flux for the rtheta_pp equation, TI:5995-6016
+#define CF7_PERT(E)                                                                                         \
+            {                                                                                               \
+                const int iEdge = BC(my_e, (E)), cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));            \
+                const real sg = BC(my_sgn, (E)), dv = BC(my_dv, (E));                                       \
+                const r2 flux = sg * dv * (LD(D.ru_save, iEdge) - LD(D.ru, iEdge)) * 0.5 * (LD(D.theta_m, cell2) + LD(D.theta_m, cell1)); \
+                tt = selb((E) < ne, tt - flux, tt);                                                         \
+            }
+#pragma unroll
+            for (int e = 0; e < CW_NE; e++) CF7_PERT(e)
+            for (int e = CW_NE; e < ne; e++) CF7_PERT(e)
+#undef CF7_PERT
+        } else {
+#define CF7_DEL4(E, ACC, FIELD, RAREA)                                                                      \
+            {                                                                                               \
+                const int cell1 = BC(my_c1, (E)), cell2 = BC(my_c2, (E));                                   \
+                const real edge_sign = BC(my_d4, (E)) * (RAREA) * BC(my_dv, (E)) * BC(my_sgn, (E)) * BC(my_idc, (E)); \
+                const r2 d = LD(FIELD, cell2) - LD(FIELD, cell1);                                           \
+                ACC = selb((E) < ne, ACC - edge_sign * d, ACC);                                             \
+            }
+            if (A.h_mom_eddy_visc4 > 0.0) {
+                const real r_areaCell = A.h_mom_eddy_visc4 * invArea;
+#pragma unroll
+                for (int e = 0; e < CW_NE; e++) CF7_DEL4(e, twe, D.delsq_w, r_areaCell)
+                for (int e = CW_NE; e < ne; e++) CF7_DEL4(e, twe, D.delsq_w, r_areaCell)
+            }
+            if (A.h_theta_eddy_visc4 > 0.0) {
+                const real r_areaCell = A.h_theta_eddy_visc4 * A.prandtl_inv * invArea;
+#pragma unroll
+                for (int e = 0; e < CW_NE; e++) CF7_DEL4(e, tte, D.delsq_theta, r_areaCell)
+                for (int e = CW_NE; e < ne; e++) CF7_DEL4(e, tte, D.delsq_theta, r_areaCell)
+            }
+#undef CF7_DEL4
+        }
+        if (i + G < D.nCellsSolve) {
+            cn = cf_conn(D, i + G, lane, rk1);          // next cell's connectivity, behind this cell's requests
+            if (D.pf_next) {
+                const int j = i + G;
+                PF(D.hdiv_w, j); PF(D.hdiv_theta, j); PF(D.tend_w_euler, j); PF(D.tend_theta_euler, j); PF(D.rw, j); PF(D.w_2, j);
+                PF(D.theta_m_2, j); PF(D.theta_m, j); PF(D.rw_save, j); PF(D.rho_zz_2, j); PF(D.tend_rho, j); PF(D.rt_diabatic_tend, j);
+                PF(D.tend_rtheta_physics, j);
+                if (rk1) { PF(D.pressure_p, j); PF(D.dpdz, j); PF(D.cqw, j); }
+            }
+        }
+        const r2 rwm1 = up1(rw);
+        {   // ---- w: vertical advection (TI:5878-5891), pressure gradient, buoyancy
+            const r2 wm1 = up1(w), wm2 = up2(w), wp1 = dn1(w);
+            const r2 f2 = 0.25 * (rw + rwm1) * (w + wm1);
+            const r2 f3 = flux3_2(wm2, wm1, w, wp1, 0.5 * (rw + rwm1), 1.0);
+            const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(kk_edge, f2, f3));     // flux at interface k
+            const r2 f1 = dn1(fz);
+            tw = tw * invArea - rdzu * (f1 - fz);
+            if (rk1) {
+                const r2 twe_new = twe - cqw * (rdzu * (pp - up1(pp)) - (fm * dpdz + fp * up1(dpdz)));
+                twe = sel(k_ge1 && k_lt_nl, twe_new, twe_in);    // rows 0 and nl keep what they held
+            }
+        }
+        const r2 out_tend_w = sel(k_ge1 && k_lt_nl, tw + twe, 0.0);
+        r2 out_rthdynten;
+        {   // ---- theta_m: vertical advection (TI:6101-6116), mixing
+            const r2 tm1 = up1(t), tm2 = up2(t), tp1 = dn1(t), tsm1 = up1(ts);
+            const r2 ftop = rws * (fm * t + fp * tm1);                                   // kk == nl-1
+            const r2 flow = rw * (fm * t + fp * tm1);                                    // kk == 1
+            const r2 f3 = flux3_2(tm2, tm1, t, tp1, rw, A.coef_3rd_order);
+            const r2 fpert = sel(lv.eq(1), flow, f3) + (rws - rw) * (fm * ts + fp * tsm1);
+            const r2 fz = sel(kk_zero, mk2(0.0, 0.0), sel(lv.eq(nl - 1), ftop, fpert));
+            const r2 f1 = dn1(fz);
+            tt = tt * invArea - rdzw * (f1 - fz);
+            out_rthdynten = sel(k_lt_nl, (tt - tend_rho * t) / rho, 0.0);
+            tt = tt + rho * rtdiab;
+        }
+        if (rk1) {
+            ST(D.tend_w_euler, i, twe);
+            ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
+        }
+        ST(D.tend_w, i, out_tend_w);
+        ST(D.rthdynten, i, out_rthdynten);
+        ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
+    }
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (b)
@@ -530,6 +773,7 @@ __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev
 // ~64 registers for 32 resident warps per SM rather than unrolled for more loads in flight (measured).
 __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.rho_edge, cw_next); PF(D.u_2, cw_next); PF(D.pv_edge, cw_next); if (A.rk_step == 1) { PF(D.cqu, cw_next); PF(D.zxu, cw_next); } else { PF(D.tend_u_euler, cw_next); PF(D.tend_ru_physics, cw_next); } }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
     const real invDc = D.invDcEdge[i];
@@ -550,7 +794,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
         tue = tue + rho_e * kdiffu * u_diffusion * D.meshScalingDel2[i];
         ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
     }
-    if (!solve) return;
+    if (!solve) continue;
     const r2 u = LD(D.u_2, i);
     r2 tu;
     {   // vertical transport of u, TI:5391-5408
@@ -581,6 +825,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
          - u * 0.5 * (LD(D.h_divergence, cell1) + LD(D.h_divergence, cell2));
     if (A.rk_step != 1) tu = tu + LD(D.tend_u_euler, i) + LD(D.tend_ru_physics, i);
     ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
+    CW_END
 }
 
 // (an earlier one-warp-per-cell version of the acoustic cell step, with lane 0 sweeping the column out of shared memory --
@@ -588,9 +833,11 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
 
 // ------------------------------------------------------------------ atm_set_smlstep_pert_variables_work  TI:2427-2508
 // zb_cell/zb3_cell are [cell][edge slot][LDK]; requires maxEdges >= CW_NE (slots beyond nEdgesOnCell exist and are skipped)
+#define PFZ(p, col, E) pf2((p), ((unsigned)(col) * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
     CW_SETUP(D.nCellsSolve)
+    if (cw_pf) { PF(D.tend_w, cw_next); PF(D.zz, cw_next); if (D.zb_any[cw_next]) { for (int e_ = 0; e_ < CW_NE; e_++) { PFZ(D.zb_cell, cw_next, e_); PFZ(D.zb3_cell, cw_next, e_); } } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -616,11 +863,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev 
 #undef SML_EDGE
     }
     ST(D.tend_w, i, sel(lv.ge(1) && lv.lt(nl), (fm * zz + fp * up1(zz)) * wt, wt_in));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
 __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     CW_SETUP(D.nCells)
+    if (cw_pf) { PF(D.w_2, cw_next); PF(D.rho_zz_2, cw_next); if (D.zb_any[cw_next]) { for (int e_ = 0; e_ < CW_NE; e_++) { PFZ(D.zb_cell, cw_next, e_); PFZ(D.zb3_cell, cw_next, e_); } } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -648,6 +897,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
     }
     const r2 den = sel(k_eq0, cf1 * rho + cf2 * dn1(rho) + cf3 * dn2(rho), fm * rho + fp * up1(rho));
     ST(D.w_2, i, sel(lv.lt(nl), w / den, w_in));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
@@ -675,6 +925,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
     ST(D.vorticity, i, sel(k_lt_nl, vort, 0.0));
     ST(D.ke_vertex, i, sel(k_lt_nl, (ke0 + ke1 + ke2) * r, 0.0));
     ST(D.pv_vertex, i, sel(k_lt_nl, D.fVertex[i] + vort, 0.0));
+    CW_END
 }
 // (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
@@ -719,11 +970,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
     ST(D.divergence, i, sel(k_lt_nl, div * r, 0.0));
     ST(D.ke, i, sel(k_lt_nl, ke, 0.0));
     if (apvm) ST(D.pv_cell, i, sel(k_lt_nl, pvc, 0.0));
+    CW_END
 }
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(u, cw_next); if (!reconstruct_v) PF(D.v, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
@@ -753,6 +1006,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev 
     if (reconstruct_v) ST(D.v, i, sel(k_lt_nl, vv, 0.0));
     if (apvm) { ST(D.gradPVt, i, sel(k_lt_nl, gt, 0.0)); ST(D.gradPVn, i, sel(k_lt_nl, gn, 0.0)); }
     ST(D.pv_edge, i, sel(k_lt_nl, pve, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (a)
@@ -760,6 +1014,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev 
 // Restriction (host falls back to k_dt_cell_a otherwise): config_mpas_cam_coef == 0.
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
+    if (cw_pf) { if (A.rk_step == 1) { PF(D.rw, cw_next); PF(D.qtot, cw_next); PF(D.tend_rho_physics, cw_next); PF(D.rho_base, cw_next); PF(D.rho_p_save, cw_next); } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -800,12 +1055,14 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev 
         ST(D.dpdz, i, sel(k_lt_nl, dpdz, 0.0));
     }
     ST(D.h_divergence, i, sel(k_lt_nl, hd, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
 // rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
+    if (cw_pf) { PF(D.kdiff, cw_next); PF(D.w_2, cw_next); PF(D.theta_m_2, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -854,6 +1111,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev 
     ST(D.tend_w_euler, i, sel(k_mid, twe, 0.0));
     ST(D.delsq_theta, i, sel(k_lt_nl, dst, 0.0));
     ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_acoustic_step_work, cell part (block-tiled)
@@ -1052,22 +1310,45 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
 #endif
 struct aff { real a, b; };          // x -> a * x + b
 __device__ __forceinline__ aff aff_after(aff later, aff earlier) { aff r; r.a = later.a * earlier.a; r.b = fma(later.a, earlier.b, later.b); return r; }
-__global__ void __launch_bounds__(CW_THREADS, AC6_MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
-    CW_SETUP(D.nCells)
+struct Ac6Conn { int ne, e, oth, is12; real f, invArea; };
+// connectivity of cell i for its lane: edge slot min(lane, ne-1) -- two dependent index loads (edgesOnCell -> cellsOnEdge, dvEdge)
+__device__ __forceinline__ Ac6Conn ac6_conn(const Dev& D, int i, int lane, real dts) {
+    Ac6Conn c;
+    c.ne = D.nEdgesOnCell[i];
+    const int le = min(lane, c.ne - 1);
+    c.e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    const int c1 = D.cellsOnEdge[2 * c.e], c2 = D.cellsOnEdge[2 * c.e + 1];
+    c.is12 = (c1 == i ? 1 : 0) | (c2 == i ? 2 : 0);
+    c.oth = (c1 == i) ? c2 : c1;
+    c.f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[c.e];
+    c.invArea = D.invAreaCell[i];
+    return c;
+}
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const bool first = small_step == 1;
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
+    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
+    // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
+    const int G = gridDim.x * WARPS;
+    int i = blockIdx.x * WARPS + wib;
+    Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
+    if (i < D.nCellsSolve) cn = ac6_conn(D, i, lane, dts);
+    for (; i < D.nCells; i += G) {
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
-    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); return; }          // halo cells: TI:2827-2842 only
-    const int ne = D.nEdgesOnCell[i];
-    const int le = min(lane, ne - 1);
-    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
-    const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
-    const bool my_is1 = my_c1 == i, my_is2 = my_c2 == i;
-    const int my_oth = my_is1 ? my_c2 : my_c1;
-    const real my_f = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * dts * D.dvEdge[my_e];
-    const real invArea = D.invAreaCell[i];
-    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); continue; }          // halo cells: TI:2827-2842 only
+    const int ne = cn.ne;
+    const int my_e = cn.e, my_oth = cn.oth;
+    const bool my_is1 = (cn.is12 & 1) != 0, my_is2 = (cn.is12 & 2) != 0;
+    const real my_f = cn.f, invArea = cn.invArea;
     if (!first) {
         rw_p = sel(k_le_nl, LD(D.rw_p, i), 0.0);
         rho_pp = sel(k_lt_nl, LD(D.rho_pp, i), 0.0);
@@ -1096,7 +1377,16 @@ __global__ void __launch_bounds__(CW_THREADS, AC6_MINB) k6_acoustic_cell(const D
 #undef AC6_EDGE
     // operands of the part after the solve: issued here so that they are in flight during the solve
     const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
-    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    if (i + G < D.nCellsSolve) {
+        cn = ac6_conn(D, i + G, lane, dts);          // next cell's connectivity, in flight with this cell's columns
+        if (D.pf_next) {                             // and its own-column operands on their way into L2
+            const int j = i + G;
+            PF(D.tend_rho, j); PF(D.tend_theta, j); PF(D.tend_w, j); PF(D.coftz, j); PF(D.cofwz, j); PF(D.cofwr, j); PF(D.cofwt, j);
+            PF(D.zz, j); PF(D.a_tri, j); PF(D.alpha_tri, j); PF(D.gamma_tri, j); PF(D.theta_m, j); PF(D.dss, j); PF(D.rw_save, j);
+            PF(D.rw, j); PF(D.rho_zz_2, j); PF(D.w_2, j);
+            if (!first) { PF(D.rtheta_pp, j); PF(D.rw_p, j); PF(D.rho_pp, j); PF(D.wwAvg, j); }
+        }
+    }
     const r2 rw_p1 = dn1(rw_p);
     const r2 coftz1 = dn1(coftz);
     rs = rho_pp + dts * tend_rho + rs - cofrz * resm * (rw_p1 - rw_p);
@@ -1159,6 +1449,7 @@ __global__ void __launch_bounds__(CW_THREADS, AC6_MINB) k6_acoustic_cell(const D
     ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
     ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
     ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1 - coftz * r), 0.0));
+    }
 }
 
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075
@@ -1166,8 +1457,9 @@ __global__ void __launch_bounds__(CW_THREADS, AC6_MINB) k6_acoustic_cell(const D
 // ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
 __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { if (first) PF(D.tend_u, cw_next); else PF(D.ru_p, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
     const real mask = 1.0 - D.specZoneMaskEdge[i];
     const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
     const r2 divCell2 = -(LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp_old, cell2));
@@ -1178,14 +1470,16 @@ __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D,
     const b2 k_lt_nl = lv.lt(nl);
     if (first) ST(D.ruAvg, i, sel(k_lt_nl, ru_p, 0.0));
     ST(D.ru_p, i, sel(k_lt_nl, ru_p + coef_divdamp * (divCell2 - divCell1) * mask / th, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, parts 1 and 2
 // (1) cell-all, TI:3294-3350 (+ the garbage cell, TI:3282-3284)
 __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const Dev D, real dt, real invNs, int rk_step, real rcv, real rgas_p0) {
     CW_SETUP(D.nCells + 1)
+    if (cw_pf) { PF(D.rho_p_save, cw_next); PF(D.rho_pp, cw_next); PF(D.rho_base, cw_next); PF(D.rtheta_base, cw_next); PF(D.zz, cw_next); PF(D.rw_save, cw_next); PF(D.wwAvg, cw_next); PF(D.rw, cw_next); PF(D.w_2, cw_next); PF(D.rtheta_p_save, cw_next); PF(D.rtheta_pp, cw_next); PF(D.rw_p, cw_next); if (rk_step == 3) { PF(D.rt_diabatic_tend, cw_next); PF(D.exner_base, cw_next); } }
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
-    if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); return; }
+    if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); continue; }
     const r2 rho_p = LD(D.rho_p_save, i) + LD(D.rho_pp, i);
     const r2 rho_zz = rho_p + LD(D.rho_base, i);
     const r2 rtb = LD(D.rtheta_base, i);
@@ -1215,10 +1509,12 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const De
     ST(D.wwAvg, i, sel(k_mid, rw_save + (wwAvg_in * invNs), wwAvg_in));
     ST(D.rw, i, sel(k_mid, rw, sel(k_ends, mk2(0.0, 0.0), rw_in)));
     ST(D.w_2, i, sel(k_mid, rw / (fm * zz + fp * up1(zz)), sel(k_ends, mk2(0.0, 0.0), w_in)));
+    CW_END
 }
 // (2) edge-all, TI:3360-3372
 __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.ru_save, cw_next); PF(D.ru_p, cw_next); PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
     const r2 rus = LD(D.ru_save, i);
@@ -1227,13 +1523,15 @@ __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real 
     ST(D.ruAvg, i, sel(k_lt_nl, rus + (LD(D.ruAvg, i) * invNs), 0.0));
     ST(D.ru, i, sel(k_lt_nl, ru, 0.0));
     ST(D.u_2, i, sel(k_lt_nl, 2. * ru / rho2, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_acoustic_step_work, edge part (small_step > 1)  TI:2751-2796
 __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.cqu, cw_next); PF(D.zxu, cw_next); PF(D.ru_p, cw_next); PF(D.tend_u, cw_next); PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
     const b2 k_lt_nl = lv.lt(nl);
     r2 pgrad = ((LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp, cell1)) * D.invDcEdge[i]) / (.5 * (LD(D.zz, cell2) + LD(D.zz, cell1)));
     pgrad = LD(D.cqu, i) * 0.5 * c2 * (LD(D.exner, cell1) + LD(D.exner, cell2)) * pgrad;
@@ -1241,6 +1539,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
     const r2 rup = LD(D.ru_p, i) + dts * (LD(D.tend_u, i) - (1.0 - D.specZoneMaskEdge[i]) * pgrad);
     ST(D.ru_p, i, sel(k_lt_nl, rup, 0.0));
     ST(D.ruAvg, i, sel(k_lt_nl, LD(D.ruAvg, i) + rup, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855
@@ -1248,6 +1547,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
 // possible weights per entry live one per lane and are broadcast; scalars are separate level-contiguous planes
 __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.ruAvg, cw_next); }
     const int nadv = D.nAdvCellsForEdge[i];
     int my_c = 0; real my_wp = 0.0, my_wm = 0.0;
     if (lane < nadv) {
@@ -1276,10 +1576,12 @@ __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
         }
         ST(D.horiz_flux_arr + (size_t)s * D.edgePlane, i, sel(k_lt_nl, acc, 0.0));
     }
+    CW_END
 }
 // owned cells: flux divergence + vertical flux + update, TI:3773-3846
 __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
     CW_SETUP(D.nCellsSolve)
+    if (cw_pf) { PF(D.rho_zz, cw_next); PF(D.rho_zz_2, cw_next); PF(D.wwAvg, cw_next); for (int s_ = 0; s_ < D.num_scalars; s_++) { PF(D.scalars_2 + (size_t)s_ * D.cellPlane, cw_next); PF(D.scalars + (size_t)s_ * D.cellPlane, cw_next); } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1317,6 +1619,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
         ST(D.scalars_tend + (size_t)s * D.cellPlane, i, mk2(0.0, 0.0));
         ST(qn, i, sel(k_lt_nl, val, 0.0));
     }
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_vert_imp_coefs_work  TI:2225-2366 (block-tiled)
@@ -1418,6 +1721,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_vertex(const Dev D) {
 #pragma unroll
     for (int j = 0; j < 3; j++) acc = acc + BC(my_s, j) * LD(D.delsq_u, BC(my_e, j));
     ST(D.delsq_vorticity, i, sel(lv.lt(nl), acc, 0.0));
+    CW_END
 }
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
     CW_SETUP(D.nCells)
@@ -1432,11 +1736,13 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
     for (int e = CW_NE; e < ne; e++) DELSQ_C(e)
 #undef DELSQ_C
     ST(D.delsq_divergence, i, sel(lv.lt(nl), acc, 0.0));
+    CW_END
 }
 // owned edges: del^4 of u (TI:5558-5584) and the final sum (TI:5694-5701).
 // Restrictions (the host falls back to k_dt_edge_d otherwise): v_mom_eddy_visc2 == 0, no Rayleigh damping of u.
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdgesSolve)
+    if (cw_pf) { PF(D.tend_u_euler, cw_next); PF(D.rho_edge, cw_next); PF(D.tend_u, cw_next); PF(D.tend_ru_physics, cw_next); }
     r2 tue = LD(D.tend_u_euler, i);
     if (A.h_mom_eddy_visc4 > 0.0) {
         const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
@@ -1452,6 +1758,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const Dy
     const b2 k_lt_nl = lv.lt(nl);
     ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
     ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, edge part (C2)
@@ -1461,6 +1768,7 @@ __device__ __forceinline__ r2 max0(r2 a) { return mk2(rmax(0.0, a.x), rmax(0.0, 
 __device__ __forceinline__ r2 min0(r2 a) { return mk2(rmin(0.0, a.x), rmin(0.0, a.y)); }
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, real dt) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
@@ -1491,6 +1799,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, 
     const b2 k_lt_nl = lv.lt(nl);
     ST(D.flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
     ST(D.flux_tmp, i, sel(k_lt_nl, dt * flux - fup, 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, the other parts
@@ -1499,6 +1808,7 @@ __device__ __forceinline__ r2 min2(r2 a, r2 b) { return mk2(rmin(a.x, b.x), rmin
 // (B) owned cells: re-integrated density, TI:4177-4204
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real dt) {
     CW_SETUP(D.nCellsSolve)
+    if (cw_pf) { PF(D.wwAvg, cw_next); PF(D.rho_zz, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1512,10 +1822,12 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real 
 #undef RHO_INT_EDGE
     const r2 ww = LD(D.wwAvg, i);
     ST(D.rho_zz_int, i, sel(lv.lt(nl), LD(D.rho_zz, i) + dt * (r - LD(D.rdzw, 0) * (dn1(ww) - ww)), 0.0));
+    CW_END
 }
 // (C1) owned cells: vertical fluxes, bounds, vertical part of the upwind update and of scale_arr  TI:4277-4344, 4426-4459
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, real dt, real coef3) {
     CW_SETUP(D.nCellsSolve)
+    if (cw_pf) { PF(D.scalars + (size_t)s * D.cellPlane, cw_next); PF(D.scalars_2 + (size_t)s * D.cellPlane, cw_next); PF(D.wwAvg, cw_next); PF(D.rho_zz, cw_next); }
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
     const int ne = D.nEdgesOnCell[i];
@@ -1547,10 +1859,12 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, 
     ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
     ST(D.scale_arr, i, sel(k_lt_nl, -rdnw * (min0(wd1) - max0(wd0)), 0.0));                     // SCALE_IN
     ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));       // SCALE_OUT
+    CW_END
 }
 // (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
     CW_SETUP(D.nCellsSolve)
+    if (cw_pf) { PF(D.scalar_new, cw_next); PF(D.scale_arr, cw_next); PF(D.scale_arr + D.cellPlane, cw_next); PF(D.s_max, cw_next); PF(D.s_min, cw_next); PF(rho_lim, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1577,24 +1891,28 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const r
     ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
     ST(D.scale_arr, i, sel(k_lt_nl, min2(splat(1.0), max0(f_in)), 0.0));
     ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, min2(splat(1.0), max0(f_out)), 0.0));
+    CW_END
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
     CW_SETUP(D.nEdges)
+    if (cw_pf) { PF(D.flux_tmp, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
     const real* __restrict__ s_in = D.scale_arr; const real* __restrict__ s_out = D.scale_arr + D.cellPlane;
     const r2 flux = LD(D.flux_tmp, i);
     const r2 f = max0(flux) * min2(LD(s_out, cell1), LD(s_in, cell2))
                + min0(flux) * min2(LD(s_in, cell1), LD(s_out, cell2));
     ST(D.flux_arr, i, sel(lv.lt(nl), f, 0.0));
+    CW_END
 }
 // (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* __restrict__ rho_div) {
     CW_SETUP(D.nCells)
+    if (cw_pf) { PF(D.scale_arr, cw_next); PF(D.scale_arr + D.cellPlane, cw_next); PF(D.wdtn, cw_next); PF(D.scalar_new, cw_next); PF(rho_div, cw_next); }
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
     const b2 k_lt_nl = lv.lt(nl);
-    if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); return; }       // warp-uniform
+    if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); continue; }       // warp-uniform
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1611,6 +1929,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
 #undef MONO5_EDGE
     snew = (snew + (-LD(D.rdzw, 0) * (w1 - w0))) / LD(rho_div, i);
     ST(out, i, sel(k_lt_nl, max0(snew), 0.0));
+    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f) split in two
@@ -1672,6 +1991,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FW) k2_dt_cell_fw(const De
         ST(D.tend_w_euler, i, twe);
     }
     ST(D.tend_w, i, sel(k_ge1 && k_lt_nl, tw + twe, 0.0));
+    CW_END
 }
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const Dev D, const DynTendArgs A) {     // tend_theta, TI:5956-6016, 6066-6126, 6134-6197
     CW_SETUP(D.nCellsSolve)
@@ -1735,4 +2055,5 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const De
     if (A.rk_step == 1) ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
     ST(D.rthdynten, i, out_rthdynten);
     ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
+    CW_END
 }

@@ -45,14 +45,14 @@ struct mpasb_handle_s {
     double* d_minmax = nullptr;
     // asynchronous summarize_timestep: device results (2 * (2 + num_scalars) doubles + 2 NaN counters as doubles' bit
     // patterns), pinned host copy, completion event
-    double* d_summary = nullptr; double* h_summary = nullptr; cudaEvent_t ev_summary = nullptr; bool summary_pending = false;
+    // (two slots, so that the summary of one request can be fetched while the next request is already enqueued)
+    double* d_summary[2] = {}; double* h_summary[2] = {}; cudaEvent_t ev_summary[2] = {}; long summary_head = 0, summary_tail = 0;
     std::string err;
     long launches = 0;
     int cpb = 4;
     bool colwarp = false;          // LDK <= 64 and <= CW_MAXNE edges per cell: the column-warp kernels apply
     int max_ne = 0;                // max(nEdgesOnCell), known once the mesh is uploaded
     bool zb_dirty = true;          // zb_any must be recomputed before the next step
-    bool physics_tend_dirty = true; // tend_*_physics must be zeroed before the next step (TI:1091-1093, no physics)
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
@@ -64,6 +64,7 @@ struct mpasb_handle_s {
     std::vector<int> hc_cellsOnCell, hc_edgesOnCell, hc_nEdgesOnCell;
     std::vector<real> hc_adv_coefs, hc_adv_coefs_3rd;
     bool rings_dirty = true, rings_ok = false;
+    bool persist = true;           // persistent launches of the column-warp kernels (MPASB_PERSIST=0: one warp per column)
     bool relaxed = true;           // re-associated / FMA kernels allowed (parity bar 1e-11, not bit equality); MPASB_STRICT=1 turns it off
     long n_regular = 0;
     bool tiles_dirty = true, tiles_ok = false;
@@ -74,6 +75,13 @@ struct mpasb_handle_s {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool comm_pending = false, overlap = true;
     HaloState halo;
+    // batched, stream-ordered field transfers (mpasb_set_fields_async / mpasb_get_fields_async): their own copy streams and
+    // staging areas, so that the upload of the next request, the step and the download of the previous one overlap
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    void* stage_in = nullptr; void* stage_out = nullptr; size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    enum { XFER_RING = 4 };         // completion events of the last XFER_RING batches per direction (mpasb_wait_*_lag)
+    cudaEvent_t ev_in_ready[XFER_RING] = {}, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_done[XFER_RING] = {};
+    long n_in = 0, n_out = 0;       // batches enqueued so far
 };
 typedef mpasb_handle_s H;
 
@@ -131,6 +139,9 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->overlap = !getenv("MPASB_NO_OVERLAP");
     h->relaxed = !mpasb_strict_arithmetic();
     memset(&h->D, 0, sizeof(Dev));
+    if (const char* pe = getenv("MPASB_PERSIST")) h->persist = atoi(pe) != 0;
+    h->D.pf_next = h->persist ? 1 : 0;
+    if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
     Dev& D = h->D;
     D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
     D.nCellsSolve = dims->nCellsSolve; D.nEdgesSolve = dims->nEdgesSolve; D.nVerticesSolve = dims->nVerticesSolve;
@@ -188,10 +199,18 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     halo_destroy(h->halo);
     for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(f.d[l]);
     if (h->staging) cudaFree(h->staging);
+    if (h->stage_in) cudaFree(h->stage_in);
+    if (h->stage_out) cudaFree(h->stage_out);
+    for (cudaEvent_t e : {h->ev_in_free, h->ev_out_ready}) if (e) cudaEventDestroy(e);
+    for (int q = 0; q < H::XFER_RING; q++) { if (h->ev_in_ready[q]) cudaEventDestroy(h->ev_in_ready[q]); if (h->ev_out_done[q]) cudaEventDestroy(h->ev_out_done[q]); }
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->d_minmax) cudaFree(h->d_minmax);
-    if (h->d_summary) cudaFree(h->d_summary);
-    if (h->h_summary) cudaFreeHost(h->h_summary);
-    if (h->ev_summary) cudaEventDestroy(h->ev_summary);
+    for (int q = 0; q < 2; q++) {
+        if (h->d_summary[q]) cudaFree(h->d_summary[q]);
+        if (h->h_summary[q]) cudaFreeHost(h->h_summary[q]);
+        if (h->ev_summary[q]) cudaEventDestroy(h->ev_summary[q]);
+    }
     if (h->D.zb_any) cudaFree(h->D.zb_any);
     if (h->D.adv_flux_w) cudaFree(h->D.adv_flux_w);
     if (h->D.adv_flux_theta) cudaFree(h->D.adv_flux_theta);
@@ -231,6 +250,136 @@ extern "C" int mpasb_field_count(mpasb_handle h, const char* name, long* count) 
 
 static inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+static bool is_padded(const FieldRec* f) {
+    return f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
+}
+// dense host layout (in `st`, device memory) -> padded device field, and back; on the compute stream
+static void launch_pad(H* h, const FieldRec* f, real* dst, const real* st) {
+    const int LDK = h->D.LDK; const size_t o = outer_of(h, f->loc); const int n1 = inner_dense1(h, f->inner);
+    if (f->inner == IN_NL || f->inner == IN_NL1) k_pad<<<nblk(o * LDK), 256, 0, h->stream>>>(dst, st, o, n1, LDK);
+    else if (f->inner == IN_NL1_ME) k_pad<<<nblk(o * h->dims.maxEdges * LDK), 256, 0, h->stream>>>(dst, st, o * h->dims.maxEdges, n1, LDK);
+    else if (f->inner == IN_S_NL) k_pad_planes<<<nblk(f->dev_count), 256, 0, h->stream>>>(dst, st, o, h->dims.nVertLevels, h->dims.num_scalars, LDK);
+    else k_pad_midplanes<<<nblk(f->dev_count), 256, 0, h->stream>>>(dst, st, o, h->dims.nVertLevels, 2, LDK);
+    h->launches++;
+}
+static void launch_unpad(H* h, const FieldRec* f, real* st, const real* src) {
+    const int LDK = h->D.LDK; const size_t o = outer_of(h, f->loc); const int n1 = inner_dense1(h, f->inner); const long count = f->host_count;
+    if (f->inner == IN_NL || f->inner == IN_NL1) k_unpad<<<nblk(count), 256, 0, h->stream>>>(st, src, o, n1, LDK);
+    else if (f->inner == IN_NL1_ME) k_unpad<<<nblk(count), 256, 0, h->stream>>>(st, src, o * h->dims.maxEdges, n1, LDK);
+    else if (f->inner == IN_S_NL) k_unpad_planes<<<nblk(count), 256, 0, h->stream>>>(st, src, o, h->dims.nVertLevels, h->dims.num_scalars, LDK);
+    else k_unpad_midplanes<<<nblk(count), 256, 0, h->stream>>>(st, src, o, h->dims.nVertLevels, 2, LDK);
+    h->launches++;
+}
+
+// ------------------------------------------------------------------ batched asynchronous transfers
+// A request = "these host arrays in, one step, those host arrays out".  With the three calls below the upload of request n+1
+// (PCIe host->device on h2d_stream), the step of request n (compute stream) and the download of request n-1 (device->host on
+// d2h_stream) overlap; within one request the order upload -> step -> download is kept by events.  One staging area per
+// direction holds the dense host layout of every field of a batch; pad / unpad kernels run on the compute stream, so the order
+// of device-field accesses is simply the order of the calls.
+static int ensure_transfer_state(H* h, size_t in_bytes, size_t out_bytes) {
+    if (!h->h2d_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&h->ev_in_free, &h->ev_out_ready}) CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (int q = 0; q < H::XFER_RING; q++) { CUDA_OK(cudaEventCreateWithFlags(&h->ev_in_ready[q], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&h->ev_out_done[q], cudaEventDisableTiming)); }
+    }
+    if (in_bytes > h->stage_in_bytes) {
+        CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaStreamSynchronize(h->h2d_stream));
+        if (h->stage_in) cudaFree(h->stage_in);
+        CUDA_OK(cudaMalloc(&h->stage_in, in_bytes)); h->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > h->stage_out_bytes) {
+        CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaStreamSynchronize(h->d2h_stream));
+        if (h->stage_out) cudaFree(h->stage_out);
+        CUDA_OK(cudaMalloc(&h->stage_out, out_bytes)); h->stage_out_bytes = out_bytes;
+    }
+    return 0;
+}
+static int batch_fields(H* h, int n, const char* const* names, const int* levels, const long* counts, std::vector<FieldRec*>& fs, size_t& bytes) {
+    bytes = 0;
+    for (int q = 0; q < n; q++) {
+        FieldRec* f = find_field(h, names[q]); if (!f) return 1;
+        if (f->type != T_REAL || levels[q] < 1 || levels[q] > f->levels || counts[q] != f->host_count) { h->err = std::string("bad field in batch: ") + names[q]; return 2; }
+        fs.push_back(f); bytes += ((size_t)f->host_count * sizeof(real) + 255) / 256 * 256;
+    }
+    return 0;
+}
+// Host arrays -> device fields.  The host arrays may be reused after mpasb_wait_uploads (or any later synchronising call).
+extern "C" int mpasb_set_fields_async(mpasb_handle h, int n, const char* const* names, const int* levels, const mpasb_real* const* src, const long* counts) {
+    cudaSetDevice(h->device);
+    std::vector<FieldRec*> fs; size_t bytes = 0;
+    if (int rc = batch_fields(h, n, names, levels, counts, fs, bytes)) return rc;
+    if (ensure_transfer_state(h, bytes, 0)) return 3;
+    if (h->n_in) CUDA_OK(cudaStreamWaitEvent(h->h2d_stream, h->ev_in_free, 0));             // the previous batch has been unpacked
+    size_t off = 0;
+    for (int q = 0; q < n; q++) {
+        CUDA_OK(cudaMemcpyAsync((char*)h->stage_in + off, src[q], (size_t)fs[q]->host_count * sizeof(real), cudaMemcpyHostToDevice, h->h2d_stream));
+        off += ((size_t)fs[q]->host_count * sizeof(real) + 255) / 256 * 256;
+    }
+    cudaEvent_t ready = h->ev_in_ready[h->n_in % H::XFER_RING];
+    CUDA_OK(cudaEventRecord(ready, h->h2d_stream));
+    CUDA_OK(cudaStreamWaitEvent(h->stream, ready, 0));
+    off = 0;
+    for (int q = 0; q < n; q++) {
+        FieldRec* f = fs[q];
+        real* dst = (real*)f->d[levels[q] - 1];
+        const real* st = (const real*)((char*)h->stage_in + off);
+        if (f->inner == IN_NL1_ME) h->zb_dirty = true;
+        if (is_padded(f)) launch_pad(h, f, dst, st);
+        else CUDA_OK(cudaMemcpyAsync(dst, st, (size_t)f->host_count * sizeof(real), cudaMemcpyDeviceToDevice, h->stream));
+        off += ((size_t)f->host_count * sizeof(real) + 255) / 256 * 256;
+    }
+    CUDA_OK(cudaEventRecord(h->ev_in_free, h->stream));
+    h->n_in++;
+    return 0;
+}
+// lag = 0: every upload enqueued so far has left the host arrays; lag = k: all but the last k batches
+extern "C" int mpasb_wait_uploads_lag(mpasb_handle h, int lag) {
+    cudaSetDevice(h->device);
+    const long b = h->n_in - 1 - lag;
+    if (lag < 0 || lag >= H::XFER_RING) { h->err = "mpasb_wait_uploads_lag: lag out of range"; return 1; }
+    if (b >= 0) CUDA_OK(cudaEventSynchronize(h->ev_in_ready[b % H::XFER_RING]));
+    return 0;
+}
+extern "C" int mpasb_wait_uploads(mpasb_handle h) { return mpasb_wait_uploads_lag(h, 0); }
+// Device fields -> host arrays, queued behind everything already enqueued on the compute stream (e.g. the step); the host
+// arrays are valid after mpasb_wait_downloads.
+extern "C" int mpasb_get_fields_async(mpasb_handle h, int n, const char* const* names, const int* levels, mpasb_real* const* dst, const long* counts) {
+    cudaSetDevice(h->device);
+    std::vector<FieldRec*> fs; size_t bytes = 0;
+    if (int rc = batch_fields(h, n, names, levels, counts, fs, bytes)) return rc;
+    if (ensure_transfer_state(h, 0, bytes)) return 3;
+    if (h->n_out) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_out_done[(h->n_out - 1) % H::XFER_RING], 0));     // the previous batch has left the staging area
+    size_t off = 0;
+    for (int q = 0; q < n; q++) {
+        FieldRec* f = fs[q];
+        const real* srcp = (const real*)f->d[levels[q] - 1];
+        real* st = (real*)((char*)h->stage_out + off);
+        if (is_padded(f)) launch_unpad(h, f, st, srcp);
+        else CUDA_OK(cudaMemcpyAsync(st, srcp, (size_t)f->host_count * sizeof(real), cudaMemcpyDeviceToDevice, h->stream));
+        off += ((size_t)f->host_count * sizeof(real) + 255) / 256 * 256;
+    }
+    CUDA_OK(cudaEventRecord(h->ev_out_ready, h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->d2h_stream, h->ev_out_ready, 0));
+    off = 0;
+    for (int q = 0; q < n; q++) {
+        CUDA_OK(cudaMemcpyAsync(dst[q], (char*)h->stage_out + off, (size_t)fs[q]->host_count * sizeof(real), cudaMemcpyDeviceToHost, h->d2h_stream));
+        off += ((size_t)fs[q]->host_count * sizeof(real) + 255) / 256 * 256;
+    }
+    CUDA_OK(cudaEventRecord(h->ev_out_done[h->n_out % H::XFER_RING], h->d2h_stream));
+    h->n_out++;
+    return 0;
+}
+extern "C" int mpasb_wait_downloads_lag(mpasb_handle h, int lag) {
+    cudaSetDevice(h->device);
+    const long b = h->n_out - 1 - lag;
+    if (lag < 0 || lag >= H::XFER_RING) { h->err = "mpasb_wait_downloads_lag: lag out of range"; return 1; }
+    if (b >= 0) CUDA_OK(cudaEventSynchronize(h->ev_out_done[b % H::XFER_RING]));
+    return 0;
+}
+extern "C" int mpasb_wait_downloads(mpasb_handle h) { return mpasb_wait_downloads_lag(h, 0); }
+
 extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level, const mpasb_real* src, long count) {
     cudaSetDevice(h->device);
     FieldRec* f = find_field(h, name); if (!f) return 1;
@@ -240,7 +389,6 @@ extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level,
     const size_t o = outer_of(h, f->loc);
     const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
     if (f->inner == IN_NL1_ME) h->zb_dirty = true;
-    if (!strncmp(name, "tend_", 5) && strstr(name, "_physics")) h->physics_tend_dirty = true;
     if (!strcmp(name, "adv_coefs") || !strcmp(name, "adv_coefs_3rd")) {
         std::vector<real>& hc = !strcmp(name, "adv_coefs") ? h->hc_adv_coefs : h->hc_adv_coefs_3rd;
         if ((long)hc.size() != count || memcmp(hc.data(), src, count * sizeof(real))) { hc.assign(src, src + count); h->rings_dirty = true; }
@@ -341,7 +489,22 @@ struct KScope {
     }
 };
 #define LAUNCH(kern, n, smem, ...) do { KScope ks_(h, "k:" #kern); kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
-#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<(unsigned)(((n) + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+// Column-warp kernels walk columns with a grid-sized stride.  Persistent launch (default; MPASB_PERSIST=0 launches one warp per
+// column as before): only as many blocks as are resident at once, so every warp handles a sequence of columns and can ask L2
+// for its next column's operands (Dev::pf_next) while it computes the current one.
+static unsigned cw_resident_blocks(H* h, const void* kern) {
+    static std::map<const void*, unsigned> cache;
+    auto it = cache.find(kern);
+    if (it != cache.end()) return it->second;
+    int occ = 0, sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CW_THREADS, 0);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device);
+    return cache[kern] = (unsigned)std::max(1, occ * sm);
+}
+#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); \
+    unsigned nb_ = (unsigned)(((n) + CW_WARPS - 1) / CW_WARPS); \
+    if (h->persist) nb_ = std::min(nb_, cw_resident_blocks(h, (const void*)kern)); \
+    if (nb_) kern<<<nb_, CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -593,12 +756,29 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
         if (h->rings_ok) {
             // relaxed arithmetic: one cell-centred sweep computes the horizontal flux divergence of w and theta_m with the
             // two-ring neighbourhood in registers; no per-edge flux arrays, 38 instead of 60 gathered columns per cell
-            {
+            static const bool one_field_per_warp = !getenv("MPASB_FLUX_BOTH");
+            if (one_field_per_warp) {
+                KScope ks_(h, "k:k5s_flux_cell");
+                k5s_flux_cell<<<(unsigned)((2 * (size_t)D.nCellsSolve + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(D);
+                h->launches++;
+            } else {
                 KScope ks_(h, "k:k5_flux_cell");
-                k5_flux_cell<<<(unsigned)((D.nCellsSolve + FX_WARPS - 1) / FX_WARPS), FX_WARPS * 32, 0, h->stream>>>(D);
+                static int sm_count = 0;
+                if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+                const unsigned need = (unsigned)((D.nCellsSolve + FX_WARPS - 1) / FX_WARPS), resident = (unsigned)(sm_count * FX_MINB);
+                k5_flux_cell<<<std::min(need, resident), FX_WARPS * 32, 0, h->stream>>>(D);       // persistent warps
                 h->launches++;
             }
-            LAUNCHW(k2_dt_cell_f<true>, D.nCellsSolve, D, A);
+            static const bool old_f = getenv("MPASB_OLD_CELL_F") != nullptr;
+            if (old_f) LAUNCHW(k2_dt_cell_f<true>, D.nCellsSolve, D, A);
+            else {
+                static int sm_count = 0;
+                if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+                const unsigned need = (unsigned)((D.nCellsSolve + CW_WARPS - 1) / CW_WARPS), resident = (unsigned)(sm_count * CF7_MINB);
+                KScope ks_(h, "k:k7_dt_cell_f");
+                k7_dt_cell_f<<<std::min(need, resident), CW_THREADS, 0, h->stream>>>(D, A);      // persistent warps
+                h->launches++;
+            }
         } else {
             if (h->tiles_dirty) build_flux_tiles(h);
             if (h->tiles_ok) {
@@ -640,7 +820,17 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
         else LAUNCHW(k2_acoustic_edge, h->D.nEdges, h->D, dts, c2);
         static const bool no_scan = getenv("MPASB_NO_SCAN") != nullptr;
         if (h->relaxed && !no_scan) {       // the column solve as a warp-level prefix of affine maps: one warp per column, registers only
-            LAUNCHW(k6_acoustic_cell, h->D.nCells, h->D, dts, small_step, epssm, resm);
+            static int sm_count = 0;
+            if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+            static const int variant = getenv("MPASB_AC6") ? atoi(getenv("MPASB_AC6")) : 1;
+            KScope ks_(h, "k:k6_acoustic_cell");
+#define AC6_LAUNCH(W, MB) do { const unsigned need = (unsigned)((h->D.nCells + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
+                k6_acoustic_cell<W, MB><<<std::min(need, resident), (W) * 32, 0, h->stream>>>(h->D, dts, small_step, epssm, resm); } while (0)
+            if (variant == 0) AC6_LAUNCH(8, 2);            // 128 registers, 16 warps per SM
+            else if (variant == 2) AC6_LAUNCH(4, 4);       // 128 registers, 16 warps per SM in smaller blocks
+            else AC6_LAUNCH(4, 3);                         // 168 registers, 12 warps per SM
+#undef AC6_LAUNCH
+            h->launches++;
             return;
         }
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
@@ -833,13 +1023,9 @@ static int srk3(H* h, real dt) {
     const mpasb_config& c = h->cfg;
     Dev& D = h->D;
     cudaSetDevice(h->device);
-    // TI:967-991, 1091-1093: qtot garbage column and the physics tendencies are zero (no physics)
-    if (h->physics_tend_dirty) {      // zero until a host uploads them again (mpasb_set_field marks them dirty)
-        cudaMemsetAsync(D.tend_ru_physics, 0, D.edgePlane * sizeof(real), h->stream);
-        cudaMemsetAsync(D.tend_rtheta_physics, 0, D.cellPlane * sizeof(real), h->stream);
-        cudaMemsetAsync(D.tend_rho_physics, 0, D.cellPlane * sizeof(real), h->stream);
-        h->physics_tend_dirty = false;
-    }
+    // TI:967-991, 1091-1093: the physics tendencies tend_ru_physics, tend_rtheta_physics, tend_rho_physics are zero from
+    // mpasb_create on and hold whatever a host with physics uploads with mpasb_set_field (physics_get_tend fills them inside
+    // atm_srk3 in the reference); mpasb_zero_physics_tendencies resets them
     int dynamics_split = c.config_dynamics_split_steps;
     real dt_dynamics;
     if (c.config_split_dynamics_transport) dt_dynamics = dt / (real)dynamics_split;
@@ -912,6 +1098,15 @@ static int srk3(H* h, real dt) {
     return 0;
 }
 
+extern "C" int mpasb_zero_physics_tendencies(mpasb_handle h) {
+    cudaSetDevice(h->device);
+    const Dev& D = h->D;
+    CUDA_OK(cudaMemsetAsync(D.tend_ru_physics, 0, D.edgePlane * sizeof(real), h->stream));
+    CUDA_OK(cudaMemsetAsync(D.tend_rtheta_physics, 0, D.cellPlane * sizeof(real), h->stream));
+    CUDA_OK(cudaMemsetAsync(D.tend_rho_physics, 0, D.cellPlane * sizeof(real), h->stream));
+    return 0;
+}
+
 extern "C" int mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep) { (void)itimestep; return srk3(h, dt); }
 
 extern "C" int mpasb_minmax(mpasb_handle h, mpasb_real out[4]) {
@@ -937,32 +1132,36 @@ extern "C" int mpasb_summarize_timestep_async(mpasb_handle h) {
     cudaSetDevice(h->device);
     const Dev& D = h->D;
     const int S = D.num_scalars, nval = 2 * (2 + S) + 2;
-    if (!h->d_summary) {
-        CUDA_OK(cudaMalloc(&h->d_summary, nval * sizeof(double)));
-        CUDA_OK(cudaMallocHost(&h->h_summary, nval * sizeof(double)));
-        CUDA_OK(cudaEventCreateWithFlags(&h->ev_summary, cudaEventDisableTiming));
+    if (h->summary_head - h->summary_tail >= 2) { h->err = "mpasb_summarize_timestep_async: two summaries are already pending, fetch one first"; return 1; }
+    const int q = (int)(h->summary_head % 2);
+    if (!h->d_summary[q]) {
+        CUDA_OK(cudaMalloc(&h->d_summary[q], nval * sizeof(double)));
+        CUDA_OK(cudaMallocHost(&h->h_summary[q], nval * sizeof(double)));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_summary[q], cudaEventDisableTiming));
     }
-    CUDA_OK(cudaMemsetAsync(h->d_summary, 0, nval * sizeof(double), h->stream));
-    unsigned long long* nan = reinterpret_cast<unsigned long long*>(h->d_summary + 2 * (2 + S));
-    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.w_2, D.nCellsSolve, D.nl, D.LDK, h->d_summary, nan);
-    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.u_2, D.nEdgesSolve, D.nl, D.LDK, h->d_summary + 2, nan + 1);
-    for (int s = 0; s < S; s++)
-        k_minmax<<<296, 256, 0, h->stream>>>(D.scalars_2 + (size_t)s * D.cellPlane, D.nCellsSolve, D.nl, D.LDK, h->d_summary + 4 + 2 * s);
+    double* ds = h->d_summary[q];
+    CUDA_OK(cudaMemsetAsync(ds, 0, nval * sizeof(double), h->stream));
+    unsigned long long* nan = reinterpret_cast<unsigned long long*>(ds + 2 * (2 + S));
+    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.w_2, D.nCellsSolve, D.nl, D.LDK, ds, nan);
+    k_minmax_nan<<<296, 256, 0, h->stream>>>(D.u_2, D.nEdgesSolve, D.nl, D.LDK, ds + 2, nan + 1);
+    for (int sc = 0; sc < S; sc++)
+        k_minmax<<<296, 256, 0, h->stream>>>(D.scalars_2 + (size_t)sc * D.cellPlane, D.nCellsSolve, D.nl, D.LDK, ds + 4 + 2 * sc);
     h->launches += 2 + S;
-    CUDA_OK(cudaMemcpyAsync(h->h_summary, h->d_summary, nval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaEventRecord(h->ev_summary, h->stream));
-    h->summary_pending = true;
+    CUDA_OK(cudaMemcpyAsync(h->h_summary[q], ds, nval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaEventRecord(h->ev_summary[q], h->stream));
+    h->summary_head++;
     return 0;
 }
 extern "C" int mpasb_summarize_timestep_fetch(mpasb_handle h, mpasb_real* minmax, long n_minmax, long nan_count[2]) {
     cudaSetDevice(h->device);
-    if (!h->summary_pending) { h->err = "mpasb_summarize_timestep_fetch without a pending mpasb_summarize_timestep_async"; return 1; }
+    if (h->summary_head == h->summary_tail) { h->err = "mpasb_summarize_timestep_fetch without a pending mpasb_summarize_timestep_async"; return 1; }
+    const int q = (int)(h->summary_tail % 2);            // oldest pending summary
     const int S = h->D.num_scalars;
     if (n_minmax < 4 || n_minmax > 2 * (2 + S)) { h->err = "mpasb_summarize_timestep_fetch: n_minmax out of range"; return 2; }
-    CUDA_OK(cudaEventSynchronize(h->ev_summary));
-    h->summary_pending = false;
-    for (long n = 0; n < n_minmax; n++) minmax[n] = (mpasb_real)h->h_summary[n];
-    const unsigned long long* nan = reinterpret_cast<const unsigned long long*>(h->h_summary + 2 * (2 + S));
+    CUDA_OK(cudaEventSynchronize(h->ev_summary[q]));
+    h->summary_tail++;
+    for (long n = 0; n < n_minmax; n++) minmax[n] = (mpasb_real)h->h_summary[q][n];
+    const unsigned long long* nan = reinterpret_cast<const unsigned long long*>(h->h_summary[q] + 2 * (2 + S));
     if (nan_count) { nan_count[0] = (long)nan[0]; nan_count[1] = (long)nan[1]; }
     return 0;
 }
@@ -986,6 +1185,8 @@ extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
 #define ENTRY(body) { cudaSetDevice(h->device); body; CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
 extern "C" int mpasb_init_coupled_diagnostics(mpasb_handle h) ENTRY(init_coupled_diagnostics(h))
 extern "C" int mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt) ENTRY(compute_solve_diagnostics(h, dt, 1, 0))
+// the same without the host synchronisation: for requests queued back to back (mpasb_set_fields_async ... mpasb_get_fields_async)
+extern "C" int mpasb_init_solve_diagnostics_async(mpasb_handle h, mpasb_real dt) { cudaSetDevice(h->device); compute_solve_diagnostics(h, dt, 1, 0); return 0; }
 extern "C" int mpasb_reconstruct(mpasb_handle h, int time_level, int include_halos) ENTRY(reconstruct(h, time_level, include_halos))
 extern "C" int mpasb_compute_output_diagnostics(mpasb_handle h, int time_level) ENTRY(compute_output_diagnostics(h, time_level))
 extern "C" int mpasb_k_rk_integration_setup(mpasb_handle h) ENTRY(rk_integration_setup(h))

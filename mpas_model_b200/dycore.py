@@ -185,6 +185,36 @@ class Dycore(Backend):
         self._check(self.lib.mpasb_set_field_int(self._h, name.encode(),
                                                  arr.ctypes.data_as(C.c_void_p), C.c_long(arr.size)), f"set_field_int {name}")
 
+    # -- batched, asynchronous transfers (mpasb_set_fields_async / mpasb_get_fields_async)
+    def _batch(self, items):
+        n = len(items)
+        names = (C.c_char_p * n)(*[nm.encode() for nm, _, _ in items])
+        levels = (C.c_int * n)(*[lev for _, lev, _ in items])
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for _, _, a in items])
+        counts = (C.c_long * n)(*[a.size for _, _, a in items])
+        for _, _, a in items:
+            assert a.dtype == self.rdtype and a.flags["C_CONTIGUOUS"]
+        return n, names, levels, ptrs, counts
+
+    def set_fields_async(self, items):
+        """items: [(pool key, time level, host array)].  Enqueue the uploads; the arrays may be reused after wait_uploads()."""
+        n, names, levels, ptrs, counts = self._batch(items)
+        self._check(self.lib.mpasb_set_fields_async(self._h, C.c_int(n), names, levels, ptrs, counts), "set_fields_async")
+
+    def get_fields_async(self, items):
+        """Enqueue the downloads behind everything enqueued so far; the arrays are valid after wait_downloads()."""
+        n, names, levels, ptrs, counts = self._batch(items)
+        self._check(self.lib.mpasb_get_fields_async(self._h, C.c_int(n), names, levels, ptrs, counts), "get_fields_async")
+
+    def wait_uploads(self, lag=0):
+        self._check(self.lib.mpasb_wait_uploads_lag(self._h, C.c_int(lag)), "wait_uploads")
+
+    def wait_downloads(self, lag=0):
+        self._check(self.lib.mpasb_wait_downloads_lag(self._h, C.c_int(lag)), "wait_downloads")
+
+    def atm_init_solve_diagnostics_async(self, dt):
+        self._check(self.lib.mpasb_init_solve_diagnostics_async(self._h, self.creal(dt)), "init_solve_diagnostics_async")
+
     def close(self):
         if self._h:
             self.lib.mpasb_destroy(self._h)

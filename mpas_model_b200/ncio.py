@@ -103,10 +103,12 @@ def read(path, only=None):
             va = r.attrs(); t = r.u32(); vsize = r.nonneg(); begin = r.offset()
             metas.append((nm, dimids, va, t, vsize, begin))
     rec_vars = [m for m in metas if m[1] and m[1][0] == unlimited]
-    recsize = sum(m[4] for m in rec_vars)
-    if len(rec_vars) == 1:                              # a single record variable is not padded
-        m = rec_vars[0]
-        recsize = int(np.prod([dim_len[d] for d in m[1][1:]], dtype=np.int64)) * np.dtype(_TYPES[m[3]]).itemsize
+    # per-record size of each record variable from its dimensions and type, padded to 4 bytes -- NOT from the header's vsize,
+    # which saturates at 2^32-1 in CDF-1/2 for variables of 4 GiB or more per record
+    def _rec_bytes(m):
+        nbytes = int(np.prod([dim_len[d] for d in m[1][1:]], dtype=np.int64)) * np.dtype(_TYPES[m[3]]).itemsize
+        return nbytes if len(rec_vars) == 1 else (nbytes + 3) // 4 * 4          # a single record variable is not padded
+    recsize = sum(_rec_bytes(m) for m in rec_vars)
     if numrecs is None:
         numrecs = (len(buf) - min(m[5] for m in rec_vars)) // recsize if rec_vars else 0
     out = {}
