@@ -152,7 +152,8 @@ def line_common(args, n_cells, n_lev, dt, world):
                                    "upload, init-time diagnostics, the min/max summary (taken once after the loop), H2D/D2H (those are in e2e)"},
         # outside `config` so that both arms print the same config object
         "implementation": "B200 CUDA library (libmpasb.so) through the C ABI" if args.impl != "reference"
-                          else "restated CPU dycore (C++/OpenMP, oracle/), not the Fortran build",
+                          else "the reference's CPU dycore: oracle/_ref (its Fortran source transliterated to C++ and compiled here) at N = 1, "
+                               "the C++/OpenMP restatement (oracle/) for decomposed N > 1 runs; not the gfortran build",
     }
 
 
@@ -170,6 +171,7 @@ def reference_arm(args, rank, world):
     n_cells, n_lev = workload_for(args)
     blocks = None
     extrapolated = False
+    kind = "port"
     if args.gpus > 1:
         # the N-block decomposition itself, every block in this process in lock step with in-process halo exchanges
         # (the oracle's "virtual ranks") -- the whole mesh is stepped, nothing is extrapolated.  Only the 8-block
@@ -192,10 +194,18 @@ def reference_arm(args, rank, world):
                        f"EXTRAPOLATED: block 0 of {args.gpus} only ({rec['block']['nCellsSolve']} owned cells + halo, halo values frozen), rate scaled by 1/{args.gpus}")
     else:
         from mpas_model_b200.case import make_case
+        from oracle import ref as oref
         d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
         frac = 1.0
         sample_what = "the whole mesh"
-        blocks = [OracleDycore(d, cfg)]
+        if oref.build() and not os.environ.get("MPASB_REF_PORT"):
+            # oracle/_ref: the reference's own mpas_atm_time_integration.F, transliterated to C++ at build time (oracle/f2cpp.py),
+            # entered by all host threads with the index ranges and barriers of its MPAS_OPENMP build
+            blocks = [oref.RefDycore(d, cfg, threads=n_threads)]
+            kind = "reference"
+            sample_what += " (reference source transliterated Fortran -> C++, OpenMP threading of mpas_atm_threading.F; without the trailing mpas_reconstruct)"
+        else:
+            blocks = [OracleDycore(d, cfg)]
     dt = cfg["config_dt"]
     multi = len(blocks) > 1
 
@@ -228,7 +238,7 @@ def reference_arm(args, rank, world):
     line = line_common(args, n_cells, n_lev, dt, args.gpus)
     line.update({
         "impl": "reference", "value": v, "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 / sps,
-        "cpu_baseline": {"value": v, "unit": "cell-columns/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": "cell-columns/s", "cores": cores, "kind": kind,
                          "sample": f"{steps} full atm_srk3 steps on {sample_what}", "extrapolated": extrapolated},
         "e2e": {"value": v, "unit": "cell-columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": sps, "sdpd": dt * sps, "cell_columns_per_s": v,

@@ -115,19 +115,14 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
     return flux4_2(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * abs2(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;
 }
 
-// One warp per column, walking columns g, g + G, g + 2G, ... (G = warps of the grid): launched with one warp per column the
-// loop runs once; launched with just the resident blocks (persistent warps, mpasb.cu: LAUNCHW) every warp also asks L2 for the
-// own-column operands of its NEXT column (CW_PF lists, cw_pf / cw_next) while it works on the current one.
 #define CW_SETUP(ncols)                                                                       \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
+    const int i = blockIdx.x * CW_WARPS + wib;                                                \
     const int LDK = D.LDK, nl = D.nl;                                                         \
+    if (i >= (ncols)) return;                                                                 \
     Lv lv; lv.k0 = 2 * lane;                                                                  \
     const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;                             \
-    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);                  \
-    const int cw_stride = gridDim.x * CW_WARPS, cw_n = (ncols);                               \
-    for (int i = blockIdx.x * CW_WARPS + wib; i < cw_n; i += cw_stride) {                     \
-        const int cw_next = i + cw_stride; const bool cw_pf = D.pf_next && cw_next < cw_n; (void)cw_next; (void)cw_pf;
-#define CW_END }
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
 #define LD(p, col) ld2((p), (unsigned)(col) * uLDK + kc)
 #define ST(p, col, v) st2((p), (unsigned)(col) * uLDK + kc, act, (v))
 #define BC(v, src) __shfl_sync(CW_FULL, (v), (src))
@@ -147,7 +142,7 @@ __device__ __forceinline__ void pf2(const real* p, unsigned off) { asm volatile(
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;           // only edges of owned cells are consumed
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;           // only edges of owned cells are consumed
     const int nadv = D.nAdvCellsForEdge[i];
     // one stencil entry per lane: cell index and the two possible weights adv_coefs +/- adv_coefs_3rd
     // (TI:5744-5750: coef + sign(ru) * coef_3rd with sign = +/-1)
@@ -174,7 +169,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
     }
     ST(D.adv_flux_w, i, sel(lv.ge(1) && lv.lt(nl), ruw * fw, 0.0));
     ST(D.adv_flux_theta, i, sel(lv.lt(nl), ruk * ft, 0.0));
-    CW_END
 }
 
 // ---- the same per-edge flux with the stencil columns staged in shared memory by bulk copies (TMA) ----
@@ -633,7 +627,6 @@ __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev
     ST(D.tend_w, i, out_tend_w);
     ST(D.rthdynten, i, out_rthdynten);
     ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
-    CW_END
 }
 
 // ---- the same cell tendency for the relaxed path: horizontal flux divergences from k5_flux_cell, persistent warps ----
@@ -773,7 +766,6 @@ __global__ void __launch_bounds__(CW_THREADS, CF7_MINB) k7_dt_cell_f(const Dev D
 // ~64 registers for 32 resident warps per SM rather than unrolled for more loads in flight (measured).
 __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.rho_edge, cw_next); PF(D.u_2, cw_next); PF(D.pv_edge, cw_next); if (A.rk_step == 1) { PF(D.cqu, cw_next); PF(D.zxu, cw_next); } else { PF(D.tend_u_euler, cw_next); PF(D.tend_ru_physics, cw_next); } }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
     const real invDc = D.invDcEdge[i];
@@ -794,7 +786,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
         tue = tue + rho_e * kdiffu * u_diffusion * D.meshScalingDel2[i];
         ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
     }
-    if (!solve) continue;
+    if (!solve) return;
     const r2 u = LD(D.u_2, i);
     r2 tu;
     {   // vertical transport of u, TI:5391-5408
@@ -825,7 +817,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
          - u * 0.5 * (LD(D.h_divergence, cell1) + LD(D.h_divergence, cell2));
     if (A.rk_step != 1) tu = tu + LD(D.tend_u_euler, i) + LD(D.tend_ru_physics, i);
     ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
-    CW_END
 }
 
 // (an earlier one-warp-per-cell version of the acoustic cell step, with lane 0 sweeping the column out of shared memory --
@@ -837,7 +828,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
     CW_SETUP(D.nCellsSolve)
-    if (cw_pf) { PF(D.tend_w, cw_next); PF(D.zz, cw_next); if (D.zb_any[cw_next]) { for (int e_ = 0; e_ < CW_NE; e_++) { PFZ(D.zb_cell, cw_next, e_); PFZ(D.zb3_cell, cw_next, e_); } } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -863,13 +853,11 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev 
 #undef SML_EDGE
     }
     ST(D.tend_w, i, sel(lv.ge(1) && lv.lt(nl), (fm * zz + fp * up1(zz)) * wt, wt_in));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
 __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     CW_SETUP(D.nCells)
-    if (cw_pf) { PF(D.w_2, cw_next); PF(D.rho_zz_2, cw_next); if (D.zb_any[cw_next]) { for (int e_ = 0; e_ < CW_NE; e_++) { PFZ(D.zb_cell, cw_next, e_); PFZ(D.zb3_cell, cw_next, e_); } } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -897,7 +885,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
     }
     const r2 den = sel(k_eq0, cf1 * rho + cf2 * dn1(rho) + cf3 * dn2(rho), fm * rho + fp * up1(rho));
     ST(D.w_2, i, sel(lv.lt(nl), w / den, w_in));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
@@ -925,7 +912,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
     ST(D.vorticity, i, sel(k_lt_nl, vort, 0.0));
     ST(D.ke_vertex, i, sel(k_lt_nl, (ke0 + ke1 + ke2) * r, 0.0));
     ST(D.pv_vertex, i, sel(k_lt_nl, D.fVertex[i] + vort, 0.0));
-    CW_END
 }
 // (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
@@ -970,13 +956,11 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
     ST(D.divergence, i, sel(k_lt_nl, div * r, 0.0));
     ST(D.ke, i, sel(k_lt_nl, ke, 0.0));
     if (apvm) ST(D.pv_cell, i, sel(k_lt_nl, pvc, 0.0));
-    CW_END
 }
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(u, cw_next); if (!reconstruct_v) PF(D.v, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
@@ -1006,7 +990,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev 
     if (reconstruct_v) ST(D.v, i, sel(k_lt_nl, vv, 0.0));
     if (apvm) { ST(D.gradPVt, i, sel(k_lt_nl, gt, 0.0)); ST(D.gradPVn, i, sel(k_lt_nl, gn, 0.0)); }
     ST(D.pv_edge, i, sel(k_lt_nl, pve, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (a)
@@ -1014,7 +997,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev 
 // Restriction (host falls back to k_dt_cell_a otherwise): config_mpas_cam_coef == 0.
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
-    if (cw_pf) { if (A.rk_step == 1) { PF(D.rw, cw_next); PF(D.qtot, cw_next); PF(D.tend_rho_physics, cw_next); PF(D.rho_base, cw_next); PF(D.rho_p_save, cw_next); } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1055,14 +1037,12 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev 
         ST(D.dpdz, i, sel(k_lt_nl, dpdz, 0.0));
     }
     ST(D.h_divergence, i, sel(k_lt_nl, hd, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
 // rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nCells)
-    if (cw_pf) { PF(D.kdiff, cw_next); PF(D.w_2, cw_next); PF(D.theta_m_2, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1111,7 +1091,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev 
     ST(D.tend_w_euler, i, sel(k_mid, twe, 0.0));
     ST(D.delsq_theta, i, sel(k_lt_nl, dst, 0.0));
     ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_acoustic_step_work, cell part (block-tiled)
@@ -1457,9 +1436,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 // ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
 __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { if (first) PF(D.tend_u, cw_next); else PF(D.ru_p, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const real mask = 1.0 - D.specZoneMaskEdge[i];
     const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
     const r2 divCell2 = -(LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp_old, cell2));
@@ -1470,16 +1448,14 @@ __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D,
     const b2 k_lt_nl = lv.lt(nl);
     if (first) ST(D.ruAvg, i, sel(k_lt_nl, ru_p, 0.0));
     ST(D.ru_p, i, sel(k_lt_nl, ru_p + coef_divdamp * (divCell2 - divCell1) * mask / th, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, parts 1 and 2
 // (1) cell-all, TI:3294-3350 (+ the garbage cell, TI:3282-3284)
 __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const Dev D, real dt, real invNs, int rk_step, real rcv, real rgas_p0) {
     CW_SETUP(D.nCells + 1)
-    if (cw_pf) { PF(D.rho_p_save, cw_next); PF(D.rho_pp, cw_next); PF(D.rho_base, cw_next); PF(D.rtheta_base, cw_next); PF(D.zz, cw_next); PF(D.rw_save, cw_next); PF(D.wwAvg, cw_next); PF(D.rw, cw_next); PF(D.w_2, cw_next); PF(D.rtheta_p_save, cw_next); PF(D.rtheta_pp, cw_next); PF(D.rw_p, cw_next); if (rk_step == 3) { PF(D.rt_diabatic_tend, cw_next); PF(D.exner_base, cw_next); } }
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
-    if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); continue; }
+    if (i == D.nCells) { ST(D.rho_zz_2, i, sel(k_lt_nl, mk2(1.0, 1.0), LD(D.rho_zz_2, i))); return; }
     const r2 rho_p = LD(D.rho_p_save, i) + LD(D.rho_pp, i);
     const r2 rho_zz = rho_p + LD(D.rho_base, i);
     const r2 rtb = LD(D.rtheta_base, i);
@@ -1509,12 +1485,10 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const De
     ST(D.wwAvg, i, sel(k_mid, rw_save + (wwAvg_in * invNs), wwAvg_in));
     ST(D.rw, i, sel(k_mid, rw, sel(k_ends, mk2(0.0, 0.0), rw_in)));
     ST(D.w_2, i, sel(k_mid, rw / (fm * zz + fp * up1(zz)), sel(k_ends, mk2(0.0, 0.0), w_in)));
-    CW_END
 }
 // (2) edge-all, TI:3360-3372
 __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.ru_save, cw_next); PF(D.ru_p, cw_next); PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
     const r2 rus = LD(D.ru_save, i);
@@ -1523,15 +1497,13 @@ __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real 
     ST(D.ruAvg, i, sel(k_lt_nl, rus + (LD(D.ruAvg, i) * invNs), 0.0));
     ST(D.ru, i, sel(k_lt_nl, ru, 0.0));
     ST(D.u_2, i, sel(k_lt_nl, 2. * ru / rho2, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_acoustic_step_work, edge part (small_step > 1)  TI:2751-2796
 __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.cqu, cw_next); PF(D.zxu, cw_next); PF(D.ru_p, cw_next); PF(D.tend_u, cw_next); PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const b2 k_lt_nl = lv.lt(nl);
     r2 pgrad = ((LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp, cell1)) * D.invDcEdge[i]) / (.5 * (LD(D.zz, cell2) + LD(D.zz, cell1)));
     pgrad = LD(D.cqu, i) * 0.5 * c2 * (LD(D.exner, cell1) + LD(D.exner, cell2)) * pgrad;
@@ -1539,7 +1511,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
     const r2 rup = LD(D.ru_p, i) + dts * (LD(D.tend_u, i) - (1.0 - D.specZoneMaskEdge[i]) * pgrad);
     ST(D.ru_p, i, sel(k_lt_nl, rup, 0.0));
     ST(D.ruAvg, i, sel(k_lt_nl, LD(D.ruAvg, i) + rup, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855
@@ -1547,7 +1518,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
 // possible weights per entry live one per lane and are broadcast; scalars are separate level-contiguous planes
 __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.ruAvg, cw_next); }
     const int nadv = D.nAdvCellsForEdge[i];
     int my_c = 0; real my_wp = 0.0, my_wm = 0.0;
     if (lane < nadv) {
@@ -1576,12 +1546,10 @@ __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
         }
         ST(D.horiz_flux_arr + (size_t)s * D.edgePlane, i, sel(k_lt_nl, acc, 0.0));
     }
-    CW_END
 }
 // owned cells: flux divergence + vertical flux + update, TI:3773-3846
 __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
     CW_SETUP(D.nCellsSolve)
-    if (cw_pf) { PF(D.rho_zz, cw_next); PF(D.rho_zz_2, cw_next); PF(D.wwAvg, cw_next); for (int s_ = 0; s_ < D.num_scalars; s_++) { PF(D.scalars_2 + (size_t)s_ * D.cellPlane, cw_next); PF(D.scalars + (size_t)s_ * D.cellPlane, cw_next); } }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1619,7 +1587,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
         ST(D.scalars_tend + (size_t)s * D.cellPlane, i, mk2(0.0, 0.0));
         ST(qn, i, sel(k_lt_nl, val, 0.0));
     }
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_vert_imp_coefs_work  TI:2225-2366 (block-tiled)
@@ -1721,7 +1688,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_vertex(const Dev D) {
 #pragma unroll
     for (int j = 0; j < 3; j++) acc = acc + BC(my_s, j) * LD(D.delsq_u, BC(my_e, j));
     ST(D.delsq_vorticity, i, sel(lv.lt(nl), acc, 0.0));
-    CW_END
 }
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
     CW_SETUP(D.nCells)
@@ -1736,13 +1702,11 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
     for (int e = CW_NE; e < ne; e++) DELSQ_C(e)
 #undef DELSQ_C
     ST(D.delsq_divergence, i, sel(lv.lt(nl), acc, 0.0));
-    CW_END
 }
 // owned edges: del^4 of u (TI:5558-5584) and the final sum (TI:5694-5701).
 // Restrictions (the host falls back to k_dt_edge_d otherwise): v_mom_eddy_visc2 == 0, no Rayleigh damping of u.
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdgesSolve)
-    if (cw_pf) { PF(D.tend_u_euler, cw_next); PF(D.rho_edge, cw_next); PF(D.tend_u, cw_next); PF(D.tend_ru_physics, cw_next); }
     r2 tue = LD(D.tend_u_euler, i);
     if (A.h_mom_eddy_visc4 > 0.0) {
         const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
@@ -1758,7 +1722,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const Dy
     const b2 k_lt_nl = lv.lt(nl);
     ST(D.tend_u_euler, i, sel(k_lt_nl, tue, 0.0));
     ST(D.tend_u, i, sel(k_lt_nl, tu, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, edge part (C2)
@@ -1768,7 +1731,6 @@ __device__ __forceinline__ r2 max0(r2 a) { return mk2(rmax(0.0, a.x), rmax(0.0, 
 __device__ __forceinline__ r2 min0(r2 a) { return mk2(rmin(0.0, a.x), rmin(0.0, a.y)); }
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, real dt) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.ruAvg, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
@@ -1799,7 +1761,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, 
     const b2 k_lt_nl = lv.lt(nl);
     ST(D.flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
     ST(D.flux_tmp, i, sel(k_lt_nl, dt * flux - fup, 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, the other parts
@@ -1808,7 +1769,6 @@ __device__ __forceinline__ r2 min2(r2 a, r2 b) { return mk2(rmin(a.x, b.x), rmin
 // (B) owned cells: re-integrated density, TI:4177-4204
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real dt) {
     CW_SETUP(D.nCellsSolve)
-    if (cw_pf) { PF(D.wwAvg, cw_next); PF(D.rho_zz, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1822,12 +1782,10 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real 
 #undef RHO_INT_EDGE
     const r2 ww = LD(D.wwAvg, i);
     ST(D.rho_zz_int, i, sel(lv.lt(nl), LD(D.rho_zz, i) + dt * (r - LD(D.rdzw, 0) * (dn1(ww) - ww)), 0.0));
-    CW_END
 }
 // (C1) owned cells: vertical fluxes, bounds, vertical part of the upwind update and of scale_arr  TI:4277-4344, 4426-4459
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, real dt, real coef3) {
     CW_SETUP(D.nCellsSolve)
-    if (cw_pf) { PF(D.scalars + (size_t)s * D.cellPlane, cw_next); PF(D.scalars_2 + (size_t)s * D.cellPlane, cw_next); PF(D.wwAvg, cw_next); PF(D.rho_zz, cw_next); }
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
     const int ne = D.nEdgesOnCell[i];
@@ -1859,12 +1817,10 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, 
     ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
     ST(D.scale_arr, i, sel(k_lt_nl, -rdnw * (min0(wd1) - max0(wd0)), 0.0));                     // SCALE_IN
     ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));       // SCALE_OUT
-    CW_END
 }
 // (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
     CW_SETUP(D.nCellsSolve)
-    if (cw_pf) { PF(D.scalar_new, cw_next); PF(D.scale_arr, cw_next); PF(D.scale_arr + D.cellPlane, cw_next); PF(D.s_max, cw_next); PF(D.s_min, cw_next); PF(rho_lim, cw_next); }
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1891,28 +1847,24 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const r
     ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
     ST(D.scale_arr, i, sel(k_lt_nl, min2(splat(1.0), max0(f_in)), 0.0));
     ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, min2(splat(1.0), max0(f_out)), 0.0));
-    CW_END
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
     CW_SETUP(D.nEdges)
-    if (cw_pf) { PF(D.flux_tmp, cw_next); }
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
-    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) continue;
+    if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const real* __restrict__ s_in = D.scale_arr; const real* __restrict__ s_out = D.scale_arr + D.cellPlane;
     const r2 flux = LD(D.flux_tmp, i);
     const r2 f = max0(flux) * min2(LD(s_out, cell1), LD(s_in, cell2))
                + min0(flux) * min2(LD(s_in, cell1), LD(s_out, cell2));
     ST(D.flux_arr, i, sel(lv.lt(nl), f, 0.0));
-    CW_END
 }
 // (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* __restrict__ rho_div) {
     CW_SETUP(D.nCells)
-    if (cw_pf) { PF(D.scale_arr, cw_next); PF(D.scale_arr + D.cellPlane, cw_next); PF(D.wdtn, cw_next); PF(D.scalar_new, cw_next); PF(rho_div, cw_next); }
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
     const b2 k_lt_nl = lv.lt(nl);
-    if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); continue; }       // warp-uniform
+    if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); return; }       // warp-uniform
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1929,7 +1881,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
 #undef MONO5_EDGE
     snew = (snew + (-LD(D.rdzw, 0) * (w1 - w0))) / LD(rho_div, i);
     ST(out, i, sel(k_lt_nl, max0(snew), 0.0));
-    CW_END
 }
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f) split in two
@@ -1991,7 +1942,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FW) k2_dt_cell_fw(const De
         ST(D.tend_w_euler, i, twe);
     }
     ST(D.tend_w, i, sel(k_ge1 && k_lt_nl, tw + twe, 0.0));
-    CW_END
 }
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const Dev D, const DynTendArgs A) {     // tend_theta, TI:5956-6016, 6066-6126, 6134-6197
     CW_SETUP(D.nCellsSolve)
@@ -2055,5 +2005,4 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const De
     if (A.rk_step == 1) ST(D.tend_theta_euler, i, sel(k_lt_nl, tte, 0.0));
     ST(D.rthdynten, i, out_rthdynten);
     ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
-    CW_END
 }

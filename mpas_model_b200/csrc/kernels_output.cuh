@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(CW_THREADS) k2_reconstruct(const Dev D, const 
     ST(D.uReconstructZ, i, sel(k_lt_nl, uz, 0.0));
     ST(D.uReconstructZonal, i, sel(k_lt_nl, uzon, 0.0));
     ST(D.uReconstructMeridional, i, sel(k_lt_nl, umer, 0.0));
-    CW_END
 }
 
 // generic version: one thread per (level, cell), for columns taller than 64 levels

@@ -64,7 +64,6 @@ struct mpasb_handle_s {
     std::vector<int> hc_cellsOnCell, hc_edgesOnCell, hc_nEdgesOnCell;
     std::vector<real> hc_adv_coefs, hc_adv_coefs_3rd;
     bool rings_dirty = true, rings_ok = false;
-    bool persist = true;           // persistent launches of the column-warp kernels (MPASB_PERSIST=0: one warp per column)
     bool relaxed = true;           // re-associated / FMA kernels allowed (parity bar 1e-11, not bit equality); MPASB_STRICT=1 turns it off
     long n_regular = 0;
     bool tiles_dirty = true, tiles_ok = false;
@@ -139,8 +138,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->overlap = !getenv("MPASB_NO_OVERLAP");
     h->relaxed = !mpasb_strict_arithmetic();
     memset(&h->D, 0, sizeof(Dev));
-    if (const char* pe = getenv("MPASB_PERSIST")) h->persist = atoi(pe) != 0;
-    h->D.pf_next = h->persist ? 1 : 0;
+    h->D.pf_next = 1;
     if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
     Dev& D = h->D;
     D.nCells = dims->nCells; D.nEdges = dims->nEdges; D.nVertices = dims->nVertices;
@@ -489,22 +487,7 @@ struct KScope {
     }
 };
 #define LAUNCH(kern, n, smem, ...) do { KScope ks_(h, "k:" #kern); kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
-// Column-warp kernels walk columns with a grid-sized stride.  Persistent launch (default; MPASB_PERSIST=0 launches one warp per
-// column as before): only as many blocks as are resident at once, so every warp handles a sequence of columns and can ask L2
-// for its next column's operands (Dev::pf_next) while it computes the current one.
-static unsigned cw_resident_blocks(H* h, const void* kern) {
-    static std::map<const void*, unsigned> cache;
-    auto it = cache.find(kern);
-    if (it != cache.end()) return it->second;
-    int occ = 0, sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CW_THREADS, 0);
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device);
-    return cache[kern] = (unsigned)std::max(1, occ * sm);
-}
-#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); \
-    unsigned nb_ = (unsigned)(((n) + CW_WARPS - 1) / CW_WARPS); \
-    if (h->persist) nb_ = std::min(nb_, cw_resident_blocks(h, (const void*)kern)); \
-    if (nb_) kern<<<nb_, CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<(unsigned)(((n) + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -756,7 +739,7 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
         if (h->rings_ok) {
             // relaxed arithmetic: one cell-centred sweep computes the horizontal flux divergence of w and theta_m with the
             // two-ring neighbourhood in registers; no per-edge flux arrays, 38 instead of 60 gathered columns per cell
-            static const bool one_field_per_warp = !getenv("MPASB_FLUX_BOTH");
+            static const bool one_field_per_warp = getenv("MPASB_FLUX_SPLIT") != nullptr;      // measured slower: 1.40 vs 0.96 ms/step
             if (one_field_per_warp) {
                 KScope ks_(h, "k:k5s_flux_cell");
                 k5s_flux_cell<<<(unsigned)((2 * (size_t)D.nCellsSolve + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(D);

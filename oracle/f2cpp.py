@@ -42,6 +42,12 @@ def load_statements(path, defines=()):
     text = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
     out, cur = [], ""
     for raw in text.split("\n"):
+        # the OpenMP directives the work routines rely on when several threads run them at once (mpas_atm_threading.F ranges):
+        # kept as statements; every other directive (PARALLEL DO of the callers, OpenACC) is a comment
+        m = re.match(r"^\s*!\$OMP\s+(END\s+MASTER|MASTER|BARRIER)\s*$", raw, re.I)
+        if m and not cur:
+            out.append("__omp_" + re.sub(r"\s+", "_", m.group(1).lower()))
+            continue
         s, q = "", None
         for ch in raw:
             if q:
@@ -904,6 +910,14 @@ class Emitter:
             self.ind -= 1
             o.append(self.line("}"))
             return o
+        if sl == "__omp_barrier":
+            return ["#pragma omp barrier"]
+        if sl == "__omp_master":
+            self.ind += 1
+            return ["#pragma omp master", self.line("{")[4:]]
+        if sl == "__omp_end_master":
+            self.ind -= 1
+            return [self.line("}")]
         if sl == "return":
             return [self.line("return;")]
         if sl == "cycle":

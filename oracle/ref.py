@@ -52,7 +52,7 @@ def build(force=False):
 
 
 class RefDycore(Backend):
-    def __init__(self, block: dict, cfg: dict, precision: str = "double"):
+    def __init__(self, block: dict, cfg: dict, precision: str = "double", threads: int = 1):
         build()
         if not os.path.exists(LIB[precision]):
             raise RuntimeError("oracle/_ref is not built (needs /root/reference at build time)")
@@ -63,6 +63,7 @@ class RefDycore(Backend):
             self.rdtype, self.creal = np.float32, C.c_float
         assert self.lib.ref_real_bytes() == np.dtype(self.rdtype).itemsize
         self.dims = make_dims(block)
+        self.cfg = dict(cfg)
         self._h = C.c_void_p(self.lib.ref_create())
         d = self.dims
         for n in ("nCells", "nEdges", "nVertices", "nCellsSolve", "nEdgesSolve", "nVerticesSolve", "nVertLevels", "maxEdges",
@@ -98,6 +99,11 @@ class RefDycore(Backend):
                 self.extra[("mesh", k)][...] = block[k]
         self._bind_all()
         self.load_block(block)
+        self.set_threads(threads)
+
+    def set_threads(self, n: int):
+        """OpenMP threads, each with the index ranges of mpas_atm_threading.F:100-111 (the reference's MPAS_OPENMP build)."""
+        self.lib.ref_set_threads(self._h, C.c_int(int(n)))
 
     def _bind(self, pool, key, lev, arr):
         shp = arr.shape[::-1]                  # numpy C order -> Fortran extents, fastest first
@@ -139,6 +145,50 @@ class RefDycore(Backend):
         ra = (C.c_double * 4)(*([a for a in args if isinstance(a, float)] + [0.0] * 4)[:4])
         rc = self.lib.ref_call(self._h, routine.encode(), ia, ra)
         assert rc == 0, routine
+
+    def atm_srk3(self, dt, itimestep=1):
+        """The routines of one step in atm_srk3's order (TI:1066-1611, single block: the halo exchanges are no-ops).  The
+        order is the hand-written part; every routine is the reference's own.  The step's trailing mpas_reconstruct
+        (TI:1606, another source file) is not part of the transliteration."""
+        cfg = self.cfg
+        split = cfg["config_dynamics_split_steps"] if cfg["config_split_dynamics_transport"] else 1
+        dt_dyn = dt / float(split)
+        nss = cfg["config_number_of_sub_steps"]
+        order = cfg["config_time_integration_order"]
+        if order == 3:                                                        # TI:1010-1038
+            rk_t = [dt_dyn / 3.0, dt_dyn / 2.0, dt_dyn]; rk_s = [dt_dyn / 3.0, dt_dyn / float(nss), dt_dyn / float(nss)]
+            n_sub = [1, max(1, nss // 2), nss]
+        else:
+            rk_t = [dt_dyn / 2.0, dt_dyn / 2.0, dt_dyn]; rk_s = [dt_dyn / float(nss)] * 3
+            n_sub = [max(1, nss // 2), max(1, nss // 2), nss]
+        coupled = cfg["config_scalar_advection"] and not cfg["config_split_dynamics_transport"]
+
+        def scalars(rk, dt_rk):                                               # advance_scalars, TI:1730-1927
+            if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
+                self.k("advance_scalars", dt_rk, rk)
+            else:
+                self.k("advance_scalars_mono", dt_rk)
+
+        for n in ("tend_ru_physics", "tend_rtheta_physics", "tend_rho_physics"):     # TI:1091-1093 (no physics)
+            self.a[(n, 1)][...] = 0.0
+        self.k("rk_integration_setup"); self.k("compute_moist_coefficients")
+        for ds in range(1, split + 1):
+            self.k("compute_vert_imp_coefs", rk_s[0])
+            for rk in (1, 2, 3):
+                if order == 3 and rk == 2:
+                    self.k("compute_vert_imp_coefs", rk_s[rk - 1])
+                self.k("compute_dyn_tend", rk, float(dt)); self.k("set_smlstep_pert_variables")
+                for ss in range(1, n_sub[rk - 1] + 1):
+                    self.k("advance_acoustic_step", rk_s[rk - 1], ss); self.k("divergence_damping_3d", rk_s[rk - 1])
+                self.k("recover_large_step_variables", rk_t[rk - 1], n_sub[rk - 1], rk)
+                if coupled:
+                    scalars(rk, rk_t[rk - 1])
+                self.k("compute_solve_diagnostics", float(dt), rk)
+            self.k("rk_dynamics_substep_finish", ds, split)
+        if cfg["config_scalar_advection"] and not coupled:
+            rk_t = [dt / 2.0 if order == 2 else dt / 3.0, dt / 2.0, float(dt)]
+            for rk in (1, 2, 3):
+                scalars(rk, rk_t[rk - 1])
 
     def atm_init_coupled_diagnostics(self): self.k("init_coupled_diagnostics")
     def atm_init_solve_diagnostics(self, dt): self.k("init_solve_diagnostics", float(dt))

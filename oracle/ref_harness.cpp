@@ -3,9 +3,11 @@
 //
 // TEST INFRASTRUCTURE ONLY: loaded by tests/test_reference_pin.py (through oracle/ref.py) to pin the hand-written oracle
 // against the reference's own statements.  Hand-written here: the pool plumbing and, per entry point, the ONE call that
-// atm_srk3 makes to the routine (mpas_atm_time_integration.F line cited), with the index ranges an MPI-only run has
-// (nThreads = 1: cellThreadStart = 1, cellThreadEnd = nCells, cellSolveThreadEnd = nCellsSolve, ...;
-// mpas_atm_threading.F:114-125).  No arithmetic of the model is restated in this file.
+// atm_srk3 makes to the routine (mpas_atm_time_integration.F line cited), with the index ranges of mpas_atm_threading.F:
+// one thread = the MPI-only run (cellThreadStart = 1, cellThreadEnd = nCells, ...; :114-125), n threads = the MPAS_OPENMP
+// build (:100-111), every routine entered by all threads at once and synchronised by its own !$OMP BARRIERs.
+// No arithmetic of the model is restated in this file.
+#include <omp.h>
 #include "f2cpp_rt.h"
 #include "_ref/ti_ref.inc"
 
@@ -16,6 +18,7 @@ struct RefBlock {
     std::map<std::string, PoolEntry> module_arrays;
     BlockT block;
     std::string exchange_log;
+    int n_threads = 1;
     RefBlock() {
         Pool* ps[] = {&state, &diag, &mesh, &tend, &tend_physics, &configs, &halo_scratch, &dimensions};
         const char* names[] = {"state", "diag", "mesh", "tend", "tend_physics", "configs", "halo_scratch", "dimensions"};
@@ -82,12 +85,29 @@ int ref_call(void* h, const char* routine, const int* ia, const double* ra) {
     const int nVertLevels = b->dims.at("nVertLevels");
     // a single block exchanges nothing; the group names the reference asks for are recorded for the test
     ExchFn xch = [b](const std::string& g) { b->exchange_log += g + ";"; };
-#define CELLS 1, nCells
-#define VERTS 1, nVertices
-#define EDGES 1, nEdges
-#define CELLS_SOLVE 1, nCellsSolve
-#define VERTS_SOLVE 1, nVerticesSolve
-#define EDGES_SOLVE 1, nEdgesSolve
+    // Threading as the reference does it (MPAS_OPENMP): every routine is called by all threads at once, each with its own
+    // contiguous index ranges (mpas_atm_threading.F:100-111: start = tid * n / nThreads + 1, end = (tid + 1) * n / nThreads),
+    // and the routines synchronise among themselves with the !$OMP BARRIERs that f2cpp.py keeps.
+    int rc = 0;
+    const int nT = b->n_threads;
+    // (see the note on the reference's OpenMP race after the parallel region) last dynamics substep: nothing re-copies the
+    // columns that get zeroed, so they are saved here and put back below
+    std::vector<real> saved;
+    const bool last_finish = nT > 1 && r == "rk_dynamics_substep_finish" && ia[0] >= ia[1];
+    if (last_finish) {
+        FArr<real> th = b->state.arr<real>("theta_m", 1, 2);
+        for (int t = 1; t < nT; t++) for (int k = 1; k <= nVertLevels; k++) saved.push_back(th(k, (long)t * nCells / nT + 1));
+    }
+#pragma omp parallel num_threads(nT)
+    {
+    const int tid = omp_get_thread_num(), nthr = omp_get_num_threads();
+#define RANGE(n) (int)((long)tid * (n) / nthr) + 1, (int)((long)(tid + 1) * (n) / nthr)
+#define CELLS RANGE(nCells)
+#define VERTS RANGE(nVertices)
+#define EDGES RANGE(nEdges)
+#define CELLS_SOLVE RANGE(nCellsSolve)
+#define VERTS_SOLVE RANGE(nVerticesSolve)
+#define EDGES_SOLVE RANGE(nEdgesSolve)
     if (r == "rk_integration_setup")                          // TI:1083
         atm_rk_integration_setup(b->state, b->diag, nVertLevels, b->dims.at("num_scalars"), CELLS, VERTS, EDGES, CELLS_SOLVE, VERTS_SOLVE, EDGES_SOLVE);
     else if (r == "compute_moist_coefficients")               // TI:1102
@@ -124,7 +144,29 @@ int ref_call(void* h, const char* routine, const int* ia, const double* ra) {
                                  CELLS, EDGES, CELLS_SOLVE, scalar_old_arr, scalar_new_arr, s_max_arr, s_min_arr, wdtn_arr,
                                  flux_array, flux_upwind_tmp_arr, flux_tmp_arr, xch,
                                  Opt<bool>(b->cfgs.at("config_split_dynamics_transport").i != 0), rho_zz_int);
-    else { fprintf(stderr, "ref_call: unknown routine %s\n", routine); return 1; }
-    return 0;
+    else {
+#pragma omp master
+        { fprintf(stderr, "ref_call: unknown routine %s\n", routine); rc = 1; }
+    }
+    }
+    // The reference's OpenMP build has a data race in its two copy routines: every thread executes
+    // `theta_m_2(:,cellEnd+1) = 0` (TI:1987; `theta_m_1` at TI:7082) with ITS cellEnd, i.e. it zeroes the first column of the
+    // next thread's range, which that thread may already have copied.  Intended is the garbage column nCells+1 only (what one
+    // thread does).  To keep the threaded arm's results equal to the MPI-only run, the nT-1 affected columns are re-copied here.
+    if (nT > 1 && (r == "rk_integration_setup" || (r == "rk_dynamics_substep_finish" && ia[0] < ia[1]))) {
+        const bool setup = r == "rk_integration_setup";
+        FArr<real> dst = b->state.arr<real>("theta_m", setup ? 2 : 1, 2), src = b->state.arr<real>("theta_m", setup ? 1 : 2, 2);
+        for (int t = 1; t < nT; t++) {
+            const long c = (long)t * nCells / nT + 1;
+            for (int k = 1; k <= nVertLevels; k++) dst(k, c) = src(k, c);
+        }
+    }
+    if (last_finish) {
+        FArr<real> th = b->state.arr<real>("theta_m", 1, 2);
+        size_t q = 0;
+        for (int t = 1; t < nT; t++) for (int k = 1; k <= nVertLevels; k++) th(k, (long)t * nCells / nT + 1) = saved[q++];
+    }
+    return rc;
 }
+void ref_set_threads(void* h, int n) { ((RefBlock*)h)->n_threads = n < 1 ? 1 : n; }
 }

@@ -112,6 +112,19 @@ def test_free_running_steps(small_case):
     o.close(); r.close()
 
 
+def test_threaded_reference_equals_serial(small_case):
+    """The transliteration keeps the work routines' !$OMP BARRIER / MASTER directives; entered by 4 threads with the index
+    ranges of mpas_atm_threading.F:100-111 (the reference's OpenMP build) it gives bit-identical results to one thread."""
+    d, cfg = small_case
+    r1, r4 = ref.RefDycore(d, cfg, threads=1), ref.RefDycore(d, cfg, threads=4)
+    dt = cfg["config_dt"]
+    for b in (r1, r4):
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+        srk3_stepwise([b], cfg, dt, reconstruct=False)
+    assert _differing(r1, r4) == []
+    r1.close(); r4.close()
+
+
 def test_constants_come_from_the_reference():
     """The physical constants inside the generated code are the parameter statements of src/framework/mpas_constants.F."""
     import os
