@@ -503,7 +503,9 @@ def main():
         "parity_rel_l2": parity["parity_rel_l2"] if parity else None,
         "steps_per_s": steps_per_s, "sdpd": dt * steps_per_s, "cell_columns_per_s": value,
         "minmax_w_u": list(minmax),
-        "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])[:14]},
+        "kernel_ms_per_step": {k[2:]: round(v[0] / nprof, 4) for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])},
+        "kernel_launches_per_step": {k[2:]: v[1] // nprof for k, v in sorted(krows.items(), key=lambda kv: -kv[1][0])},
+        "kernel_ms_sum": round(ksum / nprof, 4),
     })
     print(json.dumps(line))
 

@@ -650,7 +650,8 @@ __device__ __forceinline__ CfConn cf_conn(const Dev& D, int i, int lane, bool rk
 #ifndef CF7_MINB
 #define CF7_MINB 2
 #endif
-__global__ void __launch_bounds__(CW_THREADS, CF7_MINB) k7_dt_cell_f(const Dev D, const DynTendArgs A) {
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, const DynTendArgs A) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     Lv lv; lv.k0 = 2 * lane;
@@ -661,10 +662,12 @@ __global__ void __launch_bounds__(CW_THREADS, CF7_MINB) k7_dt_cell_f(const Dev D
     const b2 k_ge1 = lv.ge(1), k_lt_nl = lv.lt(nl);
     const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
     const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
-    const int G = gridDim.x * CW_WARPS;
-    int i = blockIdx.x * CW_WARPS + wib;
+    const int G = gridDim.x * WARPS;
+    int i = blockIdx.x * WARPS + wib;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
+    CfConn cn2 = cn;
     if (i < D.nCellsSolve) cn = cf_conn(D, i, lane, rk1);
+    if (i + G < D.nCellsSolve) cn2 = cf_conn(D, i + G, lane, rk1);
     for (; i < D.nCellsSolve; i += G) {
         const int ne = cn.ne, my_e = cn.e, my_c1 = cn.c1, my_c2 = cn.c2;
         const real my_sgn = cn.sgn, my_dv = cn.dv, my_d4 = cn.d4, my_idc = cn.idc, invArea = cn.invArea;
@@ -711,10 +714,19 @@ __global__ void __launch_bounds__(CW_THREADS, CF7_MINB) k7_dt_cell_f(const Dev D
             }
 #undef CF7_DEL4
         }
+        const CfConn cn_next = cn2;
+        if (i + 2 * G < D.nCellsSolve) cn2 = cf_conn(D, i + 2 * G, lane, rk1);          // behind this cell's requests
         if (i + G < D.nCellsSolve) {
-            cn = cf_conn(D, i + G, lane, rk1);          // next cell's connectivity, behind this cell's requests
+            cn = cn_next;
             if (D.pf_next) {
                 const int j = i + G;
+                if (D.pf_next > 1) {
+#pragma unroll
+                    for (int e = 0; e < CW_NE; e++) {
+                        if (rk1) { PF(D.delsq_w, BC(cn.c1, e)); PF(D.delsq_w, BC(cn.c2, e)); PF(D.delsq_theta, BC(cn.c1, e)); PF(D.delsq_theta, BC(cn.c2, e)); }
+                        else { PF(D.ru_save, BC(cn.e, e)); PF(D.ru, BC(cn.e, e)); PF(D.theta_m, BC(cn.c1, e)); PF(D.theta_m, BC(cn.c2, e)); }
+                    }
+                }
                 PF(D.hdiv_w, j); PF(D.hdiv_theta, j); PF(D.tend_w_euler, j); PF(D.tend_theta_euler, j); PF(D.rw, j); PF(D.w_2, j);
                 PF(D.theta_m_2, j); PF(D.theta_m, j); PF(D.rw_save, j); PF(D.rho_zz_2, j); PF(D.tend_rho, j); PF(D.rt_diabatic_tend, j);
                 PF(D.tend_rtheta_physics, j);
@@ -1319,7 +1331,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     const int G = gridDim.x * WARPS;
     int i = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
+    Ac6Conn cn2 = cn;                                    // connectivity of the cell after next: lets the next cell's GATHERS be prefetched too
     if (i < D.nCellsSolve) cn = ac6_conn(D, i, lane, dts);
+    if (i + G < D.nCellsSolve) cn2 = ac6_conn(D, i + G, lane, dts);
     for (; i < D.nCells; i += G) {
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
@@ -1356,10 +1370,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 #undef AC6_EDGE
     // operands of the part after the solve: issued here so that they are in flight during the solve
     const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
+    const Ac6Conn cn_cur_next = cn2;
+    if (i + 2 * G < D.nCellsSolve) cn2 = ac6_conn(D, i + 2 * G, lane, dts);      // in flight with this cell's columns
     if (i + G < D.nCellsSolve) {
-        cn = ac6_conn(D, i + G, lane, dts);          // next cell's connectivity, in flight with this cell's columns
-        if (D.pf_next) {                             // and its own-column operands on their way into L2
+        cn = cn_cur_next;
+        if (D.pf_next) {                             // the next cell's operands on their way into L2: own columns and gathers
             const int j = i + G;
+            if (D.pf_next > 1) {
+#pragma unroll
+                for (int e = 0; e < CW_NE; e++) { PF(D.theta_m, BC(cn.oth, e)); PF(first ? D.tend_u : D.ru_p, BC(cn.e, e)); }
+            }
             PF(D.tend_rho, j); PF(D.tend_theta, j); PF(D.tend_w, j); PF(D.coftz, j); PF(D.cofwz, j); PF(D.cofwr, j); PF(D.cofwt, j);
             PF(D.zz, j); PF(D.a_tri, j); PF(D.alpha_tri, j); PF(D.gamma_tri, j); PF(D.theta_m, j); PF(D.dss, j); PF(D.rw_save, j);
             PF(D.rw, j); PF(D.rho_zz_2, j); PF(D.w_2, j);
@@ -1487,30 +1507,51 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const De
     ST(D.w_2, i, sel(k_mid, rw / (fm * zz + fp * up1(zz)), sel(k_ends, mk2(0.0, 0.0), w_in)));
 }
 // (2) edge-all, TI:3360-3372
-__global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs) {
+// dd_mode != 0: the divergence damping of the last small step (TI:3040-3060) has not been applied to ru_p yet and is applied
+// here on the fly (1: ru_p holds the undamped value; 2: first small step, ru_p = ruAvg = dts * tend_u was never stored either).
+// Single block only: with halos the damped ru_p must exist before the exchange of TI:1322.
+__device__ __forceinline__ r2 dd_term(const Dev& D, int cell1, int cell2, int i, real coef_divdamp, unsigned uLDK, unsigned kc) {
+    const real mask = 1.0 - D.specZoneMaskEdge[i];
+    const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
+    const r2 divCell2 = -(LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp_old, cell2));
+    const r2 th = LD(D.theta_m, cell1) + LD(D.theta_m, cell2);
+    return coef_divdamp * (divCell2 - divCell1) * mask / th;
+}
+__global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs, int dd_mode, real coef_divdamp, real dts) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
     const r2 rus = LD(D.ru_save, i);
-    const r2 ru = rus + LD(D.ru_p, i);
+    r2 ru_p, ruAvg;
+    if (dd_mode == 2) { ru_p = dts * LD(D.tend_u, i); ruAvg = sel(k_lt_nl, ru_p, 0.0); }
+    else { ru_p = LD(D.ru_p, i); ruAvg = LD(D.ruAvg, i); }
+    if (dd_mode) ru_p = sel(k_lt_nl, ru_p + dd_term(D, cell1, cell2, i, coef_divdamp, uLDK, kc), 0.0);
+    const r2 ru = rus + ru_p;
     const r2 rho2 = LD(D.rho_zz_2, cell1) + LD(D.rho_zz_2, cell2);
-    ST(D.ruAvg, i, sel(k_lt_nl, rus + (LD(D.ruAvg, i) * invNs), 0.0));
+    ST(D.ruAvg, i, sel(k_lt_nl, rus + (ruAvg * invNs), 0.0));
     ST(D.ru, i, sel(k_lt_nl, ru, 0.0));
     ST(D.u_2, i, sel(k_lt_nl, 2. * ru / rho2, 0.0));
 }
 
 // ------------------------------------------------------------------ atm_advance_acoustic_step_work, edge part (small_step > 1)  TI:2751-2796
-__global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2) {
+// dd_mode != 0: the divergence damping of the PREVIOUS small step is applied first, in registers (see k2_recover_edge): the
+// separate damping kernel between two small steps disappears (its operands rtheta_pp, theta_m are gathered here anyway)
+__global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2, int dd_mode, real coef_divdamp) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const b2 k_lt_nl = lv.lt(nl);
+    const r2 tend_u = LD(D.tend_u, i);
+    r2 ru_p, ruAvg;
+    if (dd_mode == 2) { ru_p = dts * tend_u; ruAvg = sel(k_lt_nl, ru_p, 0.0); }
+    else { ru_p = LD(D.ru_p, i); ruAvg = LD(D.ruAvg, i); }
+    if (dd_mode) ru_p = sel(k_lt_nl, ru_p + dd_term(D, cell1, cell2, i, coef_divdamp, uLDK, kc), 0.0);
     r2 pgrad = ((LD(D.rtheta_pp, cell2) - LD(D.rtheta_pp, cell1)) * D.invDcEdge[i]) / (.5 * (LD(D.zz, cell2) + LD(D.zz, cell1)));
     pgrad = LD(D.cqu, i) * 0.5 * c2 * (LD(D.exner, cell1) + LD(D.exner, cell2)) * pgrad;
     pgrad = pgrad + 0.5 * LD(D.zxu, i) * GRAVITY * (LD(D.rho_pp, cell1) + LD(D.rho_pp, cell2));
-    const r2 rup = LD(D.ru_p, i) + dts * (LD(D.tend_u, i) - (1.0 - D.specZoneMaskEdge[i]) * pgrad);
+    const r2 rup = ru_p + dts * (tend_u - (1.0 - D.specZoneMaskEdge[i]) * pgrad);
     ST(D.ru_p, i, sel(k_lt_nl, rup, 0.0));
-    ST(D.ruAvg, i, sel(k_lt_nl, LD(D.ruAvg, i) + rup, 0.0));
+    ST(D.ruAvg, i, sel(k_lt_nl, ruAvg + rup, 0.0));
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855

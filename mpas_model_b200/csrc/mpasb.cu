@@ -54,6 +54,9 @@ struct mpasb_handle_s {
     int max_ne = 0;                // max(nEdgesOnCell), known once the mesh is uploaded
     bool zb_dirty = true;          // zb_any must be recomputed before the next step
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
+    bool dd_deferred = false;      // divergence damping of the last small step still to be applied (by the next edge kernel)
+    real dd_coef = 0.0, dd_dts = 0.0;
+    bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
@@ -137,6 +140,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
     h->overlap = !getenv("MPASB_NO_OVERLAP");
     h->relaxed = !mpasb_strict_arithmetic();
+    h->fuse_dd = !getenv("MPASB_NO_DD_FUSE");
     memset(&h->D, 0, sizeof(Dev));
     h->D.pf_next = 1;
     if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
@@ -757,9 +761,13 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
             else {
                 static int sm_count = 0;
                 if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
-                const unsigned need = (unsigned)((D.nCellsSolve + CW_WARPS - 1) / CW_WARPS), resident = (unsigned)(sm_count * CF7_MINB);
+                static const int variant = getenv("MPASB_CF7") ? atoi(getenv("MPASB_CF7")) : 0;
                 KScope ks_(h, "k:k7_dt_cell_f");
-                k7_dt_cell_f<<<std::min(need, resident), CW_THREADS, 0, h->stream>>>(D, A);      // persistent warps
+#define CF7_LAUNCH(W, MB) do { const unsigned need = (unsigned)((D.nCellsSolve + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
+                    k7_dt_cell_f<W, MB><<<std::min(need, resident), (W) * 32, 0, h->stream>>>(D, A); } while (0)
+                if (variant == 1) CF7_LAUNCH(4, 3);            // 168 registers, 12 warps per SM
+                else CF7_LAUNCH(8, 2);                         // 128 registers, 16 warps per SM
+#undef CF7_LAUNCH
                 h->launches++;
             }
         } else {
@@ -800,7 +808,11 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
         // first small step: ru_p = dts * tend_u is evaluated on the fly by the cell kernel and written by the
         // following divergence-damping kernel (h->ru_p_pending), saving one pass over three edge arrays
         if (small_step == 1) h->ru_p_pending = true;
-        else LAUNCHW(k2_acoustic_edge, h->D.nEdges, h->D, dts, c2);
+        else {
+            const int dd_mode = h->dd_deferred ? (h->ru_p_pending ? 2 : 1) : 0;
+            LAUNCHW(k2_acoustic_edge, h->D.nEdges, h->D, dts, c2, dd_mode, h->dd_coef);
+            h->dd_deferred = false; h->ru_p_pending = false;
+        }
         static const bool no_scan = getenv("MPASB_NO_SCAN") != nullptr;
         if (h->relaxed && !no_scan) {       // the column solve as a warp-level prefix of affine maps: one warp per column, registers only
             static int sm_count = 0;
@@ -827,10 +839,13 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
 }
-static void divergence_damping_3d(H* h, real dts) {           // TI:2987-3075
+// defer: the next kernel that reads ru_p (the edge update of the next small step, or -- single block -- the edge part of
+// recover_large_step_variables) applies the damping in registers; same arithmetic, one kernel and one ru_p round trip less
+static void divergence_damping_3d(H* h, real dts, bool defer = false) {           // TI:2987-3075
     Scope sc(h, "atm_divergence_damping_3d");
     const real rdts = 1.0 / dts;
     const real coef_divdamp = 2.0 * h->cfg.config_smdiv * h->cfg.config_len_disp * rdts;
+    if (h->colwarp && defer && h->fuse_dd) { h->dd_deferred = true; h->dd_coef = coef_divdamp; h->dd_dts = dts; return; }
     if (h->colwarp) {
         LAUNCHW(k2_divergence_damping, h->D.nEdges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts);
         h->ru_p_pending = false;
@@ -848,7 +863,11 @@ static int recover_large_step_variables(H* h, real dt, int ns, int rk_step, bool
     refresh_zb_flags(h);
     if (h->colwarp) {
         LAUNCHW(k2_recover_cell1, h->D.nCells + 1, h->D, dt, invNs, rk_step, rcv, rgas / p0);
-        LAUNCHW(k2_recover_edge, h->D.nEdges, h->D, invNs);
+        {
+            const int dd_mode = h->dd_deferred ? (h->ru_p_pending ? 2 : 1) : 0;
+            LAUNCHW(k2_recover_edge, h->D.nEdges, h->D, invNs, dd_mode, h->dd_coef, h->dd_dts);
+            h->dd_deferred = false; h->ru_p_pending = false;
+        }
     } else {
         LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
         LAUNCH(k_recover_edge, h->D.nEdges, 0, h->D, invNs);
@@ -1050,7 +1069,8 @@ static int srk3(H* h, real dt) {
                 advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step);
                 const bool more = small_step < number_sub_steps[rk_step];
                 if (exchange(h, more ? "dynamics:rtheta_pp,rho_pp" : "dynamics:rtheta_pp")) return 1;
-                divergence_damping_3d(h, rk_sub_timestep[rk_step]);
+                // (more small steps follow, or nothing exchanges ru_p: the damping is folded into the next edge kernel)
+                divergence_damping_3d(h, rk_sub_timestep[rk_step], more || !h->halo.active);
             }
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
             if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, true)) return 1;   // starts u_3 (TI:1371)
