@@ -665,9 +665,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     const int G = gridDim.x * WARPS;
     int i = blockIdx.x * WARPS + wib;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
-    CfConn cn2 = cn;
     if (i < D.nCellsSolve) cn = cf_conn(D, i, lane, rk1);
-    if (i + G < D.nCellsSolve) cn2 = cf_conn(D, i + G, lane, rk1);
     for (; i < D.nCellsSolve; i += G) {
         const int ne = cn.ne, my_e = cn.e, my_c1 = cn.c1, my_c2 = cn.c2;
         const real my_sgn = cn.sgn, my_dv = cn.dv, my_d4 = cn.d4, my_idc = cn.idc, invArea = cn.invArea;
@@ -714,19 +712,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
             }
 #undef CF7_DEL4
         }
-        const CfConn cn_next = cn2;
-        if (i + 2 * G < D.nCellsSolve) cn2 = cf_conn(D, i + 2 * G, lane, rk1);          // behind this cell's requests
         if (i + G < D.nCellsSolve) {
-            cn = cn_next;
+            cn = cf_conn(D, i + G, lane, rk1);          // next cell's connectivity, behind this cell's requests
             if (D.pf_next) {
                 const int j = i + G;
-                if (D.pf_next > 1) {
-#pragma unroll
-                    for (int e = 0; e < CW_NE; e++) {
-                        if (rk1) { PF(D.delsq_w, BC(cn.c1, e)); PF(D.delsq_w, BC(cn.c2, e)); PF(D.delsq_theta, BC(cn.c1, e)); PF(D.delsq_theta, BC(cn.c2, e)); }
-                        else { PF(D.ru_save, BC(cn.e, e)); PF(D.ru, BC(cn.e, e)); PF(D.theta_m, BC(cn.c1, e)); PF(D.theta_m, BC(cn.c2, e)); }
-                    }
-                }
                 PF(D.hdiv_w, j); PF(D.hdiv_theta, j); PF(D.tend_w_euler, j); PF(D.tend_theta_euler, j); PF(D.rw, j); PF(D.w_2, j);
                 PF(D.theta_m_2, j); PF(D.theta_m, j); PF(D.rw_save, j); PF(D.rho_zz_2, j); PF(D.tend_rho, j); PF(D.rt_diabatic_tend, j);
                 PF(D.tend_rtheta_physics, j);
@@ -1331,9 +1320,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     const int G = gridDim.x * WARPS;
     int i = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
-    Ac6Conn cn2 = cn;                                    // connectivity of the cell after next: lets the next cell's GATHERS be prefetched too
     if (i < D.nCellsSolve) cn = ac6_conn(D, i, lane, dts);
-    if (i + G < D.nCellsSolve) cn2 = ac6_conn(D, i + G, lane, dts);
     for (; i < D.nCells; i += G) {
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
@@ -1370,16 +1357,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 #undef AC6_EDGE
     // operands of the part after the solve: issued here so that they are in flight during the solve
     const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
-    const Ac6Conn cn_cur_next = cn2;
-    if (i + 2 * G < D.nCellsSolve) cn2 = ac6_conn(D, i + 2 * G, lane, dts);      // in flight with this cell's columns
     if (i + G < D.nCellsSolve) {
-        cn = cn_cur_next;
-        if (D.pf_next) {                             // the next cell's operands on their way into L2: own columns and gathers
+        cn = ac6_conn(D, i + G, lane, dts);          // next cell's connectivity, in flight with this cell's columns
+        if (D.pf_next) {                             // and its own-column operands on their way into L2
             const int j = i + G;
-            if (D.pf_next > 1) {
-#pragma unroll
-                for (int e = 0; e < CW_NE; e++) { PF(D.theta_m, BC(cn.oth, e)); PF(first ? D.tend_u : D.ru_p, BC(cn.e, e)); }
-            }
             PF(D.tend_rho, j); PF(D.tend_theta, j); PF(D.tend_w, j); PF(D.coftz, j); PF(D.cofwz, j); PF(D.cofwr, j); PF(D.cofwt, j);
             PF(D.zz, j); PF(D.a_tri, j); PF(D.alpha_tri, j); PF(D.gamma_tri, j); PF(D.theta_m, j); PF(D.dss, j); PF(D.rw_save, j);
             PF(D.rw, j); PF(D.rho_zz_2, j); PF(D.w_2, j);

@@ -766,7 +766,21 @@ class Emitter:
             s = self.sym(n)
             if s is not None and s.rank:
                 if any(a[0] == "section" for a in e[2]):
-                    raise SyntaxError(f"{self.r.name}: array section of {n} inside an expression")
+                    # conformable section on the right-hand side of an array assignment: its k-th sectioned dimension runs with
+                    # the k-th loop of the assignment (F2003 7.4.1.3), offset by the two lower bounds
+                    loops = getattr(self, "section_loops", None)
+                    if not loops:
+                        raise SyntaxError(f"{self.r.name}: array section of {n} outside an array assignment")
+                    idx, kth = [], 0
+                    for d, a in enumerate(e[2]):
+                        if a[0] == "section":
+                            v, lo_l = loops[kth]
+                            kth += 1
+                            lo_r = self.ex(a[1]) if a[1] is not None else f"{cname(n)}.lo[{d}]"
+                            idx.append(f"({lo_r} + ({v} - ({lo_l})))")
+                        else:
+                            idx.append(self.ex(a))
+                    return f"{cname(n)}(" + ", ".join(idx) + ")"
                 return f"{cname(n)}(" + ", ".join(self.ex(a) for a in e[2]) + ")"
             if s is not None and s.stmt_fn:
                 return f"{cname(n)}(" + ", ".join(self.ex(a) for a in e[2]) + ")"
@@ -961,17 +975,21 @@ class Emitter:
             # a(:, i) = scalar expression  ->  loops over the sectioned dimensions
             n = lhs[1][1]
             s = self.sym(n)
-            o, idx = [], []
-            for d, a in enumerate(lhs[2]):
+            o, idx, loops = [], [], []
+            # Fortran evaluates the whole right-hand side before storing; the loops below store as they go, which is the same
+            # unless the right-hand side reads OTHER elements of the array being assigned -- none of the statements here does
+            for d, a in reversed(list(enumerate(lhs[2]))):          # outermost loop = last dimension (column-major order)
                 if a[0] == "section":
                     v = f"i{d}__"
                     lo = self.ex(a[1]) if a[1] is not None else f"{cname(n)}.lo[{d}]"
                     hi = self.ex(a[2]) if a[2] is not None else f"({cname(n)}.lo[{d}] + {cname(n)}.n[{d}] - 1)"
                     o.append(self.line(f"for (long {v} = {lo}; {v} <= {hi}; {v}++)"))
-                    idx.append(v)
-                else:
-                    idx.append(self.ex(a))
+                    loops.insert(0, (v, lo))
+            for d, a in enumerate(lhs[2]):
+                idx.append(f"i{d}__" if a[0] == "section" else self.ex(a))
+            self.section_loops = loops
             o.append(self.line(f"    {cname(n)}({', '.join(idx)}) = {self.ex(rhs)};"))
+            self.section_loops = None
             return o
         return [self.line(f"{self.ex(lhs)} = {self.ex(rhs)};")]
 
@@ -1048,6 +1066,10 @@ TI_ROUTINES = [
 ]
 
 
+CORE_ROUTINES = ["atm_compute_mesh_scaling", "atm_compute_signs", "atm_compute_damping_coefs", "atm_adv_coef_compression",
+                 "atm_couple_coef_3rd_order"]
+
+
 def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
@@ -1057,13 +1079,15 @@ def main():
     u.add_file(os.path.join(ref, "src/core_atmosphere/dynamics/mpas_atm_boundaries.F"), ["CORE_ATMOSPHERE"], set())
     u.add_file(os.path.join(ref, "src/core_atmosphere/mpas_atm_dimensions.F"), ["CORE_ATMOSPHERE"], set())
     u.add_file(os.path.join(ref, "src/core_atmosphere/dynamics/mpas_atm_time_integration.F"), ["CORE_ATMOSPHERE", "_MPI"], set(TI_ROUTINES))
-    missing = [r for r in TI_ROUTINES if r not in u.routines]
+    # init-time derivations of atm_mpas_init_block: pins mpas_model_b200/init_block.py
+    u.add_file(os.path.join(ref, "src/core_atmosphere/mpas_atm_core.F"), ["CORE_ATMOSPHERE", "_MPI"], set(CORE_ROUTINES), module_spec=False)
+    missing = [r for r in TI_ROUTINES + CORE_ROUTINES if r not in u.routines]
     if missing:
         raise SystemExit(f"f2cpp: routines not found in the reference: {missing}")
-    body = u.emit_all(TI_ROUTINES)
+    body = u.emit_all(TI_ROUTINES + CORE_ROUTINES)
     with open(os.path.join(out_dir, "ti_ref.inc"), "w") as f:
         f.write("// GENERATED by oracle/f2cpp.py from the reference's Fortran source -- derived reference text, never commit.\n" + body)
-    print(f"f2cpp: {len(TI_ROUTINES)} routines, {len(body.splitlines())} lines -> {out_dir}/ti_ref.inc")
+    print(f"f2cpp: {len(TI_ROUTINES) + len(CORE_ROUTINES)} routines, {len(body.splitlines())} lines -> {out_dir}/ti_ref.inc")
 
 
 if __name__ == "__main__":

@@ -104,6 +104,11 @@ inline double f_cos(double x) { return std::cos(x); }
 inline float f_cos(float x) { return std::cos(x); }
 inline double f_sin(double x) { return std::sin(x); }
 inline float f_sin(float x) { return std::sin(x); }
+inline double f_acos(double x) { return std::acos(x); }
+inline float f_acos(float x) { return std::acos(x); }
+inline double f_asin(double x) { return std::asin(x); }
+inline double f_atan(double x) { return std::atan(x); }
+inline double f_tanh(double x) { return std::tanh(x); }
 inline int f_mod(int a, int b) { return a % b; }
 inline double f_mod(double a, double b) { return std::fmod(a, b); }
 template <class A, class B> inline typename std::common_type<A, B>::type f_merge(A a, B b, bool m) { return m ? a : b; }

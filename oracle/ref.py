@@ -93,8 +93,12 @@ class RefDycore(Backend):
             ("mesh", "qv_init"): np.zeros(nl, dtype=self.rdtype),
             ("mesh", "zb"): np.zeros((nE + 1, 2, nl + 1), dtype=self.rdtype), ("mesh", "zb3"): np.zeros((nE + 1, 2, nl + 1), dtype=self.rdtype),
             ("tend", "w_pgf"): np.zeros((nC + 1, nl + 1), dtype=self.rdtype), ("tend", "w_buoy"): np.zeros((nC + 1, nl + 1), dtype=self.rdtype),
+            # inputs / outputs of the init-time routines of mpas_atm_core.F (atm_compute_mesh_scaling, ...)
+            ("mesh", "meshDensity"): np.ones(nC + 1, dtype=self.rdtype),
+            ("mesh", "meshScalingRegionalCell"): np.zeros(nC + 1, dtype=self.rdtype),
+            ("mesh", "meshScalingRegionalEdge"): np.zeros(nE + 1, dtype=self.rdtype),
         }
-        for k in ("zb", "zb3"):
+        for k in ("zb", "zb3", "deriv_two", "meshDensity"):
             if k in block and np.shape(block[k]) == self.extra[("mesh", k)].shape:
                 self.extra[("mesh", k)][...] = block[k]
         self._bind_all()

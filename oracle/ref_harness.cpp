@@ -144,6 +144,23 @@ int ref_call(void* h, const char* routine, const int* ia, const double* ra) {
                                  CELLS, EDGES, CELLS_SOLVE, scalar_old_arr, scalar_new_arr, s_max_arr, s_min_arr, wdtn_arr,
                                  flux_array, flux_upwind_tmp_arr, flux_tmp_arr, xch,
                                  Opt<bool>(b->cfgs.at("config_split_dynamics_transport").i != 0), rho_zz_int);
+    // init-time derivations of atm_mpas_init_block (mpas_atm_core.F:573-586), serial as in the reference
+    else if (r == "compute_mesh_scaling") {
+#pragma omp master
+        atm_compute_mesh_scaling(b->mesh, b->configs);
+    } else if (r == "compute_signs") {
+#pragma omp master
+        atm_compute_signs(b->mesh);
+    } else if (r == "compute_damping_coefs") {
+#pragma omp master
+        atm_compute_damping_coefs(b->mesh, b->configs);
+    } else if (r == "adv_coef_compression") {
+#pragma omp master
+        atm_adv_coef_compression(b->mesh);
+    } else if (r == "couple_coef_3rd_order") {
+#pragma omp master
+        atm_couple_coef_3rd_order(b->mesh, b->configs);
+    }
     else {
 #pragma omp master
         { fprintf(stderr, "ref_call: unknown routine %s\n", routine); rc = 1; }

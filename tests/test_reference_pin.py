@@ -125,6 +125,44 @@ def test_threaded_reference_equals_serial(small_case):
     r1.close(); r4.close()
 
 
+@pytest.mark.parametrize("jitter", [0.0, 0.2], ids=["icosahedral", "irregular"])
+def test_init_block_against_the_reference_init_routines(jitter):
+    """SURVEY.md §8 row M.  mpas_model_b200/init_block.py feeds BOTH the oracle and the CUDA path, so no parity test between
+    those two can see an error in it.  Here its outputs are compared bit for bit with the reference's own init-time routines
+    (mpas_atm_core.F: atm_compute_mesh_scaling :1091, atm_compute_signs :1151, atm_compute_damping_coefs :1241,
+    atm_adv_coef_compression :1285, atm_couple_coef_3rd_order :1433), transliterated by oracle/f2cpp.py, on a mesh with a
+    non-uniform meshDensity so that the del2/del4 scalings are not trivially one."""
+    from mpas_model_b200 import init_block
+    from mpas_model_b200.case import make_case
+    d_raw, cfg = make_case(642, 10, num_scalars=1, derive=False, jitter=jitter)
+    nC = d_raw["nCells"]
+    d_raw["meshDensity"] = np.concatenate([0.4 + 0.6 * np.cos(d_raw["latCell"][:nC]) ** 2, [1.0]])
+    d = dict(d_raw)
+    init_block.init_block(d, cfg)
+    derived_real = ("edgesOnCell_sign", "edgesOnVertex_sign", "zb_cell", "zb3_cell", "meshScalingDel2", "meshScalingDel4", "dss",
+                    "adv_coefs", "adv_coefs_3rd")
+    derived_int = ("kiteForCell", "advCellsForEdge", "nAdvCellsForEdge")
+    raw = dict(d)
+    for k in derived_real + derived_int:
+        raw[k] = np.zeros_like(d[k])
+    r = ref.RefDycore(raw, cfg)
+    for routine in ("compute_mesh_scaling", "compute_signs", "compute_damping_coefs", "adv_coef_compression", "couple_coef_3rd_order"):
+        r.k(routine)                                       # order of atm_mpas_init_block, mpas_atm_core.F:573-586
+    assert float(np.abs(d["meshScalingDel2"] - 1.0).max()) > 0.05 and d["dss"].max() > 0.0
+    for k in derived_real:
+        got = r.a[(k, 1)].reshape(np.shape(d[k]))
+        if k.startswith("meshScalingDel"):                 # x ** 0.25, x ** 0.75: numpy's vectorised pow vs libm's, one ulp apart
+            assert np.allclose(got, d[k], rtol=5e-16, atol=0), k
+        else:
+            assert np.array_equal(got, d[k]), k
+    nadv = d["nAdvCellsForEdge"]
+    assert np.array_equal(r.a[("nAdvCellsForEdge", 1)], nadv)
+    assert np.array_equal(r.a[("kiteForCell", 1)][:nC], d["kiteForCell"][:nC] + 1)           # the reference's arrays are 1-based
+    used = np.arange(15)[None, :] < nadv[:, None]
+    assert np.array_equal(r.a[("advCellsForEdge", 1)][used], d["advCellsForEdge"][used] + 1)
+    r.close()
+
+
 def test_constants_come_from_the_reference():
     """The physical constants inside the generated code are the parameter statements of src/framework/mpas_constants.F."""
     import os
