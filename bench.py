@@ -91,6 +91,11 @@ KERNEL_MODEL_C = {
     "k:k_acoustic_cell": 29.0,
     # edge tendency: rk 1 reads 5 E + 8 C + 1 V and writes 3 E (34 C); rk 2,3 read 5 E + 3 C, write 1 E (21 C)
     "k:k2_dt_edge_b": (3 * 34.0 + 6 * 21.0) / 9,
+    "k:k2_dt_edge_b<false>": (3 * 34.0 + 6 * 21.0) / 9,
+    # with the Coriolis sum moved to k8_coriolis_cell the edge kernel reads 2 partial sums (6 C) instead of gathering u and
+    # pv_edge over edgesOnEdge (their own-edge reads stay): same model bytes + 6 C; k8: u, pv_edge (2 E) read, 6 C written
+    "k:k2_dt_edge_b<true>": (3 * 34.0 + 6 * 21.0) / 9 + 6.0,
+    "k:k8_coriolis_cell": 12.0,
     "k:k_dt_edge_b": (3 * 34.0 + 6 * 21.0) / 9,
     # cell tendency after the per-edge flux split: 2 E fluxes + ru, ru_save (rk > 1) + 13 C read, 3-5 C written
     "k:k2_dt_cell_f": 24.0,

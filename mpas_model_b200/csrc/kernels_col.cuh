@@ -759,12 +759,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     }
 }
 
+// ------------------------------------------------------------------ nonlinear Coriolis term, cell-centred partial sums
+// (relaxed arithmetic; TI:5418-5428).  One warp per cell c of the block: u and pv_edge of its ne edges are gathered once and for
+// every edge i of the cell P_c[i] = sum_{j != i} W[i][j] u_j (pv_i + pv_j)/2 is formed in registers, W[i][j] = weightsOnEdge of
+// edge j in the edgesOnEdge list of edge i (tables built and verified on the host, build_coriolis_tables).  The edge kernel adds
+// the two partial sums of its two cells: 2 gathered columns per edge instead of 2 (ne1 + ne2 - 2).
+__global__ void __launch_bounds__(CW_THREADS, 2) k8_coriolis_cell(const Dev D) {
+    __shared__ __align__(16) real s_w[CW_WARPS][64];
+    CW_SETUP(D.nCells)
+    const int ne = D.nEdgesOnCell[i];
+    const int le = min(lane, ne - 1);
+    const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
+    {   // 64 weights of the cell: two per lane
+        const r2 w2 = *reinterpret_cast<const r2*>(D.cor_w + (size_t)i * 64 + 2 * lane);
+        *reinterpret_cast<r2*>(&s_w[wib][2 * lane]) = w2;
+    }
+    r2 u[CW_MAXNE], pv[CW_MAXNE];
+#pragma unroll
+    for (int e = 0; e < CW_MAXNE; e++) {
+        if (e < CW_NE || e < ne) { const int iEdge = BC(my_e, min(e, ne - 1)); u[e] = LD(D.u_2, iEdge); pv[e] = LD(D.pv_edge, iEdge); }
+        else { u[e] = mk2(0.0, 0.0); pv[e] = u[e]; }
+    }
+    __syncwarp();
+    const real* __restrict__ W = s_w[wib];
+    const b2 k_lt_nl = lv.lt(nl);
+#pragma unroll
+    for (int e = 0; e < CW_MAXNE; e++) {
+        if (e < ne) {                                       // warp-uniform
+            r2 acc = mk2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < CW_MAXNE; j++) {
+                if (j != e && (j < CW_NE || j < ne)) {
+                    const real w = W[e * 8 + j];            // zero for slots beyond ne
+                    const r2 upv = u[j] * (0.5 * (pv[e] + pv[j]));
+                    acc = fma2(w, upv, acc);
+                }
+            }
+            st2(D.cor_part, ((unsigned)i * (unsigned)D.maxEdges + (unsigned)e) * uLDK + kc, act, sel(k_lt_nl, acc, 0.0));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (b)
 // edge-all: [rk 1] PGF (5379-5387), delsq_u + del2 mixing (5467-5503); [owned edges] vertical transport,
 // nonlinear Coriolis, KE gradient (5391-5447); [rk > 1] final sum with tend_u_euler (5694-5701).
 // Restriction (host falls back to k_dt_edge_b otherwise): config_rayleigh_damp_u off.
 // This kernel is bound by the L1 data pipe (46 gathered columns per edge), not by latency: it is kept at
 // ~64 registers for 32 resident warps per SM rather than unrolled for more loads in flight (measured).
+// COR: the nonlinear Coriolis sum arrives as two partial sums, one from each adjacent cell (k8_coriolis_cell, relaxed
+// arithmetic), instead of being gathered here over edgesOnEdge
+template <bool COR>
 __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
     CW_SETUP(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
@@ -803,16 +847,23 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
         tu = -LD(D.rdzw, 0) * (f1 - fz);
     }
     r2 q = mk2(0.0, 0.0);
-    const int neoe = D.nEdgesOnEdge[i];
-    int my_eoe = 0; real my_woe = 0.0;
-    if (lane < neoe) { my_eoe = D.edgesOnEdge[(unsigned)i * D.maxEdges2 + lane]; my_woe = D.weightsOnEdge[(unsigned)i * D.maxEdges2 + lane]; }
-    const r2 pv_e = LD(D.pv_edge, i);
+    if (COR) {
+        const int sl = D.cor_slot[i];
+        const r2 q1 = ld2(D.cor_part, ((unsigned)cell1 * (unsigned)D.maxEdges + (unsigned)(sl & 255)) * uLDK + kc);
+        const r2 q2 = ld2(D.cor_part, ((unsigned)cell2 * (unsigned)D.maxEdges + (unsigned)(sl >> 8)) * uLDK + kc);
+        q = q1 + q2;
+    } else {
+        const int neoe = D.nEdgesOnEdge[i];
+        int my_eoe = 0; real my_woe = 0.0;
+        if (lane < neoe) { my_eoe = D.edgesOnEdge[(unsigned)i * D.maxEdges2 + lane]; my_woe = D.weightsOnEdge[(unsigned)i * D.maxEdges2 + lane]; }
+        const r2 pv_e = LD(D.pv_edge, i);
 #pragma unroll 5
-    for (int j = 0; j < neoe; j++) {
-        const int eoe = BC(my_eoe, j);
-        const real woe = BC(my_woe, j);
-        const r2 workpv = 0.5 * (pv_e + LD(D.pv_edge, eoe));
-        q = q + woe * LD(D.u_2, eoe) * workpv;
+        for (int j = 0; j < neoe; j++) {
+            const int eoe = BC(my_eoe, j);
+            const real woe = BC(my_woe, j);
+            const r2 workpv = 0.5 * (pv_e + LD(D.pv_edge, eoe));
+            q = q + woe * LD(D.u_2, eoe) * workpv;
+        }
     }
     tu = tu + rho_e * (q - (LD(D.ke, cell2) - LD(D.ke, cell1)) * invDc)
          - u * 0.5 * (LD(D.h_divergence, cell1) + LD(D.h_divergence, cell2));

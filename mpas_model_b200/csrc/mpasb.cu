@@ -65,7 +65,9 @@ struct mpasb_handle_s {
     std::vector<int> hc_advCells, hc_nAdv, hc_cellsOnEdge;
     // host copies for the canonical-neighbourhood tables of the cell-centred flux sweep (build_flux_rings)
     std::vector<int> hc_cellsOnCell, hc_edgesOnCell, hc_nEdgesOnCell;
-    std::vector<real> hc_adv_coefs, hc_adv_coefs_3rd;
+    std::vector<real> hc_adv_coefs, hc_adv_coefs_3rd, hc_weightsOnEdge;
+    std::vector<int> hc_edgesOnEdge, hc_nEdgesOnEdge;
+    bool cor_dirty = true, cor_ok = false;
     bool rings_dirty = true, rings_ok = false;
     bool relaxed = true;           // re-associated / FMA kernels allowed (parity bar 1e-11, not bit equality); MPASB_STRICT=1 turns it off
     long n_regular = 0;
@@ -216,7 +218,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->D.zb_any) cudaFree(h->D.zb_any);
     if (h->D.adv_flux_w) cudaFree(h->D.adv_flux_w);
     if (h->D.adv_flux_theta) cudaFree(h->D.adv_flux_theta);
-    for (void* p : {(void*)h->D.fx_ring, (void*)h->D.fx_w, (void*)h->D.hdiv_w, (void*)h->D.hdiv_theta}) if (p) cudaFree(p);
+    for (void* p : {(void*)h->D.fx_ring, (void*)h->D.fx_w, (void*)h->D.hdiv_w, (void*)h->D.hdiv_theta, (void*)h->D.cor_w, (void*)h->D.cor_slot, (void*)h->D.cor_part}) if (p) cudaFree(p);
     if (h->d_tile_hdr) cudaFree(h->d_tile_hdr);
     if (h->d_tile_runs) cudaFree(h->d_tile_runs);
     if (h->d_tile_slot) cudaFree(h->d_tile_slot);
@@ -391,6 +393,9 @@ extern "C" int mpasb_set_field(mpasb_handle h, const char* name, int time_level,
     const size_t o = outer_of(h, f->loc);
     const bool padded = f->inner == IN_NL || f->inner == IN_NL1 || f->inner == IN_NL1_ME || f->inner == IN_S_NL || f->inner == IN_NL_TWO;
     if (f->inner == IN_NL1_ME) h->zb_dirty = true;
+    if (!strcmp(name, "weightsOnEdge")) {
+        if ((long)h->hc_weightsOnEdge.size() != count || memcmp(h->hc_weightsOnEdge.data(), src, count * sizeof(real))) { h->hc_weightsOnEdge.assign(src, src + count); h->cor_dirty = true; }
+    }
     if (!strcmp(name, "adv_coefs") || !strcmp(name, "adv_coefs_3rd")) {
         std::vector<real>& hc = !strcmp(name, "adv_coefs") ? h->hc_adv_coefs : h->hc_adv_coefs_3rd;
         if ((long)hc.size() != count || memcmp(hc.data(), src, count * sizeof(real))) { hc.assign(src, src + count); h->rings_dirty = true; }
@@ -449,6 +454,9 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
     {   // host copies for build_flux_rings; an identical re-upload does not invalidate the tables
         std::vector<int>* hc = !strcmp(name, "cellsOnCell") ? &h->hc_cellsOnCell : !strcmp(name, "edgesOnCell") ? &h->hc_edgesOnCell :
                                !strcmp(name, "nEdgesOnCell") ? &h->hc_nEdgesOnCell : nullptr;
+        if (!strcmp(name, "edgesOnEdge")) { h->hc_edgesOnEdge.assign(src, src + count); h->cor_dirty = true; }
+        if (!strcmp(name, "nEdgesOnEdge")) { h->hc_nEdgesOnEdge.assign(src, src + count); h->cor_dirty = true; }
+        if (hc || !strcmp(name, "cellsOnEdge")) h->cor_dirty = true;
         const bool ring_input = hc || !strcmp(name, "cellsOnEdge") || !strcmp(name, "advCellsForEdge") || !strcmp(name, "nAdvCellsForEdge");
         if (hc && ((long)hc->size() != count || memcmp(hc->data(), src, count * sizeof(int)))) { hc->assign(src, src + count); h->rings_dirty = true; }
         else if (ring_input && !hc) h->rings_dirty = true;
@@ -713,6 +721,54 @@ static void build_flux_rings(H* h) {
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return;          // the host vectors go out of scope
     h->rings_ok = true;
 }
+// Tables for the cell-centred evaluation of the nonlinear Coriolis sum (TI:5418-5428).  The edgesOnEdge list of an edge e is the
+// other edges of its two cells, so sum_j w_j u_j (pv_e + pv_j)/2 splits into one partial sum per adjacent cell; a cell that
+// holds u and pv_edge of its ne edges in registers produces the partial sums of all ne of them from 2 ne gathered columns
+// (k8_coriolis_cell), against 2 (ne1 + ne2 - 2) per edge in the edge-centred loop.  Every list is checked: if any edge with two
+// cells inside the block has an edgesOnEdge entry that is not an edge of one of its cells, or entries missing, the edge-centred
+// kernel stays in charge for the whole block.
+static void build_coriolis_tables(H* h) {
+    h->cor_dirty = false; h->cor_ok = false;
+    const int nC = h->dims.nCells, nE = h->dims.nEdges, mx = h->dims.maxEdges, mx2 = h->dims.maxEdges2;
+    // opt-in (MPASB_COR=1): measured on B200 (x1.40962 x 55) the edge kernel drops from 1.68 to 1.25 ms/step, but the cell kernel
+    // that writes the partial sums costs 0.63 ms/step (12 C of extra HBM traffic per call): 12.34 vs 12.12 ms per step
+    if (!h->relaxed || !getenv("MPASB_COR") || mx > CW_MAXNE) return;
+    if ((long)h->hc_edgesOnCell.size() != (long)(nC + 1) * mx || (long)h->hc_nEdgesOnCell.size() != nC + 1 ||
+        (long)h->hc_cellsOnEdge.size() != (long)(nE + 1) * 2 || (long)h->hc_edgesOnEdge.size() != (long)(nE + 1) * mx2 ||
+        (long)h->hc_nEdgesOnEdge.size() != nE + 1 || (long)h->hc_weightsOnEdge.size() != (long)(nE + 1) * mx2) return;
+    std::vector<real> W((size_t)(nC + 1) * 64, (real)0);
+    std::vector<int> slot((size_t)nE + 1, 0);
+    auto eoc = [&](int c, int i) { return h->hc_edgesOnCell[(size_t)c * mx + i] - 1; };
+    auto slot_of = [&](int c, int e) { for (int i = 0; i < h->hc_nEdgesOnCell[c]; i++) if (eoc(c, i) == e) return i; return -1; };
+    for (int e = 0; e < nE; e++) {
+        const int c1 = h->hc_cellsOnEdge[2 * (size_t)e] - 1, c2 = h->hc_cellsOnEdge[2 * (size_t)e + 1] - 1;
+        if (c1 < 0 || c1 >= nC || c2 < 0 || c2 >= nC) continue;            // an edge on the rim of the block: never a "solve" edge
+        const int s1 = slot_of(c1, e), s2 = slot_of(c2, e);
+        if (s1 < 0 || s2 < 0) { if (e < h->dims.nEdgesSolve) return; continue; }
+        slot[e] = s1 | (s2 << 8);
+        const int n = h->hc_nEdgesOnEdge[e];
+        int found = 0;
+        for (int j = 0; j < n; j++) {
+            const int eoe = h->hc_edgesOnEdge[(size_t)e * mx2 + j] - 1;
+            const real w = h->hc_weightsOnEdge[(size_t)e * mx2 + j];
+            const int j1 = slot_of(c1, eoe), j2 = slot_of(c2, eoe);
+            if (eoe == e || (j1 < 0) == (j2 < 0)) { if (e < h->dims.nEdgesSolve) return; found = -1000; break; }    // not exactly one owner cell
+            if (j1 >= 0) W[(size_t)c1 * 64 + s1 * 8 + j1] = w; else W[(size_t)c2 * 64 + s2 * 8 + j2] = w;
+            found++;
+        }
+        if (found != h->hc_nEdgesOnCell[c1] + h->hc_nEdgesOnCell[c2] - 2 && e < h->dims.nEdgesSolve) return;
+    }
+    Dev& D = h->D;
+    for (void* p : {(void*)D.cor_w, (void*)D.cor_slot, (void*)D.cor_part}) if (p) cudaFree(p);
+    D.cor_w = nullptr; D.cor_slot = nullptr; D.cor_part = nullptr;
+    if (cudaMalloc(&D.cor_w, W.size() * sizeof(real)) != cudaSuccess || cudaMalloc(&D.cor_slot, slot.size() * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&D.cor_part, (size_t)(nC + 1) * mx * D.LDK * sizeof(real)) != cudaSuccess) return;
+    cudaMemcpyAsync(D.cor_w, W.data(), W.size() * sizeof(real), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(D.cor_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(D.cor_part, 0, (size_t)(nC + 1) * mx * D.LDK * sizeof(real), h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return;
+    h->cor_ok = true;
+}
 // in_step: called from srk3, where (a) the exchange of w, pv_edge, rho_edge of the previous stage may still be in flight
 // while the first kernel (which reads none of them) runs, and (b) tend_u is final before the w/theta tendencies are
 // computed, so its exchange (TI:1228) is started here and overlaps them
@@ -723,7 +779,11 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
     if (h->colwarp && !(A.cam_coef > 0.0)) LAUNCHW(k2_dt_cell_a, D.nCells, D, A);
     else LAUNCH(k_dt_cell_a, D.nCells, 0, D, A);
     comm_wait(h);
-    if (h->colwarp && !A.rayleigh_damp_u) LAUNCHW(k2_dt_edge_b, D.nEdges, D, A);
+    if (h->colwarp && !A.rayleigh_damp_u) {
+        if (h->cor_dirty) build_coriolis_tables(h);
+        if (h->cor_ok) { LAUNCHW(k8_coriolis_cell, D.nCells, D); LAUNCHW(k2_dt_edge_b<true>, D.nEdges, D, A); }
+        else LAUNCHW(k2_dt_edge_b<false>, D.nEdges, D, A);
+    }
     else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
         if (A.h_mom_eddy_visc4 > 0.0) {

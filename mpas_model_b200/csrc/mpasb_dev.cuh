@@ -45,6 +45,10 @@ struct Dev {
     // the 18 cells of its two rings in canonical order + a regularity flag, the 2 x 60 stencil weights of its 6 edges in
     // canonical slot order, and the horizontal flux divergences of w and theta_m it produces
     int* fx_ring; real* fx_w; real* hdiv_w; real* hdiv_theta;
+    // cell-centred partial sums of the nonlinear Coriolis term (k8_coriolis_cell -> k2_dt_edge_b<true>): per cell the weights
+    // W[i][j] of edge j of the cell in the edgesOnEdge list of its edge i (8 x 8 reals), per edge its slot in its two cells,
+    // and the partial sums [cell][slot][LDK]
+    real* cor_w; int* cor_slot; real* cor_part;
 };
 #undef F
 #undef FIELD_REAL
