@@ -55,13 +55,14 @@ typedef struct mpasb_config {
     int config_rayleigh_damp_u;             /* logical         TI:5667 */
     int config_number_rayleigh_damp_u_levels;
     int config_number_cam_damping_levels;
-    int config_apply_lbcs;                  /* must be 0: regional path is out of scope */
+    int config_apply_lbcs;                  /* logical: regional run with lateral boundary conditions, TI:773 */
     int config_print_global_minmax_vel;     /* logical         TI:7960 */
     double config_epssm, config_smdiv, config_len_disp, config_coef_3rd_order;
     double config_visc4_2dsmag, config_smagorinsky_coef, config_del4u_div_factor;
     double config_h_mom_eddy_visc2, config_h_mom_eddy_visc4, config_v_mom_eddy_visc2;
     double config_h_theta_eddy_visc2, config_h_theta_eddy_visc4, config_v_theta_eddy_visc2;
     double config_apvm_upwinding, config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days;
+    double config_relax_zone_divdamp_coef;  /* Registry.xml:254, TI:7346-7580 */
     double cf1, cf2, cf3, sphere_radius;
     int on_a_sphere;                        /* mesh attribute (logical), mpas_vector_reconstruction.F:250 */
 } mpasb_config;
@@ -100,6 +101,10 @@ int  mpasb_step(mpasb_handle h, mpasb_real dt, int itimestep);
  * the reference, TI:1091-1093) are zero after mpasb_create and keep what mpasb_set_field uploads until this call. */
 int  mpasb_zero_physics_tendencies(mpasb_handle h);
 int  mpasb_shift_time_levels(mpasb_handle h);
+/* Regional runs (config_apply_lbcs): seconds from the START of the next step to the end of the current LBC interval, i.e. what
+ * mpas_atm_get_bdy_state derives from the clock (LBC_intv_end - currTime, mpas_atm_boundaries.F:497-503).  Call before every
+ * mpasb_step; the lbc_* fields are uploaded with mpasb_set_field whenever the host reads a new LBC time. */
+int  mpasb_set_lbc_time(mpasb_handle h, mpasb_real seconds_to_interval_end);
 /* summarize_timestep (TI:7914-8357): out = {min w, max w, min u, max u} of level 2,
  * reductions start from 0 as in TI:8291-8292. */
 int  mpasb_minmax(mpasb_handle h, mpasb_real out[4]);
@@ -128,6 +133,10 @@ int  mpasb_compute_output_diagnostics(mpasb_handle h, int time_level);
 /* Kernel-level entry points, one per *_work routine, operating on the
  * device-resident fields of the handle (parity tests drive one at a time). */
 int  mpasb_k_rk_integration_setup(mpasb_handle h);                                   /* TI:1930 */
+/* regional path (TI:7198-7910, 1343-1388): routine = "speczone_tend" | "relaxzone_tend" (a = time_dyn_step, b = dt) |
+ * "reset_u_ru" (a = time_dyn_step) | "adjust_scalars" (a = dt, b = rk_timestep) | "zero_gradient_w" |
+ * "reset_speczone_values" (a = dt) | "set_scalars" (a = dt) */
+int  mpasb_k_lbc(mpasb_handle h, const char* routine, mpasb_real a, mpasb_real b);
 int  mpasb_k_compute_moist_coefficients(mpasb_handle h);                             /* TI:2042 */
 int  mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts);                 /* TI:2225 */
 int  mpasb_k_compute_dyn_tend(mpasb_handle h, int rk_step, mpasb_real dt);           /* TI:4982 */

@@ -37,3 +37,52 @@ def add_passive_tracers(d):
         r = jw_init.sphere_distance(lat, lon, lat0, lon0, 1.0)
         bell = np.where(r < 0.6, 0.5 * (1.0 + np.cos(np.pi * r / 0.6)), 0.0)
         d["scalars"][:nC, :, s] = 1.0e-3 * (0.1 + bell[:, None] * prof[None, :])
+
+
+N_RELAX_ZONE, N_SPEC_ZONE = 5, 2          # mpas_atm_boundaries.F:35-38
+
+
+def make_regional(d: dict, cfg: dict, lat0: float = 0.6, lon0: float = 0.4, radius: float = 1.7, seed: int = 7,
+                  lbc_interval: float = 10800.0):
+    """Turn a global case into a limited-area one for the regional path (config_apply_lbcs, TI:7198-7910): everything
+    further than ``radius`` (radians) from (lat0, lon0) becomes the outermost specified-zone ring (bdyMaskCell = 7), and
+    the rings 6, 5 ... 1 are the successive cell layers inside it, as the limited-area mesh tool marks them; an edge takes
+    the smaller mask of its two cells.  specZoneMask* as mpas_atm_boundaries.F:729-730.  The driving fields are the
+    case's own state plus a smooth offset (time level 2 = state at the end of the LBC interval) and a small tendency
+    (time level 1), so that every relaxation and specified-zone branch does non-trivial arithmetic.
+    Returns (block, cfg, seconds to the end of the LBC interval at the start of the first step)."""
+    d = dict(d)
+    cfg = dict(cfg, config_apply_lbcs=True)
+    nC, nE = d["nCells"], d["nEdges"]
+    lat, lon = d["latCell"][:nC], d["lonCell"][:nC]
+    dist = jw_init.sphere_distance(lat, lon, lat0, lon0, 1.0)
+    mask = np.zeros(nC + 1, dtype=np.int32)
+    mask[:nC][dist > radius] = N_RELAX_ZONE + N_SPEC_ZONE
+    coc, ne = d["cellsOnCell"], d["nEdgesOnCell"]
+    for ring in range(N_RELAX_ZONE + N_SPEC_ZONE - 1, 0, -1):
+        outer = mask[:nC] == ring + 1
+        nxt = np.zeros(nC, dtype=bool)
+        for j in range(coc.shape[1]):
+            nb = coc[:nC, j]
+            ok = (j < ne[:nC]) & (nb < nC)
+            nxt |= ok & outer[np.minimum(nb, nC - 1)]
+        mask[:nC][nxt & (mask[:nC] == 0)] = ring
+    assert (mask[:nC] == 0).sum() > 0 and all((mask[:nC] == m).any() for m in range(1, 8)), "region too small for 7 rings"
+    c1, c2 = d["cellsOnEdge"][:nE, 0], d["cellsOnEdge"][:nE, 1]
+    emask = np.zeros(nE + 1, dtype=np.int32)
+    emask[:nE] = np.minimum(mask[c1], mask[c2])
+    d["bdyMaskCell"], d["bdyMaskEdge"] = mask, emask
+    d["specZoneMaskCell"] = (mask > N_RELAX_ZONE).astype(np.float64)
+    d["specZoneMaskEdge"] = (emask > N_RELAX_ZONE).astype(np.float64)
+    rng = np.random.default_rng(seed)
+    rho, th, u = d["rho_zz_init"], d["theta_m_init"], d["u"]         # what atm_init_coupled_diagnostics derives from the state
+    wob_c = 1.0 + 2.0e-3 * np.sin(3.0 * d["latCell"])[:, None] * np.cos(2.0 * d["lonCell"])[:, None]
+    d["lbc_rho_zz_2"] = rho * wob_c
+    d["lbc_rtheta_m_2"] = rho * th * wob_c * (1.0 + 1.0e-3)
+    d["lbc_u_2"] = u + 0.5
+    d["lbc_ru_2"] = d["ru_init"] * 1.01 + 0.5
+    d["lbc_scalars_2"] = d["scalars"] * 1.05 + 1.0e-5
+    for n in ("rho_zz", "rtheta_m", "u", "ru", "scalars"):
+        st = d["lbc_" + n + "_2"]
+        d["lbc_" + n] = st * 1.0e-6 * rng.uniform(-1.0, 1.0, size=st.shape)       # per second
+    return d, cfg, lbc_interval

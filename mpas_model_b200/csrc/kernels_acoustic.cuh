@@ -38,7 +38,8 @@ __global__ void k_acoustic_cell(const Dev D, real dts, int small_step, real epss
     real* s_al = s_a + LDK;
     real* s_ga = s_al + LDK;
     const bool incell = i < D.nCells;
-    const bool solve = i < D.nCellsSolve;
+    // cells of the specified zone of a regional run take the other branch of TI:2862 (k_lbc_acoustic_spec)
+    const bool solve = i < D.nCellsSolve && D.specZoneMaskCell[i] == 0.0;
     const bool first = small_step == 1;
     // old values of the perturbation variables (zero on the first small step, TI:2850-2860)
     real rho_pp_k = 0.0, rtheta_pp_k = 0.0, rw_p_k = 0.0, rw_p_k1 = 0.0, wwAvg_k = 0.0;
@@ -202,6 +203,7 @@ __global__ void k_recover_edge(const Dev D, real invNs) {
 __global__ void k_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     KI;
     if (i >= D.nCells || k >= nl) return;
+    if (D.bdyMaskCell[i] > 5) return;              // no update in the specified zone of a regional run, TI:3385
     const int ne = D.nEdgesOnCell[i];
     real w = AT(D.w_2, i, k);
     const real fm = D.fzm[k], fp = D.fzp[k];

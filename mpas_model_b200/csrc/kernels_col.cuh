@@ -115,7 +115,11 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
     return flux4_2(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * abs2(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;
 }
 
-#define CW_SETUP(ncols)                                                                       \
+#define CW_SETUP(ncols) PDL_ENTER CW_SETUP_NW(ncols)
+// the hot kernels: CW_ENTER, loads of static mesh data (connectivity, metric weights), then pdl_wait() before the first field access
+#define CW_ENTER(ncols) pdl_trigger(); CW_SETUP_NW(ncols)
+// ... without the wait: the kernel places pdl_wait() itself, below its loads of static mesh data
+#define CW_SETUP_NW(ncols)                                                                    \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
     const int i = blockIdx.x * CW_WARPS + wib;                                                \
     const int LDK = D.LDK, nl = D.nl;                                                         \
@@ -140,8 +144,9 @@ __device__ __forceinline__ void pf2(const real* p, unsigned off) { asm volatile(
 #define CW_MAXNE 8                      // most edges per cell these kernels handle (host checks nEdgesOnCell)
 #define CW_NE 6                         // edges per cell covered by the unrolled loops
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_flux(const Dev D) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;           // only edges of owned cells are consumed
     const int nadv = D.nAdvCellsForEdge[i];
     // one stencil entry per lane: cell index and the two possible weights adv_coefs +/- adv_coefs_3rd
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
                                                              const int4* __restrict__ tile_runs, const unsigned char* __restrict__ tile_slot) {
     extern __shared__ __align__(128) unsigned char ef_raw[];
     __shared__ __align__(8) unsigned long long ef_bar;
+    PDL_ENTER
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     real* s_w = reinterpret_cast<real*>(ef_raw);
@@ -310,6 +316,7 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
 __device__ __forceinline__ r2 fma2(real a, r2 q, r2 acc) { return mk2(fma(a, q.x, acc.x), fma(a, q.y, acc.y)); }
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev D) {
     __shared__ __align__(16) real s_wts[FX_WARPS][FX_WTS];
+    pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     Lv lv; lv.k0 = 2 * lane;
@@ -329,6 +336,7 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
         my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
         my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     }
+    pdl_wait();                                          // everything above is static mesh data
     for (; i < D.nCellsSolve; i += G) {
     const int regular = BC(my_ring, 18);
     r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
 #endif
 __global__ void __launch_bounds__(CW_THREADS, FX1_MINB) k5s_flux_cell(const Dev D) {
     __shared__ __align__(16) real s_wts[CW_WARPS][FX_WTS];
+    PDL_ENTER
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * CW_WARPS + wib;
     const int i = g >> 1, field = g & 1;
@@ -652,6 +661,7 @@ __device__ __forceinline__ CfConn cf_conn(const Dev& D, int i, int lane, bool rk
 #endif
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, const DynTendArgs A) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     Lv lv; lv.k0 = 2 * lane;
@@ -666,6 +676,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     int i = blockIdx.x * WARPS + wib;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
     if (i < D.nCellsSolve) cn = cf_conn(D, i, lane, rk1);
+    pdl_wait();                                          // everything above is static mesh data
     for (; i < D.nCellsSolve; i += G) {
         const int ne = cn.ne, my_e = cn.e, my_c1 = cn.c1, my_c2 = cn.c2;
         const real my_sgn = cn.sgn, my_dv = cn.dv, my_d4 = cn.d4, my_idc = cn.idc, invArea = cn.invArea;
@@ -810,11 +821,12 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k8_coriolis_cell(const Dev D) {
 // arithmetic), instead of being gathered here over edgesOnEdge
 template <bool COR>
 __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
     const real invDc = D.invDcEdge[i];
     const b2 k_lt_nl = lv.lt(nl);
+    pdl_wait();
     const r2 rho_e = LD(D.rho_edge, i);
     if (A.rk_step == 1) {
         r2 tue = mk2(0.0, 0.0);
@@ -879,12 +891,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
 #define PFZ(p, col, E) pf2((p), ((unsigned)(col) * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
-    CW_SETUP(D.nCellsSolve)
+    CW_ENTER(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    pdl_wait();
     const r2 wt_in = LD(D.tend_w, i);
     const r2 zz = LD(D.zz, i);
     r2 wt = wt_in;
@@ -909,12 +922,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev 
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
 __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
-    CW_SETUP(D.nCells)
+    CW_ENTER(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    pdl_wait();
     const r2 w_in = LD(D.w_2, i);
     const r2 rho = LD(D.rho_zz_2, i);
     const b2 k_eq0 = lv.eq(0);
@@ -942,7 +956,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
 // (1) vertex-all: vorticity (6452-6472), ke_vertex (6548-6561, ke_edge recomputed inline), pv_vertex (6647-6659)
 __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const real* __restrict__ u) {
-    CW_SETUP(D.nVertices)
+    CW_ENTER(D.nVertices)
     int my_e = 0; real my_s = 0.0, my_efac = 0.0;
     {
         const int l3 = min(lane, 2);
@@ -951,6 +965,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
         my_s = D.edgesOnVertex_sign[3 * i + l3] * dc;
         my_efac = dc * D.dvEdge[my_e];
     }
+    pdl_wait();
     const r2 u0 = LD(u, BC(my_e, 0)), u1 = LD(u, BC(my_e, 1)), u2 = LD(u, BC(my_e, 2));
     r2 vort = mk2(0.0, 0.0);
     vort = vort + BC(my_s, 0) * u0;
@@ -967,7 +982,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
 }
 // (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
-    CW_SETUP(D.nCells)
+    CW_ENTER(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const real r = D.invAreaCell[i];
@@ -975,6 +990,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
     const real my_dv = D.dvEdge[my_e];
     const real my_s = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * my_dv;
     const real my_efac = D.dcEdge[my_e] * my_dv;
+    pdl_wait();
     const int my_v = D.verticesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_kite = D.kiteAreasOnVertex[3 * my_v + D.kiteForCell[(unsigned)i * D.maxEdges + le]];
     r2 div = mk2(0.0, 0.0), ke = mk2(0.0, 0.0);
@@ -1012,10 +1028,11 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
+    pdl_wait();
     const r2 rho_edge = 0.5 * (LD(h, cell1) + LD(h, cell2));
     const r2 pv1 = LD(D.pv_vertex, vertex1), pv2 = LD(D.pv_vertex, vertex2);
     r2 vv;
@@ -1048,12 +1065,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev 
 // cell-all: Smagorinsky kdiff (rk 1, TI:5226-5296), h_divergence (5307-5338), tend_rho + dpdz (rk 1, 5345-5362).
 // Restriction (host falls back to k_dt_cell_a otherwise): config_mpas_cam_coef == 0.
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev D, const DynTendArgs A) {
-    CW_SETUP(D.nCells)
+    CW_ENTER(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_es = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le] * D.dvEdge[my_e];
     const b2 k_lt_nl = lv.lt(nl);
+    pdl_wait();
     r2 kd = mk2(A.fixed_visc2, A.fixed_visc2);
     if (A.rk_step == 1 && A.smag) {
         const real my_da = D.defc_a[(unsigned)i * D.maxEdges + le], my_db = D.defc_b[(unsigned)i * D.maxEdges + le];
@@ -1094,12 +1112,13 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
 // rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
-    CW_SETUP(D.nCells)
+    CW_ENTER(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const int my_c1 = D.cellsOnEdge[2 * my_e], my_c2 = D.cellsOnEdge[2 * my_e + 1];
+    pdl_wait();
     // one of the two cells of every edge is this cell: its columns are loaded once, only the other cell is gathered
     const bool my_is1 = my_c1 == i, my_is2 = my_c2 == i;
     const int my_oth = my_is1 ? my_c2 : my_c1;
@@ -1166,6 +1185,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev 
 #endif
 __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
     extern __shared__ __align__(16) real sm3[];
+    PDL_ENTER
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     const int S = LDK | 1;                                  // odd row stride (LDK is even)
@@ -1357,6 +1377,7 @@ __device__ __forceinline__ Ac6Conn ac6_conn(const Dev& D, int i, int lane, real 
 }
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     Lv lv; lv.k0 = 2 * lane;
@@ -1364,7 +1385,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const bool first = small_step == 1;
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
-    const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
+    const r2 rdzw = LD(D.rdzw, 0);
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
     // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
     // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
@@ -1372,6 +1393,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     int i = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
     if (i < D.nCellsSolve) cn = ac6_conn(D, i, lane, dts);
+    pdl_wait();                                          // everything above is static mesh data
+    const r2 cofrz = LD(D.cofrz, 0);                     // (written by the vertical-coefficient kernel)
     for (; i < D.nCells; i += G) {
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
@@ -1487,8 +1510,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 // first != 0: also performs the first-small-step edge update of atm_advance_acoustic_step_work (TI:2798-2806:
 // ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
 __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const real mask = 1.0 - D.specZoneMaskEdge[i];
     const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
@@ -1550,9 +1574,10 @@ __device__ __forceinline__ r2 dd_term(const Dev& D, int cell1, int cell2, int i,
     return coef_divdamp * (divCell2 - divCell1) * mask / th;
 }
 __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs, int dd_mode, real coef_divdamp, real dts) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
+    pdl_wait();
     const r2 rus = LD(D.ru_save, i);
     r2 ru_p, ruAvg;
     if (dd_mode == 2) { ru_p = dts * LD(D.tend_u, i); ruAvg = sel(k_lt_nl, ru_p, 0.0); }
@@ -1569,8 +1594,9 @@ __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real 
 // dd_mode != 0: the divergence damping of the PREVIOUS small step is applied first, in registers (see k2_recover_edge): the
 // separate damping kernel between two small steps disappears (its operands rtheta_pp, theta_m are gathered here anyway)
 __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real dts, real c2, int dd_mode, real coef_divdamp) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const b2 k_lt_nl = lv.lt(nl);
     const r2 tend_u = LD(D.tend_u, i);
@@ -1679,6 +1705,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
 #endif
 __global__ void __launch_bounds__(VIC_WARPS * 32, MB_VIC) k3_vert_imp_coefs(const Dev D, real dtseps, real c2, real rcv) {
     extern __shared__ __align__(16) real smv[];
+    PDL_ENTER
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
     const int S = LDK | 1;
@@ -1923,8 +1950,9 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const r
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
-    CW_SETUP(D.nEdges)
+    CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
     const real* __restrict__ s_in = D.scale_arr; const real* __restrict__ s_out = D.scale_arr + D.cellPlane;
     const r2 flux = LD(D.flux_tmp, i);

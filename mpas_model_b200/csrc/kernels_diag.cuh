@@ -161,6 +161,7 @@ struct Seg { real* d; real* s; unsigned n2; int op; };        // n2 = number of 
 struct SegList { Seg seg[SEG_MAX]; real scale; };
 #define SEG_BLOCKS 296                                        // blocks per segment: 2 per SM
 __global__ void __launch_bounds__(256) k_segments(const SegList L) {
+    PDL_ENTER
     const Seg g = L.seg[blockIdx.y];
 #ifdef MPASB_SINGLE
     typedef float2 v2;

@@ -468,6 +468,7 @@ __global__ void k_dt_cell_f(const Dev D, const DynTendArgs A) {
 __global__ void k_smlstep_pert(const Dev D) {
     KI;
     if (i >= D.nCellsSolve || k < 1 || k >= nl) return;
+    if (D.bdyMaskCell[i] > 5) return;              // no conversion in the specified zone of a regional run, TI:2482
     const int ne = D.nEdgesOnCell[i];
     const real fm = D.fzm[k], fp = D.fzp[k];
     real wt = AT(D.tend_w, i, k);

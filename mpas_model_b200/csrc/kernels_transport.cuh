@@ -15,6 +15,18 @@ __global__ void k_scalars_edge(const Dev D) {
     RP ac = D.adv_coefs + (size_t)i * 15;
     RP ac3 = D.adv_coefs_3rd + (size_t)i * 15;
     const real su = sign1(AT(D.ruAvg, i, k));
+    if (D.apply_lbcs && D.bdyMaskEdge[i] >= 4) {            // regional run, TI:3732-3750: the two outermost relaxation-zone edges
+        if (D.bdyMaskEdge[i] > 5) return;                    // take the upwind value, edges of the specified zone nothing
+        const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+        const real u_direction = copysign((real)0.5, AT(D.ruAvg, i, k));
+        const real u_positive = D.dvEdge[i] * fabs(u_direction + 0.5);
+        const real u_negative = D.dvEdge[i] * fabs(u_direction - 0.5);
+        for (int s = 0; s < D.num_scalars; s++) {
+            RP q = D.scalars_2 + (size_t)s * D.cellPlane;
+            AT(D.horiz_flux_arr + (size_t)s * D.edgePlane, i, k) = u_positive * AT(q, cell1, k) + u_negative * AT(q, cell2, k);
+        }
+        return;
+    }
     for (int s = 0; s < D.num_scalars; s++) {
         RP q = D.scalars_2 + (size_t)s * D.cellPlane;
         real acc; int j0;
@@ -40,7 +52,7 @@ __device__ __forceinline__ real wdtn_raw(const real* __restrict__ q, const real*
 // ---- owned cells: flux divergence + vertical flux + update, TI:3773-3846
 __global__ void k_scalars_cell(const Dev D, real dt, real weight_time_old, real weight_time_new, real coef3) {
     KI;
-    const bool act = i < D.nCellsSolve && k < nl;
+    const bool act = i < D.nCellsSolve && k < nl && D.bdyMaskCell[min(i, D.nCells)] <= 5;       // TI:3775: not the specified zone
     const int ne = act ? D.nEdgesOnCell[i] : 0;
     const real rho_old = act ? AT(D.rho_zz, i, k) : 1.0, rho_new = act ? AT(D.rho_zz_2, i, k) : 1.0;
     const real rho_zz_new_inv = 1.0 / (weight_time_old * rho_old + weight_time_new * rho_new);
@@ -170,7 +182,10 @@ __global__ void k_mono_edge2(const Dev D, int s, real dt) {
     }
     const real fup = D.dvEdge[i] * dt * (rmax(0.0, uh) * AT(so, cell1, k) + rmin(0.0, uh) * AT(so, cell2, k));
     AT(D.flux_upwind_tmp, i, k) = fup;
-    AT(D.flux_tmp, i, k) = dt * flux - fup;
+    // TI:4479 (and :4592), as written there: `config_apply_lbcs .and. (m == nRelaxZone) .or. (m == nRelaxZone-1)`
+    const int m = D.bdyMaskEdge[i];
+    const bool upwind_only = (D.apply_lbcs && m == 5) || m == 4;
+    AT(D.flux_tmp, i, k) = upwind_only ? (real)0.0 : dt * flux - fup;
 }
 // (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
 __global__ void k_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
@@ -221,6 +236,7 @@ __global__ void k_mono_cell5(const Dev D, int s, const real* __restrict__ rho_di
     KI;
     if (i >= D.nCells || k >= nl) return;
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
+    if (D.bdyMaskCell[i] > 2) return;              // TI:4709 `bdyMaskCell <= nSpecZone`: these cells are set after the transport
     if (i >= D.nCellsSolve) { AT(out, i, k) = rmax(0.0, AT(out, i, k)); return; }
     const real w0 = mono_wdtn_scaled(D, k, i, LDK, nl), w1 = mono_wdtn_scaled(D, k + 1, i, LDK, nl);
     const int ne = D.nEdgesOnCell[i];

@@ -21,6 +21,7 @@
 #include "kernels_transport.cuh"
 #include "kernels_col.cuh"
 #include "kernels_output.cuh"
+#include "kernels_lbc.cuh"
 #include "halo.cuh"
 
 enum { T_REAL = 0, T_INT = 1 };
@@ -56,7 +57,9 @@ struct mpasb_handle_s {
     bool ru_p_pending = false;     // first-small-step ru_p/ruAvg still to be written by the divergence-damping kernel
     bool dd_deferred = false;      // divergence damping of the last small step still to be applied (by the next edge kernel)
     real dd_coef = 0.0, dd_dts = 0.0;
+    real lbc_dt_end = 0.0;         // regional runs: seconds from the start of the next step to the end of the LBC interval
     bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
+    bool pdl = true;               // MPASB_PDL=0: no programmatic dependent launch
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
@@ -127,7 +130,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 2;      // fail loudly: no CPU fallback
     if (device < 0 || device >= ndev) return 3;
-    if (dims->nVertLevels < 4 || dims->maxEdges < 1 || cfg->config_apply_lbcs) return 4;
+    if (dims->nVertLevels < 4 || dims->maxEdges < 1) return 4;
     H* h = new H();
     h->dims = *dims; h->cfg = *cfg; h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return 5; }
@@ -143,6 +146,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->overlap = !getenv("MPASB_NO_OVERLAP");
     h->relaxed = !mpasb_strict_arithmetic();
     h->fuse_dd = !getenv("MPASB_NO_DD_FUSE");
+    if (const char* e = getenv("MPASB_PDL")) h->pdl = atoi(e) != 0;
     memset(&h->D, 0, sizeof(Dev));
     h->D.pf_next = 1;
     if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
@@ -152,6 +156,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     D.nl = dims->nVertLevels; D.LDKA = (dims->nVertLevels + 1 + 1) / 2 * 2; D.LDK = D.LDKA;
     if (const char* al = getenv("MPASB_LDK_ALIGN")) { const int a = std::max(2, atoi(al)) / 2 * 2; D.LDK = (D.LDKA + a - 1) / a * a; }
     D.maxEdges = dims->maxEdges; D.maxEdges2 = dims->maxEdges2; D.num_scalars = dims->num_scalars;
+    D.apply_lbcs = cfg->config_apply_lbcs != 0;
     D.index_qv = dims->index_qv - 1; D.moist_start = dims->moist_start - 1; D.moist_end = dims->moist_end - 1;
     D.cellPlane = (size_t)(dims->nCells + 1) * D.LDK; D.edgePlane = (size_t)(dims->nEdges + 1) * D.LDK;
     h->cpb = std::max(1, 256 / D.LDK);
@@ -446,7 +451,8 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
     if (!strcmp(name, "nEdgesOnCell")) {
         h->max_ne = 0;
         for (long n = 0; n < count; n++) h->max_ne = std::max(h->max_ne, src[n]);
-        h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS");
+        h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS") &&
+                     !h->cfg.config_apply_lbcs;       // the bdyMask / specZoneMask branches of a regional run live in the generic family
     }
     if (!strcmp(name, "advCellsForEdge")) { h->hc_advCells.assign(src, src + count); h->tiles_dirty = true; }
     if (!strcmp(name, "nAdvCellsForEdge")) { h->hc_nAdv.assign(src, src + count); h->tiles_dirty = true; }
@@ -499,7 +505,18 @@ struct KScope {
     }
 };
 #define LAUNCH(kern, n, smem, ...) do { KScope ks_(h, "k:" #kern); kern<<<GRID(n), smem, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
-#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<(unsigned)(((n) + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+// Launch of a kernel that contains pdl_wait() (every column-warp kernel, k_segments): with programmatic dependent launch its
+// blocks may become resident while the previous kernel of the stream drains (mpasb_dev.cuh); MPASB_PDL=0 launches them plainly.
+template <typename... P, typename... A>
+static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization; at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+#define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + CW_WARPS - 1) / CW_WARPS)), dim3(CW_THREADS), 0, __VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -516,7 +533,7 @@ struct SegBuilder {       // collects the column ranges of one routine into one 
     void flush() {
         if (!n) return;
         KScope ks_(h, "k:k_segments");
-        k_segments<<<dim3(SEG_BLOCKS, n), 256, 0, h->stream>>>(L);
+        klaunch(h, k_segments, dim3(SEG_BLOCKS, n), dim3(256), 0, L);
         h->launches++; n = 0;
     }
 };
@@ -550,7 +567,7 @@ static void compute_vert_imp_coefs(H* h, real dts) {   // TI:2225-2366
         const size_t smem3 = (size_t)3 * VIC_COLS * (h->D.LDK | 1) * sizeof(real);
         if (!h->smem_attr_vic) { cudaFuncSetAttribute(k3_vert_imp_coefs, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); h->smem_attr_vic = true; }
         KScope ks_(h, "k:k3_vert_imp_coefs");
-        k3_vert_imp_coefs<<<(unsigned)((h->D.nCellsSolve + VIC_COLS - 1) / VIC_COLS), VIC_WARPS * 32, smem3, h->stream>>>(h->D, dtseps, c2, rcv);
+        klaunch(h, k3_vert_imp_coefs, dim3((unsigned)((h->D.nCellsSolve + VIC_COLS - 1) / VIC_COLS)), dim3(VIC_WARPS * 32), smem3, h->D, dtseps, c2, rcv);
         h->launches++;
         return;
     }
@@ -806,14 +823,14 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
             static const bool one_field_per_warp = getenv("MPASB_FLUX_SPLIT") != nullptr;      // measured slower: 1.40 vs 0.96 ms/step
             if (one_field_per_warp) {
                 KScope ks_(h, "k:k5s_flux_cell");
-                k5s_flux_cell<<<(unsigned)((2 * (size_t)D.nCellsSolve + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, h->stream>>>(D);
+                klaunch(h, k5s_flux_cell, dim3((unsigned)((2 * (size_t)D.nCellsSolve + CW_WARPS - 1) / CW_WARPS)), dim3(CW_THREADS), 0, D);
                 h->launches++;
             } else {
                 KScope ks_(h, "k:k5_flux_cell");
                 static int sm_count = 0;
                 if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
                 const unsigned need = (unsigned)((D.nCellsSolve + FX_WARPS - 1) / FX_WARPS), resident = (unsigned)(sm_count * FX_MINB);
-                k5_flux_cell<<<std::min(need, resident), FX_WARPS * 32, 0, h->stream>>>(D);       // persistent warps
+                klaunch(h, k5_flux_cell, dim3(std::min(need, resident)), dim3(FX_WARPS * 32), 0, D);       // persistent warps
                 h->launches++;
             }
             static const bool old_f = getenv("MPASB_OLD_CELL_F") != nullptr;
@@ -824,7 +841,7 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
                 static const int variant = getenv("MPASB_CF7") ? atoi(getenv("MPASB_CF7")) : 0;
                 KScope ks_(h, "k:k7_dt_cell_f");
 #define CF7_LAUNCH(W, MB) do { const unsigned need = (unsigned)((D.nCellsSolve + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
-                    k7_dt_cell_f<W, MB><<<std::min(need, resident), (W) * 32, 0, h->stream>>>(D, A); } while (0)
+                    klaunch(h, k7_dt_cell_f<W, MB>, dim3(std::min(need, resident)), dim3((W) * 32), 0, D, A); } while (0)
                 if (variant == 1) CF7_LAUNCH(4, 3);            // 168 registers, 12 warps per SM
                 else CF7_LAUNCH(8, 2);                         // 128 registers, 16 warps per SM
 #undef CF7_LAUNCH
@@ -834,8 +851,8 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
             if (h->tiles_dirty) build_flux_tiles(h);
             if (h->tiles_ok) {
                 KScope ks_(h, "k:k4_dt_edge_flux");
-                k4_dt_edge_flux<<<(unsigned)((D.nEdges + EF_EB - 1) / EF_EB), CW_THREADS, 2 * EF_MAXT * D.LDK * sizeof(real), h->stream>>>(
-                    D, h->d_tile_hdr, h->d_tile_runs, h->d_tile_slot);
+                klaunch(h, k4_dt_edge_flux, dim3((unsigned)((D.nEdges + EF_EB - 1) / EF_EB)), dim3(CW_THREADS), 2 * EF_MAXT * D.LDK * sizeof(real),
+                        D, (const int4*)h->d_tile_hdr, (const int4*)h->d_tile_runs, (const unsigned char*)h->d_tile_slot);
                 h->launches++;
             }
             else LAUNCHW(k2_dt_edge_flux, D.nEdges, D);
@@ -880,7 +897,7 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
             static const int variant = getenv("MPASB_AC6") ? atoi(getenv("MPASB_AC6")) : 1;
             KScope ks_(h, "k:k6_acoustic_cell");
 #define AC6_LAUNCH(W, MB) do { const unsigned need = (unsigned)((h->D.nCells + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
-                k6_acoustic_cell<W, MB><<<std::min(need, resident), (W) * 32, 0, h->stream>>>(h->D, dts, small_step, epssm, resm); } while (0)
+                klaunch(h, k6_acoustic_cell<W, MB>, dim3(std::min(need, resident)), dim3((W) * 32), 0, h->D, dts, small_step, epssm, resm); } while (0)
             if (variant == 0) AC6_LAUNCH(8, 2);            // 128 registers, 16 warps per SM
             else if (variant == 2) AC6_LAUNCH(4, 4);       // 128 registers, 16 warps per SM in smaller blocks
             else AC6_LAUNCH(4, 3);                         // 168 registers, 12 warps per SM
@@ -891,13 +908,14 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
         if (!h->smem_attr_ac) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); h->smem_attr_ac = true; }
         KScope ks_(h, "k:k3_acoustic_cell");
-        k3_acoustic_cell<<<(unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS), AC3_WARPS * 32, smem3, h->stream>>>(h->D, dts, small_step, epssm, resm);
+        klaunch(h, k3_acoustic_cell, dim3((unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS)), dim3(AC3_WARPS * 32), smem3, h->D, dts, small_step, epssm, resm);
         h->launches++;
         return;
     }
     LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
+    if (h->D.apply_lbcs) LAUNCH(k_lbc_acoustic_spec, h->D.nCellsSolve, 0, h->D, dts, small_step, epssm);      // TI:2962-2971
 }
 // defer: the next kernel that reads ru_p (the edge update of the next small step, or -- single block -- the edge part of
 // recover_large_step_variables) applies the damping in registers; same arithmetic, one kernel and one ru_p round trip less
@@ -1051,6 +1069,36 @@ static void compute_output_diagnostics(H* h, int time_lev) {
     LAUNCH(k_output_diagnostics, D.nCells, 0, D, time_lev == 2 ? D.theta_m_2 : D.theta_m, time_lev == 2 ? D.rho_zz_2 : D.rho_zz, qv, rv / rgas);
 }
 
+// ------------------------------------------------------------------ regional runs (config_apply_lbcs), kernels_lbc.cuh
+// delta_t as in mpas_atm_get_bdy_state (mpas_atm_boundaries.F:497-503): dt = (LBC_intv_end - currTime) - delta_t, in RKIND
+static real lbc_dtl(H* h, real delta_t) { real dt = h->lbc_dt_end; dt = dt - delta_t; return dt; }
+static void lbc_speczone_tend(H* h) {                              // TI:1218-1239
+    Scope sc(h, "atm_bdy_adjust_dynamics_speczone_tend");
+    LAUNCH(k_lbc_speczone_cell, h->D.nCellsSolve, 0, h->D);
+    LAUNCH(k_lbc_speczone_edge, h->D.nEdgesSolve, 0, h->D);
+}
+static void lbc_relaxzone_tend(H* h, real time_dyn_step, real dt) {    // TI:1243-1267
+    Scope sc(h, "atm_bdy_adjust_dynamics_relaxzone_tend");
+    const real dtl = lbc_dtl(h, time_dyn_step);
+    LAUNCH(k_lbc_relax_cell, h->D.nCellsSolve, 0, h->D, dt, dtl);
+    LAUNCH(k_lbc_relax_edge, h->D.nEdges, 0, h->D, dt, dtl, (real)h->cfg.config_relax_zone_divdamp_coef);
+}
+static void lbc_reset_u_ru(H* h, real time_dyn_step) { LAUNCH(k_lbc_reset_u_ru, h->D.nEdges, 0, h->D, lbc_dtl(h, time_dyn_step)); }    // TI:1343-1388
+static void lbc_adjust_scalars(H* h, real dt, real dt_rk) {        // TI:1413-1428, 1565-1580
+    Scope sc(h, "atm_bdy_adjust_scalars");
+    const real dtl = lbc_dtl(h, dt_rk);
+    for (int s = 0; s < h->D.num_scalars; s++) {
+        LAUNCH(k_lbc_adjust_scalars_a, h->D.nCellsSolve, 0, h->D, s, dt, dt_rk, dtl, h->D.scalar_new);
+        LAUNCH(k_lbc_adjust_scalars_b, h->D.nCellsSolve, 0, h->D, s, h->D.scalar_new);
+    }
+}
+static void lbc_zero_gradient_w(H* h) { LAUNCH(k_lbc_zero_w, h->D.nCellsSolve, 0, h->D); }                  // TI:1477-1484
+static void lbc_reset_speczone_values(H* h, real dt) { LAUNCH(k_lbc_reset_speczone, h->D.nCellsSolve, 0, h->D, lbc_dtl(h, dt)); }   // TI:1676-1695
+static void lbc_set_scalars(H* h, real dt) {                       // TI:1700-1719
+    const real dtl = lbc_dtl(h, dt);
+    for (int s = 0; s < h->D.num_scalars; s++) LAUNCH(k_lbc_set_scalars, h->D.nCellsSolve, 0, h->D, s, dtl);
+}
+
 // ------------------------------------------------------------------ halo exchange (mpas_halo.F:498-846)
 #include "halo_host.inl"
 
@@ -1106,6 +1154,7 @@ static int srk3(H* h, real dt) {
     } else { h->err = "config_time_integration_order must be 2 or 3"; return 1; }
     // config_split_dynamics_transport = false: the scalars are advanced inside the dynamics RK loop (TI:1404-1407)
     const bool coupled_transport = c.config_scalar_advection && !c.config_split_dynamics_transport;
+    const bool lbcs = c.config_apply_lbcs != 0;               // regional run: TI:1218-1268, 1343-1430, 1477-1484, 1560-1582, 1676-1720
     auto advance_scalars_stage = [&](int rk_step, real dt_rk) -> int {        // advance_scalars, TI:1730-1927
         if (rk_step < 3 || (!c.config_monotonic && !c.config_positive_definite)) { advance_scalars(h, dt_rk, rk_step); return 0; }
         return advance_scalars_mono(h, dt_rk);
@@ -1121,6 +1170,8 @@ static int srk3(H* h, real dt) {
             if (c.config_time_integration_order == 3 && rk_step == 2) compute_vert_imp_coefs(h, rk_sub_timestep[rk_step]);
             if (compute_dyn_tend(h, rk_step, dt, true)) return 1;        // starts the exchange of tend_u (TI:1228)
             comm_wait(h);
+            const real time_dyn_step = dt_dynamics * (real)(dynamics_substep - 1) + rk_timestep[rk_step];        // TI:1246
+            if (lbcs) { lbc_speczone_tend(h); lbc_relaxzone_tend(h, time_dyn_step, dt); }                          // TI:1218-1268
             set_smlstep_pert_variables(h);
             for (int small_step = 1; small_step <= number_sub_steps[rk_step]; small_step++) {
                 // TI:1279 exchanges rho_pp before every acoustic step.  On the first small step nothing reads the
@@ -1133,14 +1184,25 @@ static int srk3(H* h, real dt) {
                 divergence_damping_3d(h, rk_sub_timestep[rk_step], more || !h->halo.active);
             }
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
-            if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, true)) return 1;   // starts u_3 (TI:1371)
+            if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, !lbcs)) return 1;   // starts u_3 (TI:1371)
             comm_wait(h);
-            if (coupled_transport && advance_scalars_stage(rk_step, rk_timestep[rk_step])) return 1;
+            if (lbcs) {                                           // TI:1343-1395: driving u, ru in the specified zone, then all three edge layers
+                lbc_reset_u_ru(h, time_dyn_step);
+                if (exchange(h, "dynamics:u_123")) return 1;
+            }
+            if (coupled_transport) {
+                if (advance_scalars_stage(rk_step, rk_timestep[rk_step])) return 1;
+                if (lbcs) {                                       // TI:1409-1430
+                    if (exchange(h, "dynamics:scalars")) return 1;
+                    lbc_adjust_scalars(h, dt, rk_timestep[rk_step]);
+                }
+            }
             compute_solve_diagnostics(h, dt, 2, rk_step);
             // TI:1424.  Stages 1 and 2: the next kernels (vertical coefficients, first cell kernel of the tendencies) read none
             // of the three fields, so the exchange overlaps them; after stage 3 the substep roll copies w and must wait
             const char* grp = coupled_transport ? "dynamics:w,pv_edge,rho_edge,scalars" : "dynamics:w,pv_edge,rho_edge";      // TI:1463-1473
-            if (rk_step < 3 ? exchange_async(h, grp) : exchange(h, grp)) return 1;
+            if (rk_step < 3 && !lbcs ? exchange_async(h, grp) : exchange(h, grp)) return 1;
+            if (lbcs) { lbc_zero_gradient_w(h); if (exchange(h, "dynamics:w")) return 1; }       // TI:1477-1484
         }
         if (dynamics_substep < dynamics_split)
             if (exchange(h, "dynamics:theta_m,pressure_p,rtheta_p")) return 1;
@@ -1151,8 +1213,17 @@ static int srk3(H* h, real dt) {
         if (c.config_time_integration_order == 2) rk_timestep[1] = dt / 2.;
         for (int rk_step = 1; rk_step <= 3; rk_step++) {
             if (advance_scalars_stage(rk_step, rk_timestep[rk_step])) return 1;
+            if (lbcs) {                                           // TI:1560-1582
+                if (exchange(h, "dynamics:scalars")) return 1;
+                lbc_adjust_scalars(h, dt, rk_timestep[rk_step]);
+            }
             if (rk_step < 3) if (exchange(h, "dynamics:scalars")) return 1;
         }
+    }
+    if (lbcs) {                                                   // TI:1676-1720
+        lbc_reset_speczone_values(h, dt);
+        if (exchange(h, "dynamics:scalars")) return 1;
+        lbc_set_scalars(h, dt);
     }
     comm_wait(h);
     reconstruct(h, 2, 0);                         // TI:1596-1611: uReconstruct* from u (time level 2), owned cells
@@ -1252,6 +1323,22 @@ extern "C" int mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt) ENTRY
 extern "C" int mpasb_init_solve_diagnostics_async(mpasb_handle h, mpasb_real dt) { cudaSetDevice(h->device); compute_solve_diagnostics(h, dt, 1, 0); return 0; }
 extern "C" int mpasb_reconstruct(mpasb_handle h, int time_level, int include_halos) ENTRY(reconstruct(h, time_level, include_halos))
 extern "C" int mpasb_compute_output_diagnostics(mpasb_handle h, int time_level) ENTRY(compute_output_diagnostics(h, time_level))
+extern "C" int mpasb_set_lbc_time(mpasb_handle h, mpasb_real seconds_to_interval_end) { h->lbc_dt_end = seconds_to_interval_end; return 0; }
+// the regional-path routines one at a time (parity tests); a, b: the real arguments of the reference call (see kernels_lbc.cuh)
+extern "C" int mpasb_k_lbc(mpasb_handle h, const char* routine, mpasb_real a, mpasb_real b) {
+    cudaSetDevice(h->device);
+    const std::string r = routine;
+    if (r == "speczone_tend") lbc_speczone_tend(h);
+    else if (r == "relaxzone_tend") lbc_relaxzone_tend(h, a, b);          // a = time_dyn_step, b = dt
+    else if (r == "reset_u_ru") lbc_reset_u_ru(h, a);                     // a = time_dyn_step
+    else if (r == "adjust_scalars") lbc_adjust_scalars(h, a, b);          // a = dt, b = rk_timestep(rk_step)
+    else if (r == "zero_gradient_w") lbc_zero_gradient_w(h);
+    else if (r == "reset_speczone_values") lbc_reset_speczone_values(h, a);    // a = dt
+    else if (r == "set_scalars") lbc_set_scalars(h, a);                   // a = dt
+    else { h->err = "mpasb_k_lbc: unknown routine " + r; return 1; }
+    CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError());
+    return 0;
+}
 extern "C" int mpasb_k_rk_integration_setup(mpasb_handle h) ENTRY(rk_integration_setup(h))
 extern "C" int mpasb_k_compute_moist_coefficients(mpasb_handle h) ENTRY(compute_moist_coefficients(h))
 extern "C" int mpasb_k_compute_vert_imp_coefs(mpasb_handle h, mpasb_real dts) ENTRY(compute_vert_imp_coefs(h, dts))

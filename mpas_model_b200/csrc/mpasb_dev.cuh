@@ -18,6 +18,15 @@ typedef float real;
 typedef double real;
 #endif
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still draining.  pdl_trigger() lets the successor of THIS kernel
+// do that (its blocks take the SM slots this kernel's last wave vacates); pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible.  Everything before pdl_wait() may only touch data no kernel of the step writes (mesh
+// connectivity, weights); launched without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define PDL_ENTER pdl_trigger(); pdl_wait();
+
 enum { LOC_CELL = 0, LOC_EDGE = 1, LOC_VERTEX = 2, LOC_LEVS = 3 };
 enum { IN_ONE, IN_NL, IN_NL1, IN_ME, IN_ME2, IN_VD, IN_TWO, IN_F15, IN_NL1_ME, IN_S_NL, IN_NL_TWO, IN_THREE_ME };
 
@@ -34,6 +43,7 @@ struct Dev {
     int LDKA;          // active width: nVertLevels+1 rounded up to an even count; rows [LDKA, LDK) are never touched
     int maxEdges, maxEdges2, num_scalars;
     int index_qv, moist_start, moist_end;      // 0-based
+    int apply_lbcs;    // config_apply_lbcs: regional run (kernels_lbc.cuh and the bdyMask branches of the work routines)
     size_t cellPlane, edgePlane;               // (n+1)*LDK, stride between scalar planes
     // derived, library-internal: 1 where any zb_cell/zb3_cell entry of the cell is non-zero (terrain slope);
     // cells with 0 skip the 2 x maxEdges x nVertLevels metric reads of TI:2480-2500 and TI:3379-3414

@@ -45,7 +45,7 @@ _CFG_REAL = ("config_epssm", "config_smdiv", "config_len_disp", "config_coef_3rd
              "config_h_mom_eddy_visc2", "config_h_mom_eddy_visc4", "config_v_mom_eddy_visc2",
              "config_h_theta_eddy_visc2", "config_h_theta_eddy_visc4", "config_v_theta_eddy_visc2",
              "config_apvm_upwinding", "config_mpas_cam_coef", "config_rayleigh_damp_u_timescale_days",
-             "cf1", "cf2", "cf3", "sphere_radius")
+             "config_relax_zone_divdamp_coef", "cf1", "cf2", "cf3", "sphere_radius")
 
 
 class Config(C.Structure):
@@ -350,6 +350,14 @@ class Dycore(Backend):
 
     # -- one *_work routine at a time (parity tests)
     def k(self, routine, *args):
+        if routine.startswith("lbc_"):            # regional path: mpasb_k_lbc(handle, routine, a, b)
+            ra = [float(a) for a in args] + [0.0, 0.0]
+            self._check(self.lib.mpasb_k_lbc(self._h, routine[4:].encode(), self.creal(ra[0]), self.creal(ra[1])), routine)
+            return
         fn = getattr(self.lib, "mpasb_k_" + routine)
         cargs = [self.creal(a) if isinstance(a, float) else C.c_int(a) for a in args]
         self._check(fn(self._h, *cargs), routine)
+
+    def set_lbc_time(self, seconds_to_interval_end: float):
+        """Regional runs: LBC_intv_end - currTime at the start of the next step (mpas_atm_boundaries.F:497-503)."""
+        self._check(self.lib.mpasb_set_lbc_time(self._h, self.creal(seconds_to_interval_end)), "set_lbc_time")

@@ -31,7 +31,7 @@ def default_config(len_disp: float, dt: float) -> dict:
         config_h_ScaleWithMesh=True, config_zd=22000.0, config_xnutr=0.2,
         config_mpas_cam_coef=0.0, config_number_cam_damping_levels=4,
         config_rayleigh_damp_u=False, config_rayleigh_damp_u_timescale_days=5.0,
-        config_number_rayleigh_damp_u_levels=6, config_apply_lbcs=False,
+        config_number_rayleigh_damp_u_levels=6, config_apply_lbcs=False, config_relax_zone_divdamp_coef=6.0,
     )
 
 
@@ -161,6 +161,12 @@ def init_block(d: dict, cfg: dict) -> dict:
     d["specZoneMaskEdge"] = np.zeros(nE + 1)
     d["bdyMaskCell"] = np.zeros(nC + 1, dtype=np.int32)
     d["bdyMaskEdge"] = np.zeros(nE + 1, dtype=np.int32)
+    # relaxation-zone scalings of a regional run (mpas_atm_core.F:1131-1146)
+    d["meshScalingRegionalCell"] = np.ones(nC + 1)
+    d["meshScalingRegionalEdge"] = np.ones(nE + 1)
+    if cfg["config_h_ScaleWithMesh"]:
+        d["meshScalingRegionalEdge"][:nE] = 1.0 / ((md[c1[:nE]] + md[c2[:nE]]) / 2.0) ** 0.25
+        d["meshScalingRegionalCell"][:nC] = 1.0 / md[:nC] ** 0.25
     # mpas_atm_core.F:534-535: mpas_rbf_interp_initialize (-> mpas_initialize_vectors), mpas_init_reconstruct -> coeffs_reconstruct (owned cells)
     from .reconstruct import mpas_init_reconstruct
     mpas_init_reconstruct(d)

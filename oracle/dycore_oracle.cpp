@@ -42,7 +42,7 @@ struct OCfg {
     real config_epssm, config_smdiv, config_len_disp, config_coef_3rd_order, config_visc4_2dsmag, config_smagorinsky_coef,
          config_del4u_div_factor, config_h_mom_eddy_visc2, config_h_mom_eddy_visc4, config_v_mom_eddy_visc2,
          config_h_theta_eddy_visc2, config_h_theta_eddy_visc4, config_v_theta_eddy_visc2, config_apvm_upwinding,
-         config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days, cf1, cf2, cf3, sphere_radius;
+         config_mpas_cam_coef, config_rayleigh_damp_u_timescale_days, config_relax_zone_divdamp_coef, cf1, cf2, cf3, sphere_radius;
     int on_a_sphere;
     OCfg() {}
     explicit OCfg(const mpasb_config& c) {
@@ -55,7 +55,7 @@ struct OCfg {
         CR(config_epssm) CR(config_smdiv) CR(config_len_disp) CR(config_coef_3rd_order) CR(config_visc4_2dsmag) CR(config_smagorinsky_coef)
         CR(config_del4u_div_factor) CR(config_h_mom_eddy_visc2) CR(config_h_mom_eddy_visc4) CR(config_v_mom_eddy_visc2)
         CR(config_h_theta_eddy_visc2) CR(config_h_theta_eddy_visc4) CR(config_v_theta_eddy_visc2) CR(config_apvm_upwinding)
-        CR(config_mpas_cam_coef) CR(config_rayleigh_damp_u_timescale_days) CR(cf1) CR(cf2) CR(cf3) CR(sphere_radius)
+        CR(config_mpas_cam_coef) CR(config_rayleigh_damp_u_timescale_days) CR(config_relax_zone_divdamp_coef) CR(cf1) CR(cf2) CR(cf3) CR(sphere_radius)
 #undef CI
 #undef CR
     }

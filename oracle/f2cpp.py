@@ -1063,6 +1063,10 @@ TI_ROUTINES = [
     "atm_compute_solve_diagnostics_work", "atm_compute_solve_diagnostics",
     "atm_rk_integration_setup", "atm_compute_moist_coefficients", "atm_init_coupled_diagnostics",
     "atm_rk_dynamics_substep_finish",
+    # regional (limited-area) path, config_apply_lbcs (TI:7198-7910)
+    "atm_zero_gradient_w_bdy_work", "atm_zero_gradient_w_bdy", "atm_bdy_adjust_dynamics_speczone_tend",
+    "atm_bdy_adjust_dynamics_relaxzone_tend", "atm_bdy_reset_speczone_values", "atm_bdy_adjust_scalars_work", "atm_bdy_adjust_scalars",
+    "atm_bdy_set_scalars_work", "atm_bdy_set_scalars",
 ]
 
 

@@ -79,6 +79,7 @@ class RefDycore(Backend):
                 self.lib.ref_set_cfg_real(self._h, k.encode(), C.c_double(float(v)))
         self.lib.ref_set_cfg_real(self._h, b"sphere_radius", C.c_double(float(block["sphere_radius"])))
         self.lib.ref_set_cfg_int(self._h, b"config_apply_lbcs", C.c_int(int(cfg.get("config_apply_lbcs", 0))))
+        self.set_lbc_time(0.0)
         # host arrays in the reference's layout
         self.a = {}
         for name, fd in FIELDS.items():
@@ -95,8 +96,7 @@ class RefDycore(Backend):
             ("tend", "w_pgf"): np.zeros((nC + 1, nl + 1), dtype=self.rdtype), ("tend", "w_buoy"): np.zeros((nC + 1, nl + 1), dtype=self.rdtype),
             # inputs / outputs of the init-time routines of mpas_atm_core.F (atm_compute_mesh_scaling, ...)
             ("mesh", "meshDensity"): np.ones(nC + 1, dtype=self.rdtype),
-            ("mesh", "meshScalingRegionalCell"): np.zeros(nC + 1, dtype=self.rdtype),
-            ("mesh", "meshScalingRegionalEdge"): np.zeros(nE + 1, dtype=self.rdtype),
+            ("mesh", "nearestRelaxationCell"): np.zeros(nC + 1, dtype=np.int32),
         }
         for k in ("zb", "zb3", "deriv_two", "meshDensity"):
             if k in block and np.shape(block[k]) == self.extra[("mesh", k)].shape:
@@ -104,6 +104,10 @@ class RefDycore(Backend):
         self._bind_all()
         self.load_block(block)
         self.set_threads(threads)
+
+    def set_lbc_time(self, seconds_to_interval_end: float):
+        """LBC_intv_end - currTime at the start of the next step (mpas_atm_boundaries.F:497-503)."""
+        self.lib.ref_set_cfg_real(self._h, b"lbc_dt_end", C.c_double(float(seconds_to_interval_end)))
 
     def set_threads(self, n: int):
         """OpenMP threads, each with the index ranges of mpas_atm_threading.F:100-111 (the reference's MPAS_OPENMP build)."""
@@ -175,24 +179,41 @@ class RefDycore(Backend):
 
         for n in ("tend_ru_physics", "tend_rtheta_physics", "tend_rho_physics"):     # TI:1091-1093 (no physics)
             self.a[(n, 1)][...] = 0.0
+        lbcs = bool(cfg.get("config_apply_lbcs", False))
         self.k("rk_integration_setup"); self.k("compute_moist_coefficients")
         for ds in range(1, split + 1):
             self.k("compute_vert_imp_coefs", rk_s[0])
             for rk in (1, 2, 3):
                 if order == 3 and rk == 2:
                     self.k("compute_vert_imp_coefs", rk_s[rk - 1])
-                self.k("compute_dyn_tend", rk, float(dt)); self.k("set_smlstep_pert_variables")
+                self.k("compute_dyn_tend", rk, float(dt))
+                time_dyn_step = dt_dyn * float(ds - 1) + rk_t[rk - 1]             # TI:1246
+                if lbcs:                                                          # TI:1218-1268
+                    self.k("lbc_speczone_tend")
+                    self.k("lbc_relaxzone_tend", float(time_dyn_step), float(dt))
+                self.k("set_smlstep_pert_variables")
                 for ss in range(1, n_sub[rk - 1] + 1):
                     self.k("advance_acoustic_step", rk_s[rk - 1], ss); self.k("divergence_damping_3d", rk_s[rk - 1])
                 self.k("recover_large_step_variables", rk_t[rk - 1], n_sub[rk - 1], rk)
+                if lbcs:                                                          # TI:1343-1388
+                    self.k("lbc_reset_u_ru", float(time_dyn_step))
                 if coupled:
                     scalars(rk, rk_t[rk - 1])
+                    if lbcs:                                                      # TI:1409-1430
+                        self.k("lbc_adjust_scalars", float(dt), float(rk_t[rk - 1]))
                 self.k("compute_solve_diagnostics", float(dt), rk)
+                if lbcs:                                                          # TI:1477-1484
+                    self.k("lbc_zero_gradient_w")
             self.k("rk_dynamics_substep_finish", ds, split)
         if cfg["config_scalar_advection"] and not coupled:
             rk_t = [dt / 2.0 if order == 2 else dt / 3.0, dt / 2.0, float(dt)]
             for rk in (1, 2, 3):
                 scalars(rk, rk_t[rk - 1])
+                if lbcs:                                                          # TI:1560-1582
+                    self.k("lbc_adjust_scalars", float(dt), float(rk_t[rk - 1]))
+        if lbcs:                                                                  # TI:1676-1720
+            self.k("lbc_reset_speczone_values", float(dt))
+            self.k("lbc_set_scalars", float(dt))
 
     def atm_init_coupled_diagnostics(self): self.k("init_coupled_diagnostics")
     def atm_init_solve_diagnostics(self, dt): self.k("init_solve_diagnostics", float(dt))

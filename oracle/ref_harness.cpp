@@ -144,6 +144,64 @@ int ref_call(void* h, const char* routine, const int* ia, const double* ra) {
                                  CELLS, EDGES, CELLS_SOLVE, scalar_old_arr, scalar_new_arr, s_max_arr, s_min_arr, wdtn_arr,
                                  flux_array, flux_upwind_tmp_arr, flux_tmp_arr, xch,
                                  Opt<bool>(b->cfgs.at("config_split_dynamics_transport").i != 0), rho_zz_int);
+    // ---- regional path (config_apply_lbcs).  The driving fields come from mpas_atm_get_bdy_tend / _state
+    // (mpas_atm_boundaries.F:375-437, 473-674), restated by bdy_tend / bdy_state below: tendency = time level 1 of lbc_<field>,
+    // state at now + delta_t = level 2 - (seconds to the end of the LBC interval - delta_t) * level 1.  One thread, as TI does
+    // (`do thread=1,nThreads` loops inside a single region are serial calls with thread ranges: same result).
+    else if (r.rfind("lbc_", 0) == 0) {
+#pragma omp master
+        {
+        const real dt_end = (real)b->cfgs.at("lbc_dt_end").r;
+        const int S = b->dims.at("num_scalars");
+        auto bdy_state = [&](const char* f, real delta_t, std::vector<real>& out, long n) {
+            FArr<real> tend = b->mesh.arr<real>(f, 1, 0), state = b->mesh.arr<real>(f, 2, 0);
+            real dtl = dt_end; dtl = dtl - delta_t;
+            out.resize(n);
+            for (long q = 0; q < n; q++) out[q] = state.p[q] - dtl * tend.p[q];
+        };
+        auto view2 = [&](std::vector<real>& v, long n1, long n2) { FArr<real> a; a.bind(v.data(), 1, n1, 1, n2); return a; };
+        std::vector<real> va, vb, vc;
+        const int one = 1;
+        if (r == "lbc_speczone_tend")                        // TI:1223-1235
+            atm_bdy_adjust_dynamics_speczone_tend(b->tend, b->mesh, b->configs, nVertLevels, b->mesh.arr<real>("lbc_ru", 1, 2),
+                                                  b->mesh.arr<real>("lbc_rtheta_m", 1, 2), b->mesh.arr<real>("lbc_rho_zz", 1, 2),
+                                                  one, nCells, one, nEdges, one, nCellsSolve, one, nEdgesSolve);
+        else if (r == "lbc_relaxzone_tend") {                // TI:1246-1261: ra[0] = time_dyn_step, ra[1] = dt
+            bdy_state("lbc_ru", (real)ra[0], va, (long)nVertLevels * (nEdges + 1));
+            bdy_state("lbc_rtheta_m", (real)ra[0], vb, (long)nVertLevels * (nCells + 1));
+            bdy_state("lbc_rho_zz", (real)ra[0], vc, (long)nVertLevels * (nCells + 1));
+            atm_bdy_adjust_dynamics_relaxzone_tend(b->configs, b->tend, b->state, b->diag, b->mesh, nVertLevels, (real)ra[1],
+                                                   view2(va, nVertLevels, nEdges + 1), view2(vb, nVertLevels, nCells + 1), view2(vc, nVertLevels, nCells + 1),
+                                                   one, nCells, one, nEdges, one, nCellsSolve, one, nEdgesSolve);
+        } else if (r == "lbc_reset_u_ru") {                  // TI:1343-1388 (inline in atm_srk3): ra[0] = time_dyn_step
+            FArr<int> bdyMaskEdge = b->mesh.arr<int>("bdyMaskEdge", 1, 1);
+            FArr<real> u = b->state.arr<real>("u", 2, 2), ru = b->diag.arr<real>("ru", 1, 2);
+            bdy_state("lbc_u", (real)ra[0], va, (long)nVertLevels * (nEdges + 1));
+            FArr<real> dv = view2(va, nVertLevels, nEdges + 1);
+            for (int iEdge = 1; iEdge <= nEdgesSolve; iEdge++)
+                if (bdyMaskEdge(iEdge) > nrelaxzone) for (int k = 1; k <= nVertLevels; k++) u(k, iEdge) = dv(k, iEdge);
+            bdy_state("lbc_ru", (real)ra[0], va, (long)nVertLevels * (nEdges + 1));
+            dv = view2(va, nVertLevels, nEdges + 1);
+            for (int iEdge = 1; iEdge <= nEdges; iEdge++)
+                if (bdyMaskEdge(iEdge) > nrelaxzone) for (int k = 1; k <= nVertLevels; k++) ru(k, iEdge) = dv(k, iEdge);
+        } else if (r == "lbc_adjust_scalars") {              // TI:1413-1428 / 1565-1580: ra[0] = dt, ra[1] = rk_timestep(rk_step)
+            bdy_state("lbc_scalars", (real)ra[1], va, (long)S * nVertLevels * (nCells + 1));
+            FArr<real> sd; sd.bind(va.data(), 1, S, 1, nVertLevels, 1, nCells + 1);
+            atm_bdy_adjust_scalars(b->state, b->diag, b->mesh, b->configs, sd, nVertLevels, (real)ra[0], (real)ra[1], one, nCells, one, nCellsSolve);
+        } else if (r == "lbc_zero_gradient_w")               // TI:1477-1484
+            atm_zero_gradient_w_bdy(b->state, b->mesh, one, nCellsSolve);
+        else if (r == "lbc_reset_speczone_values") {         // TI:1676-1695: ra[0] = dt
+            bdy_state("lbc_rtheta_m", (real)ra[0], va, (long)nVertLevels * (nCells + 1));
+            bdy_state("lbc_rho_zz", (real)ra[0], vb, (long)nVertLevels * (nCells + 1));
+            atm_bdy_reset_speczone_values(b->state, b->diag, b->mesh, nVertLevels, view2(va, nVertLevels, nCells + 1), view2(vb, nVertLevels, nCells + 1),
+                                          one, nCells, one, nCellsSolve);
+        } else if (r == "lbc_set_scalars") {                 // TI:1700-1719: ra[0] = dt
+            bdy_state("lbc_scalars", (real)ra[0], va, (long)S * nVertLevels * (nCells + 1));
+            FArr<real> sd; sd.bind(va.data(), 1, S, 1, nVertLevels, 1, nCells + 1);
+            atm_bdy_set_scalars(b->state, b->mesh, sd, nVertLevels, one, nCells, one, nCellsSolve);
+        } else { fprintf(stderr, "ref_call: unknown routine %s\n", routine); rc = 1; }
+        }
+    }
     // init-time derivations of atm_mpas_init_block (mpas_atm_core.F:573-586), serial as in the reference
     else if (r == "compute_mesh_scaling") {
 #pragma omp master

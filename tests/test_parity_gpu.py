@@ -59,8 +59,8 @@ def test_set_get_roundtrip(pair):
 
 
 def test_error_convention(pair, tiny_case):
-    """every entry point returns 0 or a nonzero code with a message; nothing aborts.  The regional
-    path is refused at creation (config_apply_lbcs), unknown keys / wrong sizes / wrong time levels at the call."""
+    """every entry point returns 0 or a nonzero code with a message; nothing aborts: bad dimensions are refused
+    at creation, unknown keys / wrong sizes / wrong time levels at the call."""
     import ctypes as C
     from mpas_model_b200.dycore import Dycore, make_config, make_dims
     d, cfg, o, g = pair
@@ -77,7 +77,7 @@ def test_error_convention(pair, tiny_case):
         g.summarize_timestep_fetch()
     dt, cfg_t = tiny_case
     with pytest.raises(RuntimeError):
-        Dycore(dt, dict(cfg_t, config_apply_lbcs=True))
+        Dycore(dict(dt, nVertLevels=3), cfg_t)
     bad = Dycore(dt, dict(cfg_t, config_time_integration_order=4))
     with pytest.raises(RuntimeError, match="config_time_integration_order"):
         bad.atm_srk3(cfg_t["config_dt"])

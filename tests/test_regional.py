@@ -1,0 +1,137 @@
+"""The regional (limited-area) path, config_apply_lbcs: atm_bdy_* (mpas_atm_time_integration.F "TI":7198-7910), the inline
+specified-zone resets of atm_srk3 (TI:1343-1388) and the bdyMask / specZoneMask branches of the work routines
+(TI:2482, 2779, 2862, 3061, 3385, 3672-3750, 3775, 4479, 4592, 4709).
+
+The checker here is oracle/_ref -- the reference's own statements, transliterated from the Fortran source by oracle/f2cpp.py --
+driven in atm_srk3's order; the driving fields come from mpas_atm_get_bdy_tend / _state (mpas_atm_boundaries.F:375-674):
+tendency = time level 1 of lbc_<field>, value at now + delta_t = level 2 - (seconds to the end of the LBC interval - delta_t) x level 1.
+"""
+import numpy as np
+import pytest
+
+from tests.util import STATE, real_fields, srk3_stepwise, sync_all
+
+ref = pytest.importorskip("oracle.ref")
+if not ref.build():
+    pytest.skip("oracle/_ref is not built (the reference tree is needed at build time)", allow_module_level=True)
+
+NOT_COMPARED = {"ke_edge", "wdtn", "scalar_old", "scalar_new", "flux_arr"}      # scratch the CUDA path fuses away (tests/util.py)
+
+
+@pytest.fixture(scope="module")
+def regional_case():
+    from mpas_model_b200.case import make_case, make_regional
+    d, cfg = make_case(642, 10, num_scalars=2)
+    return make_regional(d, cfg)
+
+
+def _driving(d, name, dtl):
+    return d["lbc_" + name + "_2"] - dtl * d["lbc_" + name]
+
+
+def test_masks_and_zones(regional_case):
+    d, cfg, t_end = regional_case
+    nC, nE = d["nCells"], d["nEdges"]
+    m, me = d["bdyMaskCell"], d["bdyMaskEdge"]
+    assert cfg["config_apply_lbcs"] and set(np.unique(m[:nC])) == set(range(8))
+    # rings are nested: a cell of ring r only touches rings r-1, r, r+1
+    for j in range(d["cellsOnCell"].shape[1]):
+        nb = d["cellsOnCell"][:nC, j]
+        ok = (j < d["nEdgesOnCell"][:nC]) & (nb < nC)
+        assert np.abs(m[:nC][ok] - m[nb[ok]]).max() <= 1
+    assert np.array_equal(d["specZoneMaskCell"][:nC], (m[:nC] > 5).astype(float))
+    assert np.array_equal(d["specZoneMaskEdge"][:nE], (me[:nE] > 5).astype(float))
+
+
+def test_reference_step_holds_the_specified_zone_to_the_driving_values(regional_case):
+    """One step of the transliterated reference: in the specified zone theta_m, scalars, u are the driving values at the
+    end of the step and w is zero (TI:1343-1388, 1477-1484, 1676-1720); the interior is untouched by the zone logic
+    (equal to a global run where no stencil reaches the relaxation zone)."""
+    d, cfg, t_end = regional_case
+    dt = cfg["config_dt"]
+    r = ref.RefDycore(d, cfg)
+    r.set_lbc_time(t_end)
+    r.atm_init_coupled_diagnostics(); r.atm_init_solve_diagnostics(dt)
+    r.atm_srk3(dt)
+    nC, nE = d["nCells"], d["nEdges"]
+    spec_c, spec_e = d["bdyMaskCell"][:nC] > 5, d["bdyMaskEdge"][:nE] > 5
+    dtl = t_end - dt
+    rt, rho = _driving(d, "rtheta_m", dtl), _driving(d, "rho_zz", dtl)
+    assert np.array_equal(r.get_array("theta_m", 2)[:nC][spec_c], (rt[:nC] / rho[:nC])[spec_c])
+    assert np.array_equal(r.get_array("scalars", 2)[:nC][spec_c], _driving(d, "scalars", dtl)[:nC][spec_c])
+    assert np.array_equal(r.get_array("u", 2)[:nE][spec_e], _driving(d, "u", dtl)[:nE][spec_e])
+    assert np.array_equal(r.get_array("ru", 1)[:nE][spec_e], _driving(d, "ru", dtl)[:nE][spec_e])
+    assert float(np.abs(r.get_array("w", 2)[:nC][spec_c][:, 1:-1]).max()) == 0.0
+    # relaxation zone: pulled towards the driving state, i.e. different from the same step without LBCs
+    g = ref.RefDycore(d, dict(cfg, config_apply_lbcs=False))
+    g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
+    g.atm_srk3(dt)
+    relax = (d["bdyMaskCell"][:nC] > 1) & (d["bdyMaskCell"][:nC] <= 5)
+    assert float(np.abs(r.get_array("theta_m", 2) - g.get_array("theta_m", 2))[:nC][relax].max()) > 1e-6
+    r.close(); g.close()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _differing(a, b):
+    return [f"{n}@{lev}" for n, lev in real_fields() if n not in NOT_COMPARED
+            and not np.array_equal(a.get_array(n, lev), b.get_array(n, lev), equal_nan=True)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["default", "coupled_transport_order3"])
+def test_every_regional_routine_bit_identical_to_the_reference_source(regional_case, variant):
+    """GPU library against oracle/_ref routine by routine on identical inputs, every field, bit for bit -- except the
+    stage-3 pow() of recover_large_step_variables (<= 1e-13, as in the global case)."""
+    from mpas_model_b200.dycore import Dycore
+    d, cfg, t_end = regional_case
+    if variant != "default":
+        cfg = dict(cfg, config_split_dynamics_transport=False, config_time_integration_order=3, config_number_of_sub_steps=4)
+    dt = cfg["config_dt"]
+    g, r = Dycore(d, cfg), ref.RefDycore(d, cfg)
+    for b in (g, r):
+        b.set_lbc_time(t_end)
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+    sync_all(r, g)
+    labels = []
+
+    def after(label):
+        bad = _differing(r, g)
+        if label.startswith("recover_large_step_variables") and label.endswith("3)"):
+            for f in bad:
+                n, lev = f.split("@")
+                a, b = g.get_array(n, int(lev)), r.get_array(n, int(lev))
+                assert np.linalg.norm((a - b).ravel()) <= 1e-13 * np.linalg.norm(b.ravel()), (label, f)
+        else:
+            assert bad == [], (label, bad)
+        labels.append(label)
+        sync_all(r, g)
+
+    srk3_stepwise([r, g], cfg, dt, after, reconstruct=False)
+    assert sum(l.startswith("lbc_") for l in labels) >= 15
+    g.close(); r.close()
+
+
+@pytest.mark.gpu
+def test_regional_free_running_steps(regional_case):
+    """Three free-running steps of mpasb_step (the fused regional srk3, LBC time advanced by the host each step) against the
+    transliterated reference: rel-L2 <= 1e-11 per step accumulates to <= 1e-10; the specified zone is bit-identical
+    (it is a pure function of the driving fields)."""
+    from mpas_model_b200.dycore import Dycore
+    d, cfg, t_end = regional_case
+    dt = cfg["config_dt"]
+    g, r = Dycore(d, cfg), ref.RefDycore(d, cfg)
+    for b in (g, r):
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+    for step in range(3):
+        for b in (g, r):
+            b.set_lbc_time(t_end - step * dt)
+            b.atm_srk3(dt)
+            b.mpas_pool_shift_time_levels()
+    nC = d["nCells"]
+    spec_c = d["bdyMaskCell"][:nC] > 5
+    for n in STATE:
+        a, b = g.get_array(n, 1), r.get_array(n, 1)
+        assert np.linalg.norm((a - b).ravel()) <= 1e-10 * np.linalg.norm(b.ravel()), n
+    for n in ("theta_m", "scalars"):
+        assert np.array_equal(g.get_array(n, 1)[:nC][spec_c], r.get_array(n, 1)[:nC][spec_c]), n
+    g.close(); r.close()

@@ -61,6 +61,7 @@ def srk3_stepwise(backends, cfg, dt, after=None, reconstruct=True):
         rk_s = [dt_dyn / float(nss)] * 3
         n_sub = [max(1, nss // 2), max(1, nss // 2), nss]
     coupled = cfg["config_scalar_advection"] and not cfg["config_split_dynamics_transport"]
+    lbcs = bool(cfg.get("config_apply_lbcs", False))
 
     def advance_scalars(rk, dt_rk):
         if rk < 3 or not (cfg["config_monotonic"] or cfg["config_positive_definite"]):
@@ -79,19 +80,34 @@ def srk3_stepwise(backends, cfg, dt, after=None, reconstruct=True):
             if cfg["config_time_integration_order"] == 3 and rk == 2:
                 call("compute_vert_imp_coefs", rk_s[rk - 1])
             call("compute_dyn_tend", rk, float(dt))
+            time_dyn_step = dt_dyn * float(ds - 1) + rk_t[rk - 1]      # TI:1246
+            if lbcs:                                     # regional run, TI:1218-1268
+                call("lbc_speczone_tend")
+                call("lbc_relaxzone_tend", float(time_dyn_step), float(dt))
             call("set_smlstep_pert_variables")
             for ss in range(1, n_sub[rk - 1] + 1):
                 call("advance_acoustic_step", rk_s[rk - 1], ss)
                 call("divergence_damping_3d", rk_s[rk - 1])
             call("recover_large_step_variables", rk_t[rk - 1], n_sub[rk - 1], rk)
+            if lbcs:                                     # TI:1343-1388
+                call("lbc_reset_u_ru", float(time_dyn_step))
             if coupled:                                  # config_split_dynamics_transport = false, TI:1404-1407
                 advance_scalars(rk, rk_t[rk - 1])
+                if lbcs:                                 # TI:1409-1430
+                    call("lbc_adjust_scalars", float(dt), float(rk_t[rk - 1]))
             call("compute_solve_diagnostics", float(dt), rk)
+            if lbcs:                                     # TI:1477-1484
+                call("lbc_zero_gradient_w")
         call("rk_dynamics_substep_finish", ds, split)
     if cfg["config_scalar_advection"] and not coupled:
         rk_t = [dt / 2.0 if cfg["config_time_integration_order"] == 2 else dt / 3.0, dt / 2.0, float(dt)]
         for rk in (1, 2, 3):
             advance_scalars(rk, rk_t[rk - 1])
+            if lbcs:                                     # TI:1560-1582
+                call("lbc_adjust_scalars", float(dt), float(rk_t[rk - 1]))
+    if lbcs:                                             # TI:1676-1720
+        call("lbc_reset_speczone_values", float(dt))
+        call("lbc_set_scalars", float(dt))
     if not reconstruct:
         return
     for b in backends:                      # TI:1596-1611
