@@ -74,15 +74,18 @@ def make_regional(d: dict, cfg: dict, lat0: float = 0.6, lon0: float = 0.4, radi
     d["bdyMaskCell"], d["bdyMaskEdge"] = mask, emask
     d["specZoneMaskCell"] = (mask > N_RELAX_ZONE).astype(np.float64)
     d["specZoneMaskEdge"] = (emask > N_RELAX_ZONE).astype(np.float64)
-    rng = np.random.default_rng(seed)
     rho, th, u = d["rho_zz_init"], d["theta_m_init"], d["u"]         # what atm_init_coupled_diagnostics derives from the state
-    wob_c = 1.0 + 2.0e-3 * np.sin(3.0 * d["latCell"])[:, None] * np.cos(2.0 * d["lonCell"])[:, None]
+    wob_c = 1.0 + 1.0e-3 * np.sin(3.0 * d["latCell"])[:, None] * np.cos(2.0 * d["lonCell"])[:, None]
+    wob_e = 1.0 + 1.0e-2 * np.sin(2.0 * d["latEdge"])[:, None] * np.cos(3.0 * d["lonEdge"])[:, None]
     d["lbc_rho_zz_2"] = rho * wob_c
-    d["lbc_rtheta_m_2"] = rho * th * wob_c * (1.0 + 1.0e-3)
-    d["lbc_u_2"] = u + 0.5
-    d["lbc_ru_2"] = d["ru_init"] * 1.01 + 0.5
+    d["lbc_rtheta_m_2"] = rho * th * wob_c * (1.0 + 5.0e-4)
+    d["lbc_u_2"] = u * wob_e
+    d["lbc_ru_2"] = d["ru_init"] * wob_e
     d["lbc_scalars_2"] = d["scalars"] * 1.05 + 1.0e-5
-    for n in ("rho_zz", "rtheta_m", "u", "ru", "scalars"):
+    # tendencies over the interval (per second): smooth, a 0.1 % drift of the driving state over three hours
+    ten_c = 1.0e-7 * np.cos(2.0 * d["latCell"]) * np.sin(d["lonCell"] + float(seed))
+    ten_e = 1.0e-7 * np.cos(2.0 * d["latEdge"]) * np.sin(d["lonEdge"] + float(seed))
+    for n, ten in (("rho_zz", ten_c), ("rtheta_m", ten_c), ("scalars", ten_c), ("u", ten_e), ("ru", ten_e)):
         st = d["lbc_" + n + "_2"]
-        d["lbc_" + n] = st * 1.0e-6 * rng.uniform(-1.0, 1.0, size=st.shape)       # per second
+        d["lbc_" + n] = st * ten.reshape((-1,) + (1,) * (st.ndim - 1))
     return d, cfg, lbc_interval

@@ -121,9 +121,10 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
 // ... without the wait: the kernel places pdl_wait() itself, below its loads of static mesh data
 #define CW_SETUP_NW(ncols)                                                                    \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
-    const int i = blockIdx.x * CW_WARPS + wib;                                                \
+    const int i_fwd_ = blockIdx.x * CW_WARPS + wib;                                           \
     const int LDK = D.LDK, nl = D.nl;                                                         \
-    if (i >= (ncols)) return;                                                                 \
+    if (i_fwd_ >= (ncols)) return;                                                            \
+    const int i = D.rev ? (ncols) - 1 - i_fwd_ : i_fwd_;                                      \
     Lv lv; lv.k0 = 2 * lane;                                                                  \
     const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;                             \
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
     const int LDK = D.LDK, nl = D.nl;
     real* s_w = reinterpret_cast<real*>(ef_raw);
     real* s_t = s_w + EF_MAXT * LDK;
-    const int tile = blockIdx.x;
+    const int tile = D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
     const int4 hdr = tile_hdr[tile];                        // (runs, staged columns, active-edge mask); runs < 0: gather from global memory
     const int nt = hdr.x;
     Lv lv; lv.k0 = 2 * lane;
@@ -329,18 +330,22 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
     // fetched while the current cell's columns are in flight: one exposed round trip per cell instead of two.
     const int G = gridDim.x * FX_WARPS;
     const int le = min(lane, 5), lr = min(lane, FX_RING - 1);
-    int i = blockIdx.x * FX_WARPS + wib;
+    const int nSolve = D.nCellsSolve;
+#define FX_COL(j) (D.rev ? nSolve - 1 - (j) : (j))            /* sweep direction of this launch (Dev::rev) */
+    int j = blockIdx.x * FX_WARPS + wib;
     int my_ring = 0, my_e = 0; real my_sgn = 0.0;
-    if (i < D.nCellsSolve) {
+    if (j < nSolve) {
+        const int i = FX_COL(j);
         my_ring = D.fx_ring[(unsigned)i * FX_RING + lr];
         my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
         my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     }
     pdl_wait();                                          // everything above is static mesh data
-    for (; i < D.nCellsSolve; i += G) {
+    for (; j < nSolve; j += G) {
+    const int i = FX_COL(j);
     const int regular = BC(my_ring, 18);
     r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
-    const int inext = i + G;
+    const int inext = j + G < nSolve ? FX_COL(j + G) : nSolve;
     int nx_ring = 0, nx_e = 0; real nx_sgn = 0.0;
     if (regular) {
         const real* __restrict__ wsrc = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
     ST(D.hdiv_theta, i, sel(k_lt_nl, tt, 0.0));
     my_ring = nx_ring; my_e = nx_e; my_sgn = nx_sgn;
     }
+#undef FX_COL
 }
 
 // ---- the same sweep with ONE FIELD PER WARP (warp 2c: w of cell c, warp 2c + 1: theta_m): half the registers per thread, twice
@@ -436,9 +442,10 @@ __global__ void __launch_bounds__(CW_THREADS, FX1_MINB) k5s_flux_cell(const Dev 
     PDL_ENTER
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * CW_WARPS + wib;
-    const int i = g >> 1, field = g & 1;
+    const int field = g & 1;
     const int LDK = D.LDK, nl = D.nl;
-    if (i >= D.nCellsSolve) return;
+    if ((g >> 1) >= D.nCellsSolve) return;
+    const int i = D.rev ? D.nCellsSolve - 1 - (g >> 1) : (g >> 1);
     Lv lv; lv.k0 = 2 * lane;
     const int k0 = lv.k0; const bool act = k0 < D.LDKA;
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
@@ -673,11 +680,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
     const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
     const int G = gridDim.x * WARPS;
-    int i = blockIdx.x * WARPS + wib;
+    const int nSolve = D.nCellsSolve;
+#define CF7_COL(j) (D.rev ? nSolve - 1 - (j) : (j))           /* sweep direction of this launch (Dev::rev) */
+    int jcol = blockIdx.x * WARPS + wib;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
-    if (i < D.nCellsSolve) cn = cf_conn(D, i, lane, rk1);
+    if (jcol < nSolve) cn = cf_conn(D, CF7_COL(jcol), lane, rk1);
     pdl_wait();                                          // everything above is static mesh data
-    for (; i < D.nCellsSolve; i += G) {
+    for (; jcol < nSolve; jcol += G) {
+        const int i = CF7_COL(jcol);
         const int ne = cn.ne, my_e = cn.e, my_c1 = cn.c1, my_c2 = cn.c2;
         const real my_sgn = cn.sgn, my_dv = cn.dv, my_d4 = cn.d4, my_idc = cn.idc, invArea = cn.invArea;
         // own-column operands: requested up front, together with the gathers below
@@ -723,10 +733,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
             }
 #undef CF7_DEL4
         }
-        if (i + G < D.nCellsSolve) {
-            cn = cf_conn(D, i + G, lane, rk1);          // next cell's connectivity, behind this cell's requests
+        if (jcol + G < nSolve) {
+            const int j = CF7_COL(jcol + G);
+            cn = cf_conn(D, j, lane, rk1);              // next cell's connectivity, behind this cell's requests
             if (D.pf_next) {
-                const int j = i + G;
                 PF(D.hdiv_w, j); PF(D.hdiv_theta, j); PF(D.tend_w_euler, j); PF(D.tend_theta_euler, j); PF(D.rw, j); PF(D.w_2, j);
                 PF(D.theta_m_2, j); PF(D.theta_m, j); PF(D.rw_save, j); PF(D.rho_zz_2, j); PF(D.tend_rho, j); PF(D.rt_diabatic_tend, j);
                 PF(D.tend_rtheta_physics, j);
@@ -768,6 +778,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
         ST(D.rthdynten, i, out_rthdynten);
         ST(D.tend_theta, i, sel(k_lt_nl, tt + tte + trp, 0.0));
     }
+#undef CF7_COL
 }
 
 // ------------------------------------------------------------------ nonlinear Coriolis term, cell-centred partial sums
@@ -955,7 +966,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
 
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
 // (1) vertex-all: vorticity (6452-6472), ke_vertex (6548-6561, ke_edge recomputed inline), pv_vertex (6647-6659)
-__global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const real* __restrict__ u) {
+__global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const real* u) {
     CW_ENTER(D.nVertices)
     int my_e = 0; real my_s = 0.0, my_efac = 0.0;
     {
@@ -981,7 +992,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const 
     ST(D.pv_vertex, i, sel(k_lt_nl, D.fVertex[i] + vort, 0.0));
 }
 // (2) cell-all: divergence (6479-6499), ke (6515-6534) + Hollingsworth blend (6569-6593), pv_cell (6693-6709)
-__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* __restrict__ u, int apvm) {
+__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev D, const real* u, int apvm) {
     CW_ENTER(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -1026,7 +1037,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
     if (apvm) ST(D.pv_cell, i, sel(k_lt_nl, pvc, 0.0));
 }
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
-__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* __restrict__ u, const real* __restrict__ h,
+__global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* u, const real* h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
     CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
@@ -1200,7 +1211,7 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const bool first = small_step == 1;
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
-    const int base = blockIdx.x * AC3_COLS;
+    const int base = (D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * AC3_COLS;      // sweep direction of this launch
     const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
     // connectivity of ALL columns of this warp in one pass: lane = (column slot << 3) | edge slot, so the two
     // dependent index loads (edgesOnCell -> cellsOnEdge/dvEdge) are exposed once per warp, not once per column
@@ -1390,15 +1401,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
     // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
     const int G = gridDim.x * WARPS;
-    int i = blockIdx.x * WARPS + wib;
+    const int nAll = D.nCells;
+#define AC6_COL(j) (D.rev ? nAll - 1 - (j) : (j))             /* sweep direction of this launch (Dev::rev) */
+    int jcol = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
-    if (i < D.nCellsSolve) cn = ac6_conn(D, i, lane, dts);
+    if (jcol < nAll && AC6_COL(jcol) < D.nCellsSolve) cn = ac6_conn(D, AC6_COL(jcol), lane, dts);
     pdl_wait();                                          // everything above is static mesh data
     const r2 cofrz = LD(D.cofrz, 0);                     // (written by the vertical-coefficient kernel)
-    for (; i < D.nCells; i += G) {
+    for (; jcol < nAll; jcol += G) {
+    const int i = AC6_COL(jcol);
+    const int inext = jcol + G < nAll ? AC6_COL(jcol + G) : nAll;     // the next column of this warp (nAll: none)
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
-    if (i >= D.nCellsSolve) { ST(D.rtheta_pp_old, i, rtheta_pp); continue; }          // halo cells: TI:2827-2842 only
+    if (i >= D.nCellsSolve) {                                                          // halo cells: TI:2827-2842 only
+        ST(D.rtheta_pp_old, i, rtheta_pp);
+        if (inext < D.nCellsSolve) cn = ac6_conn(D, inext, lane, dts);                 // (backward sweep: halo cells come first)
+        continue;
+    }
     const int ne = cn.ne;
     const int my_e = cn.e, my_oth = cn.oth;
     const bool my_is1 = (cn.is12 & 1) != 0, my_is2 = (cn.is12 & 2) != 0;
@@ -1431,10 +1450,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 #undef AC6_EDGE
     // operands of the part after the solve: issued here so that they are in flight during the solve
     const r2 dss = LD(D.dss, i), rw_save = LD(D.rw_save, i), rw_now = LD(D.rw, i), rho = LD(D.rho_zz_2, i), w_now = LD(D.w_2, i);
-    if (i + G < D.nCellsSolve) {
-        cn = ac6_conn(D, i + G, lane, dts);          // next cell's connectivity, in flight with this cell's columns
+    if (inext < D.nCellsSolve) {
+        cn = ac6_conn(D, inext, lane, dts);          // next cell's connectivity, in flight with this cell's columns
         if (D.pf_next) {                             // and its own-column operands on their way into L2
-            const int j = i + G;
+            const int j = inext;
             PF(D.tend_rho, j); PF(D.tend_theta, j); PF(D.tend_w, j); PF(D.coftz, j); PF(D.cofwz, j); PF(D.cofwr, j); PF(D.cofwt, j);
             PF(D.zz, j); PF(D.a_tri, j); PF(D.alpha_tri, j); PF(D.gamma_tri, j); PF(D.theta_m, j); PF(D.dss, j); PF(D.rw_save, j);
             PF(D.rw, j); PF(D.rho_zz_2, j); PF(D.w_2, j);
@@ -1504,6 +1523,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
     ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1 - coftz * r), 0.0));
     }
+#undef AC6_COL
 }
 
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075
@@ -1716,7 +1736,7 @@ __global__ void __launch_bounds__(VIC_WARPS * 32, MB_VIC) k3_vert_imp_coefs(cons
     const int k0 = lv.k0; const bool act = k0 < D.LDKA;
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
-    const int base = blockIdx.x * VIC_COLS;
+    const int base = (D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * VIC_COLS;      // sweep direction of this launch
     const r2 fzm = LD(D.fzm, 0), fzp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0), rdzu = LD(D.rdzu, 0);
     const r2 cofrz = dtseps * rdzw;
     if (blockIdx.x == 0 && wib == 0) ST(D.cofrz, 0, sel(k_lt_nl, cofrz, 0.0));
@@ -1919,7 +1939,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, 
     ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));       // SCALE_OUT
 }
 // (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* __restrict__ rho_lim) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* rho_lim) {
     CW_SETUP(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -1961,7 +1981,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
     ST(D.flux_arr, i, sel(lv.lt(nl), f, 0.0));
 }
 // (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* __restrict__ rho_div) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* rho_div) {
     CW_SETUP(D.nCells)
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
     const b2 k_lt_nl = lv.lt(nl);

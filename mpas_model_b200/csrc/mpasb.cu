@@ -60,6 +60,7 @@ struct mpasb_handle_s {
     real lbc_dt_end = 0.0;         // regional runs: seconds from the start of the next step to the end of the LBC interval
     bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
     bool pdl = true;               // MPASB_PDL=0: no programmatic dependent launch
+    bool snake = true;             // MPASB_SNAKE=0: every kernel sweeps its columns forward (Dev::rev)
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
@@ -147,6 +148,7 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->relaxed = !mpasb_strict_arithmetic();
     h->fuse_dd = !getenv("MPASB_NO_DD_FUSE");
     if (const char* e = getenv("MPASB_PDL")) h->pdl = atoi(e) != 0;
+    if (const char* e = getenv("MPASB_SNAKE")) h->snake = atoi(e) != 0;
     memset(&h->D, 0, sizeof(Dev));
     h->D.pf_next = 1;
     if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
@@ -475,7 +477,8 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
 }
 
 extern "C" int mpasb_shift_time_levels(mpasb_handle h) {     // mpas_pool_shift_time_levels, shift_time_levs_array.inc:26-33
-    for (FieldRec& f : h->fields) if (f.levels == 2) { std::swap(f.d[0], f.d[1]); set_dev_ptr(h, f); }
+    // the state pool only (mpas_atm_core.F:808); the two "levels" of the lbc_* fields are tendency and state, not times
+    for (FieldRec& f : h->fields) if (f.levels == 2 && strncmp(f.name, "lbc_", 4) != 0) { std::swap(f.d[0], f.d[1]); set_dev_ptr(h, f); }
     h->halo.parity ^= 1;        // halo plans cache field pointers per time-level parity
     return 0;
 }
@@ -509,6 +512,7 @@ struct KScope {
 // blocks may become resident while the previous kernel of the stream drains (mpasb_dev.cuh); MPASB_PDL=0 launches them plainly.
 template <typename... P, typename... A>
 static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+    if (h->snake) h->D.rev ^= 1;          // alternate the sweep direction (the Dev argument is a reference to h->D: copied below)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute at;
@@ -533,6 +537,7 @@ struct SegBuilder {       // collects the column ranges of one routine into one 
     void flush() {
         if (!n) return;
         KScope ks_(h, "k:k_segments");
+        L.rev = h->snake ? !h->D.rev : 0;          // the direction klaunch is about to switch to
         klaunch(h, k_segments, dim3(SEG_BLOCKS, n), dim3(256), 0, L);
         h->launches++; n = 0;
     }

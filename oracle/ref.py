@@ -144,7 +144,7 @@ class RefDycore(Backend):
 
     def mpas_pool_shift_time_levels(self):
         for name, fd in FIELDS.items():
-            if fd.levels == 2:
+            if fd.levels == 2 and not name.startswith("lbc_"):       # the state pool only (mpas_atm_core.F:808)
                 self.a[(name, 1)], self.a[(name, 2)] = self.a[(name, 2)], self.a[(name, 1)]
         self._bind_all()
 

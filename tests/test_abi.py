@@ -84,8 +84,11 @@ def test_bindings_agree_with_the_header():
     # both RKIND widths
     assert "#ifdef SINGLE_PRECISION" in binding and "c_float" in binding and "c_double" in binding
     # the replacement bodies only call bound symbols, keep the reference's entry-point names ...
-    used = set(re.findall(r"\b(mpasb_[a-z_0-9]+)\(", shim)) - {"mpasb_check", "mpasb_upload_state", "mpasb_download_for_output", "mpasb_c_to_f"}
+    used = set(re.findall(r"\b(mpasb_[a-z_0-9]+)\(", shim)) - {"mpasb_check", "mpasb_upload_state", "mpasb_upload_lbc", "mpasb_download_for_output", "mpasb_c_to_f"}
     assert used <= bound, used - bound
+    # regional runs: the driving fields (both time levels) and the time to the end of the LBC interval reach the library
+    assert "mpasb_set_lbc_time(mpasb_h" in shim and all(f"'lbc_{n}', 'lbc_{n}', {lev}," in shim
+                                                        for n in ("u", "ru", "rho_zz", "rtheta_m", "scalars") for lev in (1, 2))
     for name in ("subroutine mpas_atm_dynamics_init(domain)", "subroutine mpas_atm_dynamics_finalize(domain)",
                  "subroutine atm_timestep(domain, dt, nowTime, itimestep, exchange_halo_group)"):
         assert name in shim, name
@@ -109,3 +112,39 @@ def test_fortran_shim_is_generated_from_the_header_and_the_field_table():
     for name, text in {"mpasb_binding.F90": gen.wrap(gen.binding()), "mpas_atm_dynamics_b200.F": gen.wrap(gen.dynamics())}.items():
         with open(os.path.join(ROOT, "fortran", name)) as f:
             assert f.read() == text, name
+
+
+def test_no_invariant_load_above_the_dependency_wait():
+    """Programmatic dependent launch (mpasb_dev.cuh): before `griddepcontrol.wait` (SASS ACQBULK) a kernel may only read static
+    mesh data.  A load through a `const __restrict__` pointer is an invariant load (LDG.CONSTANT) that the compiler may hoist
+    above the wait -- which is how a field read once raced with the previous kernel.  No kernel of either build may have one
+    there."""
+    import re
+    import shutil
+    import subprocess
+    from mpas_model_b200 import dycore
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    for lib in (dycore.LIB_PATH, dycore.LIB_PATH_SINGLE):
+        sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+        name, waited, hoisted, n_wait = None, False, {}, 0
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                name, waited = m.group(1), False
+            elif "ACQBULK" in line:
+                n_wait += not waited
+                waited = True
+            elif not waited and re.search(r"LDG\S*CONSTANT", line):
+                hoisted[name] = hoisted.get(name, 0) + 1
+        with_wait = set()
+        name = None
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                name = m.group(1)
+            elif "ACQBULK" in line:
+                with_wait.add(name)
+        assert n_wait >= 40, n_wait                                   # every column-warp kernel waits
+        assert {k: v for k, v in hoisted.items() if k in with_wait} == {}

@@ -120,3 +120,31 @@ def test_compare_tool_against_a_restart_file(tmp_path):
     ncio.write(rst, {"Time": 0, "nCells": nC, "nEdges": nE, "nVertLevels": nz, "nVertLevelsP1": nz + 1}, {}, fields, version=5, unlimited="Time")
     assert tool.main(["compare", init, rst, "--steps", "2"]) == 0.0
     assert tool.main(["compare", init, rst, "--steps", "1"]) > 1e-6          # and it does notice a different state
+
+
+@pytest.mark.gpu
+def test_gpu_step_started_from_an_init_file(tmp_path):
+    """Row f3 on the GPU: x1.642.init.nc (written in the reference's on-disk conventions) -> initfile.read_init_file (which ends
+    with atm_mpas_init_block's derivations) -> the CUDA library through the C ABI -> two steps; compared with the oracle started
+    from the generated case (not from the file): rel-L2 <= 1e-11 per step, and bit-identical between file start and case
+    start on the GPU itself."""
+    from mpas_model_b200.case import make_case
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    d, cfg = make_case(642, 10, num_scalars=2)
+    p = str(tmp_path / "x1.642.init.nc")
+    initfile.write_init_file(d, p)
+    d2, cfg2 = initfile.read_init_file(p, dt=cfg["config_dt"])
+    dt = cfg["config_dt"]
+    o, g_file, g_case = OracleDycore(d, cfg), Dycore(d2, cfg2), Dycore(d, cfg)
+    for b in (o, g_file, g_case):
+        b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
+        for _ in range(2):
+            b.atm_srk3(dt); b.mpas_pool_shift_time_levels()
+    for name in ("u", "w", "rho_zz", "theta_m", "scalars"):
+        a, r = g_file.get_array(name, 1), o.get_array(name, 1)
+        assert np.array_equal(a, g_case.get_array(name, 1)), name
+        assert np.linalg.norm((a - r).ravel()) <= 2e-11 * np.linalg.norm(r.ravel()), name
+    assert g_file.kernel_launch_count() > 0
+    for b in (o, g_file, g_case):
+        b.close()

@@ -18,6 +18,7 @@ TEND = {"tend_u": "u", "tend_w": "w", "tend_theta": "theta_m", "tend_rho": "rho_
         "scalars_tend": "scalars_tend"}
 TEND_PHYSICS = ("rthdynten", "tend_ru_physics", "tend_rtheta_physics", "tend_rho_physics")
 STATE = ("u", "w", "rho_zz", "theta_m", "scalars")
+LBC = ("lbc_u", "lbc_ru", "lbc_rho_zz", "lbc_rtheta_m", "lbc_scalars")      # var_struct "lbc", two time levels
 SCRATCH = ("tend_u_euler", "tend_w_euler", "tend_theta_euler", "qtot", "delsq_theta", "delsq_w", "delsq_divergence", "dpdz", "delsq_u",
            "delsq_vorticity", "ke_vertex", "ke_edge", "scalar_old", "scalar_new", "s_max", "s_min", "rho_zz_int", "wdtn", "flux_arr",
            "flux_upwind_tmp", "flux_tmp", "scale_arr", "horiz_flux_arr")
@@ -168,7 +169,7 @@ def dynamics():
     A("module atm_time_integration_b200")
     A("")
     for u in ("iso_c_binding", "mpas_derived_types", "mpas_pool_routines", "mpas_kind_types", "mpas_constants", "mpas_dmpar", "mpas_log",
-              "mpas_timer", "mpas_timekeeping", "mpasb_binding"):
+              "mpas_timer", "mpas_timekeeping", "mpas_atm_boundaries", "mpasb_binding"):
         A(f"   use {u}")
     A("")
     A("   implicit none")
@@ -178,6 +179,7 @@ def dynamics():
     A("   type(c_ptr), save :: mpasb_h = c_null_ptr")
     A("   logical, save :: state_on_device = .false.     ! set .false. again by whoever overwrites the host state (restart read, DA, IAU)")
     A("   logical, save :: summary_pending = .false.")
+    A("   real (kind=RKIND), save :: lbc_prev_to_end = -1.0_RKIND     ! regional runs: seconds to the end of the LBC interval at the last step")
     A("")
     A("   abstract interface")
     A("      subroutine halo_exchange_routine(domain, halo_group, ierr)")
@@ -420,6 +422,17 @@ def dynamics():
     A(put(byname["rt_diabatic_tend"], "tend", "rt_diabatic_tend"))
     A("   end subroutine mpasb_upload_state")
     A("")
+    A("   ! regional runs: the driving fields of the current LBC interval, var_struct 'lbc' (time level 1 = tendency, 2 = state at the")
+    A("   ! end of the interval, mpas_atm_boundaries.F:78-339), re-sent whenever mpas_atm_update_bdy_tend has read a new LBC time")
+    A("   subroutine mpasb_upload_lbc(block)")
+    A("      type (block_type), intent(inout) :: block")
+    A("      type (mpas_pool_type), pointer :: lbc")
+    A("      call mpas_pool_get_subpool(block % structs, 'lbc', lbc)")
+    for n in LBC:
+        for lev in (1, 2):
+            A(put(byname[n], "lbc", n, lev, True))
+    A("   end subroutine mpasb_upload_lbc")
+    A("")
     A("   ! device -> host pools on output / restart alarms (mpas_atm_core.F:812-890), before the stream write")
     A("   subroutine mpasb_download_for_output(block)")
     A("      type (block_type), intent(inout) :: block")
@@ -446,8 +459,11 @@ def dynamics():
     A("      type (block_type), pointer :: block")
     A("      type (mpas_pool_type), pointer :: state")
     A("      character (len=StrKIND), pointer :: config_time_integration, xtime")
-    A("      logical, pointer :: config_print_global_minmax_vel, config_print_global_minmax_sca")
+    A("      logical, pointer :: config_print_global_minmax_vel, config_print_global_minmax_sca, config_apply_lbcs")
     A("      integer, pointer :: num_scalars")
+    A("      type (MPAS_TimeInterval_type) :: lbc_interval")
+    A("      integer :: dd_intv, s_intv, sn_intv, sd_intv")
+    A("      real (kind=RKIND) :: lbc_to_end")
     A("      real (kind=mpasb_real), allocatable :: mm(:)")
     A("      real (kind=RKIND) :: gmin, gmax")
     A("      integer(c_long) :: nan_count(2)")
@@ -468,6 +484,19 @@ def dynamics():
     A("      if (.not. state_on_device) then          ! first call, or the host state was rewritten (restart read, DA, IAU)")
     A("         call mpasb_upload_state(block)")
     A("         state_on_device = .true.")
+    A("      end if")
+    A("")
+    A("      call mpas_pool_get_config(block % configs, 'config_apply_lbcs', config_apply_lbcs)")
+    A("      if (config_apply_lbcs) then              ! regional run (TI:773): what mpas_atm_get_bdy_state derives from the clock,")
+    A("         ! mpas_atm_boundaries.F:497-503.  LBC_intv_end is private to mpas_atm_boundaries: mpas_atm_bdy_interval_end() is the one")
+    A("         ! accessor a maintainer adds there (`function mpas_atm_bdy_interval_end() result(t); t = LBC_intv_end; end function`)")
+    A("         lbc_interval = mpas_atm_bdy_interval_end() - nowTime")
+    A("         call mpas_get_timeInterval(interval=lbc_interval, DD=dd_intv, S=s_intv, S_n=sn_intv, S_d=sd_intv, ierr=ierr)")
+    A("         lbc_to_end = 86400.0_RKIND * real(dd_intv, kind=RKIND) + real(s_intv, kind=RKIND) &")
+    A("                      + (real(sn_intv, kind=RKIND) / real(sd_intv, kind=RKIND))")
+    A("         if (lbc_to_end > lbc_prev_to_end) call mpasb_upload_lbc(block)     ! a new LBC interval began (mpas_atm_core.F:724, 754)")
+    A("         lbc_prev_to_end = lbc_to_end")
+    A("         call mpasb_check(mpasb_set_lbc_time(mpasb_h, real(lbc_to_end, mpasb_real)), 'set_lbc_time')")
     A("      end if")
     A("")
     A("      call mpasb_check(mpasb_step(mpasb_h, real(dt, mpasb_real), int(itimestep, c_int)), 'step')      ! atm_srk3, TI:803-1725")
