@@ -38,6 +38,20 @@ E2E_OUT = (("u", 2), ("w", 2), ("rho_zz", 2), ("theta_m", 2), ("scalars", 2), ("
            ("rtheta_p", 1), ("rho_p", 1), ("exner", 1), ("pressure_p", 1))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal-CPU mask), so that the pinned host buffers of the e2e leg are
+    first-touched on the GPU's own NUMA node instead of every rank's on node 0.  Returns what was done (for the JSON line)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"bound": True, "cpus": len(os.sched_getaffinity(0)), "cpus_before": len(before), "_restore": before}
+    except Exception as e:                                # no NVML, a container cpuset without those CPUs, ...
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def model_bytes_per_step(n_cells, n_levels, n_scalars, real_bytes=8):
     """B_step = (2197 + 107 S) * nVertLevels * nCells * sizeof(real)."""
     return (2197 + 107 * n_scalars) * n_levels * n_cells * real_bytes
@@ -112,13 +126,13 @@ KERNEL_MODEL_C = {
 }
 
 
-NCU_STEP_CSV = os.path.join("profiles", "r1_ncu_step_metrics.csv")
+NCU_STEP_CSV = os.path.join("profiles", "r2_ncu_step_metrics_n.csv")
 
 
 def kernel_traffic(kernel, n_cells, n_lev, rb):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one step in the
-    committed ncu capture profiles/r1_ncu_step_metrics.csv (tools/ncu_step_metrics.sh: x1.40962 x 55 levels, fp64).
-    Only valid for that workload; None otherwise."""
+    committed ncu capture NCU_STEP_CSV (tools/ncu_step_metrics.sh: x1.40962 x 55 levels, fp64; template arguments of the
+    kernel name ignored).  Only valid for that workload; None otherwise."""
     path = os.path.join(ROOT, NCU_STEP_CSV)
     if not (os.path.exists(path) and (n_cells, n_lev, rb) == (40962, 55, 8)):
         return None
@@ -128,9 +142,12 @@ def kernel_traffic(kernel, n_cells, n_lev, rb):
         rows = [r for r in csv.reader(f) if len(r) > 10]
     hdr = rows[0]
     ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    iu = hdr.index("Metric Unit")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    base = lambda n: n.split("(")[0].replace("void ", "").split("<")[0].strip()
     for r in rows[1:]:
-        if r[ik].split("(")[0] == kernel and r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(r[iv].replace(",", "")); launches.add(r[iid])
+        if base(r[ik]) == base(kernel) and r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0); launches.add(r[iid])
     return tot / len(launches) if launches else None
 
 
@@ -263,6 +280,7 @@ def main():
     ap.add_argument("--precision", default="double", choices=("double", "single"), help="RKIND of the library build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-members", type=int, default=3, help="independent host-resident instances alternating in the e2e leg (1..4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -282,6 +300,7 @@ def main():
         raise SystemExit(f"bench.py: --gpus {args.gpus} needs {args.gpus} ranks (torch.distributed.run), got WORLD_SIZE={world}")
     n_cells, n_lev = workload_for(args)
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)          # before any pinned allocation: first touch decides the NUMA node
     dist = None
     if world > 1:
         from mpas_model_b200 import multigpu as mg
@@ -356,7 +375,8 @@ def main():
     if not args.no_e2e:
         tdt = torch.float64 if g.rdtype == np.float64 else torch.float32
         members = []
-        for m in range(2):
+        M = max(1, min(4, args.e2e_members))
+        for m in range(M):
             host = {}
             for name, lev in set(E2E_FIELDS) | set(E2E_OUT):
                 host[(name, lev)] = torch.empty(tuple(g.shape(name)), dtype=tdt).pin_memory().numpy()
@@ -406,24 +426,33 @@ def main():
         barrier()
         serial_s = max_over_ranks((time.perf_counter() - t0) / ns)
 
-        # pipelined: request k is member k % 2; before member m is re-submitted its previous result must be down
+        # pipelined: request k belongs to member k % M; a member's next request needs its previous result on the host
+        # (its output arrays are the next input), so request k - M is retired before request k is submitted
+        for m in range(1, M):                               # every member has stepped once before the clock starts
+            serial_step(members[m])
         submit(members[0])
         g.wait_downloads(0); retire(members[0])
         barrier()
         t0 = time.perf_counter()
-        submit(members[0])
-        for k in range(1, e2e_steps):
-            submit(members[k % 2])
-            g.wait_downloads(1)                             # request k-1 is complete on the host ...
-            retire(members[(k - 1) % 2])                    # ... (summary of k-1 was enqueued before request k: fetch it now)
-        g.wait_downloads(0); retire(members[(e2e_steps - 1) % 2])
+        for k in range(e2e_steps):
+            if k >= M:
+                g.wait_downloads(M - 1)                     # request k - M is complete on the host ...
+                retire(members[(k - M) % M])                # ... log line, host-side time-level shift
+            submit(members[k % M])
+        for j in range(max(0, e2e_steps - M), e2e_steps):
+            g.wait_downloads(e2e_steps - 1 - j); retire(members[j % M])
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": n_cells / e2e_s, "unit": "cell-columns/s", "steps_per_s": 1.0 / e2e_s, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": 1e3 * e2e_s, "serial_ms_per_step": 1e3 * serial_s,
-               "mode": "2 independent host-resident instances alternating; upload of the next request, step, and download of the "
-                       "previous one overlap (copy streams + events); every request moves its full state both ways"}
+               "members": M,
+               "mode": f"{M} independent host-resident instances (ensemble members) taking turns on one device handle; the upload of "
+                       "a later request, the step, and the download of an earlier one overlap (copy streams + events); every request "
+                       "moves its full state both ways and waits for its own previous result; serial_ms_per_step is one instance, "
+                       "nothing overlapped"}
     clocks = sampler.stop() if rank == 0 else None
+    if numa.get("_restore"):                            # the CPU baseline below uses every core again
+        os.sched_setaffinity(0, numa.pop("_restore"))
 
     # ---------------- per-kernel timing (CUDA events on the launching stream) for the roofline object
     barrier()
@@ -501,7 +530,7 @@ def main():
         line["config"]["workload"] = line["config"]["workload"].replace("fp64", "fp32 (PRECISION=single build)")
     line.update({
         "value": value, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "host_affinity": numa, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "step_roofline": {"model_bytes_per_step": B_step, "achieved_gbs": step_gbs,
                           "frac_of_measured_peak": step_gbs / (peak * world), "frac_of_nominal_8TBs": step_gbs / (8000.0 * world)},
         "cpu_baseline": cpu, "parity": parity,

@@ -47,7 +47,8 @@ struct mpasb_handle_s {
     // asynchronous summarize_timestep: device results (2 * (2 + num_scalars) doubles + 2 NaN counters as doubles' bit
     // patterns), pinned host copy, completion event
     // (two slots, so that the summary of one request can be fetched while the next request is already enqueued)
-    double* d_summary[2] = {}; double* h_summary[2] = {}; cudaEvent_t ev_summary[2] = {}; long summary_head = 0, summary_tail = 0;
+    enum { SUMMARY_RING = 4 };      // summaries that may be pending at once (requests in flight, mpasb_summarize_timestep_async)
+    double* d_summary[SUMMARY_RING] = {}; double* h_summary[SUMMARY_RING] = {}; cudaEvent_t ev_summary[SUMMARY_RING] = {}; long summary_head = 0, summary_tail = 0;
     std::string err;
     long launches = 0;
     int cpb = 4;
@@ -217,7 +218,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->d_minmax) cudaFree(h->d_minmax);
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < H::SUMMARY_RING; q++) {
         if (h->d_summary[q]) cudaFree(h->d_summary[q]);
         if (h->h_summary[q]) cudaFreeHost(h->h_summary[q]);
         if (h->ev_summary[q]) cudaEventDestroy(h->ev_summary[q]);
@@ -1271,8 +1272,8 @@ extern "C" int mpasb_summarize_timestep_async(mpasb_handle h) {
     cudaSetDevice(h->device);
     const Dev& D = h->D;
     const int S = D.num_scalars, nval = 2 * (2 + S) + 2;
-    if (h->summary_head - h->summary_tail >= 2) { h->err = "mpasb_summarize_timestep_async: two summaries are already pending, fetch one first"; return 1; }
-    const int q = (int)(h->summary_head % 2);
+    if (h->summary_head - h->summary_tail >= H::SUMMARY_RING) { h->err = "mpasb_summarize_timestep_async: four summaries are already pending, fetch one first"; return 1; }
+    const int q = (int)(h->summary_head % H::SUMMARY_RING);
     if (!h->d_summary[q]) {
         CUDA_OK(cudaMalloc(&h->d_summary[q], nval * sizeof(double)));
         CUDA_OK(cudaMallocHost(&h->h_summary[q], nval * sizeof(double)));
@@ -1294,7 +1295,7 @@ extern "C" int mpasb_summarize_timestep_async(mpasb_handle h) {
 extern "C" int mpasb_summarize_timestep_fetch(mpasb_handle h, mpasb_real* minmax, long n_minmax, long nan_count[2]) {
     cudaSetDevice(h->device);
     if (h->summary_head == h->summary_tail) { h->err = "mpasb_summarize_timestep_fetch without a pending mpasb_summarize_timestep_async"; return 1; }
-    const int q = (int)(h->summary_tail % 2);            // oldest pending summary
+    const int q = (int)(h->summary_tail % H::SUMMARY_RING);            // oldest pending summary
     const int S = h->D.num_scalars;
     if (n_minmax < 4 || n_minmax > 2 * (2 + S)) { h->err = "mpasb_summarize_timestep_fetch: n_minmax out of range"; return 2; }
     CUDA_OK(cudaEventSynchronize(h->ev_summary[q]));
