@@ -281,6 +281,12 @@ __global__ void k_int_to_zero_based(int* __restrict__ dst, const int* __restrict
     if (t < n) dst[t] = src[t] - sub;
 }
 
+// a few values from device memory into pinned (device-accessible) host memory, without a copy engine
+__global__ void k_copy_to_host(double* __restrict__ host, const double* __restrict__ dev, int n) {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) host[t] = dev[t];
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------ halo exchange pack / unpack
 // One launch packs every (field, list element, level) of one exchange group.  seg[] describes
 // contiguous runs of the send buffer: run r moves `count` columns of field `fld` listed in

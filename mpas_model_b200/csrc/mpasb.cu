@@ -1287,7 +1287,11 @@ extern "C" int mpasb_summarize_timestep_async(mpasb_handle h) {
     for (int sc = 0; sc < S; sc++)
         k_minmax<<<296, 256, 0, h->stream>>>(D.scalars_2 + (size_t)sc * D.cellPlane, D.nCellsSolve, D.nl, D.LDK, ds + 4 + 2 * sc);
     h->launches += 2 + S;
-    CUDA_OK(cudaMemcpyAsync(h->h_summary[q], ds, nval * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // The result goes to the pinned host buffer by stores from a kernel (pinned memory is device-accessible under unified
+    // addressing), not by cudaMemcpyAsync: a copy-engine transfer on the compute stream would queue behind a bulk download
+    // already running on the same engine (mpasb_get_fields_async) and hold the next step back for its whole duration --
+    // measured: 17.6 instead of 13.1 ms per pipelined request.
+    k_copy_to_host<<<1, 64, 0, h->stream>>>(h->h_summary[q], ds, nval);
     CUDA_OK(cudaEventRecord(h->ev_summary[q], h->stream));
     h->summary_head++;
     return 0;
