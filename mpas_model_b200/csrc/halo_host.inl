@@ -115,6 +115,7 @@ extern "C" int mpasb_set_halo_lists(mpasb_handle h, int kind, int n_neighbors, c
     for (int i = 0; i < ts; i++) K.h_send[i] = send_src[i] - 1;     // ABI is 1-based
     for (int i = 0; i < tr; i++) K.h_recv[i] = recv_dst[i] - 1;
     h->halo.active = true;
+    h->ac_lists_ok = false;            // boundary / interior column lists of the cell solve follow the send lists
     return 0;
 }
 

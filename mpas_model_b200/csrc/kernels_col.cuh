@@ -1387,7 +1387,11 @@ __device__ __forceinline__ Ac6Conn ac6_conn(const Dev& D, int i, int lane, real 
     return c;
 }
 template <int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+// list != nullptr: the kernel works through the nlist columns of `list` instead of all cells -- a decomposed block runs it
+// twice per small step, first over the columns a neighbour rank needs (and its own halo columns), then, while their
+// exchange is on its way, over the rest (srk3: TI:1279/1302 exchanges hidden behind interior columns)
+__global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm,
+                                                                     const int* __restrict__ list, int nlist) {
     pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
@@ -1401,8 +1405,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
     // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
     const int G = gridDim.x * WARPS;
-    const int nAll = D.nCells;
-#define AC6_COL(j) (D.rev ? nAll - 1 - (j) : (j))             /* sweep direction of this launch (Dev::rev) */
+    const int nAll = list ? nlist : D.nCells;
+#define AC6_POS(j) (D.rev ? nAll - 1 - (j) : (j))             /* sweep direction of this launch (Dev::rev) */
+#define AC6_COL(j) (list ? list[AC6_POS(j)] : AC6_POS(j))
     int jcol = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
     if (jcol < nAll && AC6_COL(jcol) < D.nCellsSolve) cn = ac6_conn(D, AC6_COL(jcol), lane, dts);
@@ -1410,7 +1415,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     const r2 cofrz = LD(D.cofrz, 0);                     // (written by the vertical-coefficient kernel)
     for (; jcol < nAll; jcol += G) {
     const int i = AC6_COL(jcol);
-    const int inext = jcol + G < nAll ? AC6_COL(jcol + G) : nAll;     // the next column of this warp (nAll: none)
+    const int inext = jcol + G < nAll ? AC6_COL(jcol + G) : D.nCells; // the next column of this warp (nCells: none)
     r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
     if (!first) rtheta_pp = sel(k_lt_nl, LD(D.rtheta_pp, i), 0.0);
     if (i >= D.nCellsSolve) {                                                          // halo cells: TI:2827-2842 only
@@ -1524,6 +1529,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1 - coftz * r), 0.0));
     }
 #undef AC6_COL
+#undef AC6_POS
 }
 
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075

@@ -62,6 +62,7 @@ struct mpasb_handle_s {
     bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
     bool pdl = true;               // MPASB_PDL=0: no programmatic dependent launch
     bool snake = true;             // MPASB_SNAKE=0: every kernel sweeps its columns forward (Dev::rev)
+    int* d_ac_bnd = nullptr; int* d_ac_int = nullptr; int n_ac_bnd = 0, n_ac_int = 0; bool ac_lists_ok = false;   // build_acoustic_lists
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
@@ -218,6 +219,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->d_minmax) cudaFree(h->d_minmax);
+    if (h->d_ac_bnd) { cudaFree(h->d_ac_bnd); cudaFree(h->d_ac_int); }
     for (int q = 0; q < H::SUMMARY_RING; q++) {
         if (h->d_summary[q]) cudaFree(h->d_summary[q]);
         if (h->h_summary[q]) cudaFreeHost(h->h_summary[q]);
@@ -881,7 +883,27 @@ static void set_smlstep_pert_variables(H* h) {               // TI:2427-2508
     if (h->colwarp) LAUNCHW(k2_smlstep_pert, h->D.nCellsSolve, h->D);
     else LAUNCH(k_smlstep_pert, h->D.nCellsSolve, 0, h->D);
 }
-static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:2646-2984
+// Columns of the cell solve that an exchange of cell fields touches -- every owned cell on a send list, and the halo cells,
+// whose old rtheta_pp must be saved before the exchange overwrites it (TI:2827-2842) -- and all the others.
+static void build_acoustic_lists(H* h) {
+    const HaloKind& K = h->halo.kind[0];
+    const int nC = h->D.nCells, nS = h->D.nCellsSolve;
+    std::vector<char> mark(nC, 0);
+    for (int c : K.h_send) if (c >= 0 && c < nC) mark[c] = 1;
+    for (int c = nS; c < nC; c++) mark[c] = 1;
+    std::vector<int> bnd, inter;
+    for (int c = 0; c < nC; c++) (mark[c] ? bnd : inter).push_back(c);
+    if (h->d_ac_bnd) { cudaFree(h->d_ac_bnd); cudaFree(h->d_ac_int); }
+    cudaMalloc(&h->d_ac_bnd, std::max<size_t>(1, bnd.size()) * sizeof(int)); cudaMalloc(&h->d_ac_int, std::max<size_t>(1, inter.size()) * sizeof(int));
+    cudaMemcpyAsync(h->d_ac_bnd, bnd.data(), bnd.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_ac_int, inter.data(), inter.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    h->n_ac_bnd = (int)bnd.size(); h->n_ac_int = (int)inter.size(); h->ac_lists_ok = true;
+}
+// group != nullptr: the exchange of the cell fields this step produces (TI:1279/1302) is issued here as well -- between the
+// boundary and the interior columns of the cell solve where that is possible, after the routine otherwise
+static int advance_acoustic_step(H* h, real dts, int small_step, const char* group = nullptr) {    // TI:2646-2984
+    comm_wait(h);
     Scope sc(h, "atm_advance_acoustic_step");
     const real epssm = h->cfg.config_epssm;
     const real rcv = rgas / (cp - rgas);
@@ -902,26 +924,38 @@ static void advance_acoustic_step(H* h, real dts, int small_step) {    // TI:264
             if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
             static const int variant = getenv("MPASB_AC6") ? atoi(getenv("MPASB_AC6")) : 1;
             KScope ks_(h, "k:k6_acoustic_cell");
-#define AC6_LAUNCH(W, MB) do { const unsigned need = (unsigned)((h->D.nCells + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
-                klaunch(h, k6_acoustic_cell<W, MB>, dim3(std::min(need, resident)), dim3((W) * 32), 0, h->D, dts, small_step, epssm, resm); } while (0)
-            if (variant == 0) AC6_LAUNCH(8, 2);            // 128 registers, 16 warps per SM
-            else if (variant == 2) AC6_LAUNCH(4, 4);       // 128 registers, 16 warps per SM in smaller blocks
-            else AC6_LAUNCH(4, 3);                         // 168 registers, 12 warps per SM
+#define AC6_LAUNCH(W, MB, LIST, N) do { const unsigned need = (unsigned)(((N) + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
+                klaunch(h, k6_acoustic_cell<W, MB>, dim3(std::max(1u, std::min(need, resident))), dim3((W) * 32), 0, h->D, dts, small_step, epssm, resm, (const int*)(LIST), (int)(N)); \
+                h->launches++; } while (0)
+#define AC6_RUN(LIST, N) do { if (variant == 0) AC6_LAUNCH(8, 2, LIST, N);      /* 128 registers, 16 warps per SM */ \
+                              else if (variant == 2) AC6_LAUNCH(4, 4, LIST, N); /* 128 registers, 16 warps per SM in smaller blocks */ \
+                              else AC6_LAUNCH(4, 3, LIST, N); } while (0)       /* 168 registers, 12 warps per SM */
+            static const bool no_split = getenv("MPASB_NO_SPLIT") != nullptr;
+            if (group && h->halo.active && h->overlap && !h->profile && !no_split) {
+                // boundary columns first; their exchange travels while the interior columns are solved
+                if (!h->ac_lists_ok) build_acoustic_lists(h);
+                AC6_RUN(h->d_ac_bnd, h->n_ac_bnd);
+                if (exchange_async(h, group)) return 1;
+                AC6_RUN(h->d_ac_int, h->n_ac_int);
+                return 0;
+            }
+            AC6_RUN(nullptr, h->D.nCells);
+#undef AC6_RUN
 #undef AC6_LAUNCH
-            h->launches++;
-            return;
+            return group ? exchange(h, group) : 0;
         }
         const size_t smem3 = (size_t)AC3_ARRAYS * AC3_COLS * (h->D.LDK | 1) * sizeof(real);
         if (!h->smem_attr_ac) { cudaFuncSetAttribute(k3_acoustic_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); h->smem_attr_ac = true; }
         KScope ks_(h, "k:k3_acoustic_cell");
         klaunch(h, k3_acoustic_cell, dim3((unsigned)((h->D.nCells + AC3_COLS - 1) / AC3_COLS)), dim3(AC3_WARPS * 32), smem3, h->D, dts, small_step, epssm, resm);
         h->launches++;
-        return;
+        return group ? exchange(h, group) : 0;
     }
     LAUNCH(k_acoustic_edge, h->D.nEdges, 0, h->D, dts, small_step, c2);
     const size_t smem = (size_t)6 * h->D.LDK * h->cpb * sizeof(real);
     LAUNCH(k_acoustic_cell, h->D.nCells, smem, h->D, dts, small_step, epssm, resm);
     if (h->D.apply_lbcs) LAUNCH(k_lbc_acoustic_spec, h->D.nCellsSolve, 0, h->D, dts, small_step, epssm);      // TI:2962-2971
+    return group ? exchange(h, group) : 0;
 }
 // defer: the next kernel that reads ru_p (the edge update of the next small step, or -- single block -- the edge part of
 // recover_large_step_variables) applies the damping in registers; same arithmetic, one kernel and one ru_p round trip less
@@ -930,6 +964,7 @@ static void divergence_damping_3d(H* h, real dts, bool defer = false) {         
     const real rdts = 1.0 / dts;
     const real coef_divdamp = 2.0 * h->cfg.config_smdiv * h->cfg.config_len_disp * rdts;
     if (h->colwarp && defer && h->fuse_dd) { h->dd_deferred = true; h->dd_coef = coef_divdamp; h->dd_dts = dts; return; }
+    comm_wait(h);                      // the rtheta_pp halos of an exchange started inside advance_acoustic_step
     if (h->colwarp) {
         LAUNCHW(k2_divergence_damping, h->D.nEdges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts);
         h->ru_p_pending = false;
@@ -1183,9 +1218,8 @@ static int srk3(H* h, real dt) {
                 // TI:1279 exchanges rho_pp before every acoustic step.  On the first small step nothing reads the
                 // halo of rho_pp (the edge update is ru_p = dts * tend_u, TI:2798-2806), so that exchange is skipped;
                 // on later ones it is merged into the rtheta_pp exchange (TI:1302) that directly precedes it.
-                advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step);
                 const bool more = small_step < number_sub_steps[rk_step];
-                if (exchange(h, more ? "dynamics:rtheta_pp,rho_pp" : "dynamics:rtheta_pp")) return 1;
+                if (advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step, more ? "dynamics:rtheta_pp,rho_pp" : "dynamics:rtheta_pp")) return 1;
                 // (more small steps follow, or nothing exchanges ru_p: the damping is folded into the next edge kernel)
                 divergence_damping_3d(h, rk_sub_timestep[rk_step], more || !h->halo.active);
             }
