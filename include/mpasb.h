@@ -164,6 +164,8 @@ int  mpasb_set_halo_lists(mpasb_handle h, int kind /*0 cell,1 edge,2 vertex*/, i
 int  mpasb_comm_init(mpasb_handle h, int rank, int world_size, const void* nccl_unique_id /*128 bytes*/);
 int  mpasb_get_nccl_unique_id(void* out128);
 int  mpasb_exchange_halo_group(mpasb_handle h, const char* group_name);   /* HALOS:90-167 names */
+/* the same, only enqueued: for requests queued back to back (mpasb_set_fields_async ... mpasb_get_fields_async) */
+int  mpasb_exchange_halo_group_async(mpasb_handle h, const char* group_name);
 /* Optional: exchanges by direct stores into the neighbours' mailboxes over NVLink (CUDA IPC) instead of NCCL send/recv.
  * After mpasb_set_halo_lists and mpasb_comm_init, on every rank of ONE node (2..9 ranks):
  *   n = mpasb_p2p_max_message(h)                      largest message of this rank, in reals

@@ -116,6 +116,7 @@ extern "C" int mpasb_set_halo_lists(mpasb_handle h, int kind, int n_neighbors, c
     for (int i = 0; i < tr; i++) K.h_recv[i] = recv_dst[i] - 1;
     h->halo.active = true;
     h->ac_lists_ok = false;            // boundary / interior column lists of the cell solve follow the send lists
+    h->dd_lists_ok = false;            // ... and so do the edges the damping kernel must finish before the ru_p exchange
     return 0;
 }
 
@@ -284,6 +285,11 @@ extern "C" int mpasb_p2p_enable(mpasb_handle h, int on) {
     return 0;
 }
 
+extern "C" int mpasb_exchange_halo_group_async(mpasb_handle h, const char* group_name) {
+    cudaSetDevice(h->device);
+    if (!h->halo.active) return 0;
+    return exchange(h, group_name) ? 1 : 0;
+}
 extern "C" int mpasb_exchange_halo_group(mpasb_handle h, const char* group_name) {
     cudaSetDevice(h->device);
     if (!h->halo.active) return 0;

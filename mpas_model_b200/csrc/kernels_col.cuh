@@ -1391,7 +1391,7 @@ template <int WARPS, int MINB>
 // twice per small step, first over the columns a neighbour rank needs (and its own halo columns), then, while their
 // exchange is on its way, over the rest (srk3: TI:1279/1302 exchanges hidden behind interior columns)
 __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm,
-                                                                     const int* __restrict__ list, int nlist) {
+                                                                     const int* list, int nlist) {
     pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
@@ -1535,8 +1535,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075
 // first != 0: also performs the first-small-step edge update of atm_advance_acoustic_step_work (TI:2798-2806:
 // ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
-__global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts) {
-    CW_ENTER(D.nEdges)
+// list != nullptr: only the nlist edges of `list` (a decomposed block: the owned edges a neighbour rank receives; the damping
+// of every other edge is folded into k2_recover_edge)
+__global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D, real coef_divdamp, int first, real dts,
+                                                                    const int* list, int nlist) {
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ncols = list ? nlist : D.nEdges;
+    const int i_fwd = blockIdx.x * CW_WARPS + wib;
+    const int LDK = D.LDK, nl = D.nl;
+    if (i_fwd >= ncols) return;
+    const int i_pos = D.rev ? ncols - 1 - i_fwd : i_fwd;
+    const int i = list ? list[i_pos] : i_pos;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
@@ -1591,7 +1604,9 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC1) k2_recover_cell1(const De
 // (2) edge-all, TI:3360-3372
 // dd_mode != 0: the divergence damping of the last small step (TI:3040-3060) has not been applied to ru_p yet and is applied
 // here on the fly (1: ru_p holds the undamped value; 2: first small step, ru_p = ruAvg = dts * tend_u was never stored either).
-// Single block only: with halos the damped ru_p must exist before the exchange of TI:1322.
+// With halos the damped ru_p must exist before the exchange of TI:1322 on every edge a neighbour receives: those edges are damped
+// by k2_divergence_damping (list form) and flagged in dd_done; the fold applies to the other edges this block computes itself
+// (an owned cell on either side), and edges further out keep the value the exchange delivered.
 __device__ __forceinline__ r2 dd_term(const Dev& D, int cell1, int cell2, int i, real coef_divdamp, unsigned uLDK, unsigned kc) {
     const real mask = 1.0 - D.specZoneMaskEdge[i];
     const r2 divCell1 = -(LD(D.rtheta_pp, cell1) - LD(D.rtheta_pp_old, cell1));
@@ -1599,10 +1614,12 @@ __device__ __forceinline__ r2 dd_term(const Dev& D, int cell1, int cell2, int i,
     const r2 th = LD(D.theta_m, cell1) + LD(D.theta_m, cell2);
     return coef_divdamp * (divCell2 - divCell1) * mask / th;
 }
-__global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs, int dd_mode, real coef_divdamp, real dts) {
+__global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs, int dd_mode_in, real coef_divdamp, real dts,
+                                                              const unsigned char* dd_done) {
     CW_ENTER(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
+    const int dd_mode = (dd_done && (dd_done[i] || !(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve))) ? 0 : dd_mode_in;   // warp-uniform
     pdl_wait();
     const r2 rus = LD(D.ru_save, i);
     r2 ru_p, ruAvg;

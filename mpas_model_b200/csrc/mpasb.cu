@@ -62,6 +62,7 @@ struct mpasb_handle_s {
     bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
     bool pdl = true;               // MPASB_PDL=0: no programmatic dependent launch
     bool snake = true;             // MPASB_SNAKE=0: every kernel sweeps its columns forward (Dev::rev)
+    int* d_dd_edges = nullptr; unsigned char* d_dd_done = nullptr; int n_dd_edges = 0; bool dd_lists_ok = false, dd_partial = false;   // build_dd_lists
     int* d_ac_bnd = nullptr; int* d_ac_int = nullptr; int n_ac_bnd = 0, n_ac_int = 0; bool ac_lists_ok = false;   // build_acoustic_lists
     bool profile = false;
     bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
@@ -220,6 +221,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->d_minmax) cudaFree(h->d_minmax);
     if (h->d_ac_bnd) { cudaFree(h->d_ac_bnd); cudaFree(h->d_ac_int); }
+    if (h->d_dd_edges) { cudaFree(h->d_dd_edges); cudaFree(h->d_dd_done); }
     for (int q = 0; q < H::SUMMARY_RING; q++) {
         if (h->d_summary[q]) cudaFree(h->d_summary[q]);
         if (h->h_summary[q]) cudaFreeHost(h->h_summary[q]);
@@ -930,8 +932,11 @@ static int advance_acoustic_step(H* h, real dts, int small_step, const char* gro
 #define AC6_RUN(LIST, N) do { if (variant == 0) AC6_LAUNCH(8, 2, LIST, N);      /* 128 registers, 16 warps per SM */ \
                               else if (variant == 2) AC6_LAUNCH(4, 4, LIST, N); /* 128 registers, 16 warps per SM in smaller blocks */ \
                               else AC6_LAUNCH(4, 3, LIST, N); } while (0)       /* 168 registers, 12 warps per SM */
-            static const bool no_split = getenv("MPASB_NO_SPLIT") != nullptr;
-            if (group && h->halo.active && h->overlap && !h->profile && !no_split) {
+            // opt-in (MPASB_SPLIT=1): measured on 4 B200 it does not pay -- 13.73 / 13.85 ms per step against 13.60 ms with the
+            // exchange simply following the kernel: the two launches lose more (a scattered boundary launch, two tails) than
+            // the ~20 us of exchange they hide (profiles/r2_bench_t_4gpu_*)
+            static const bool split = getenv("MPASB_SPLIT") != nullptr && atoi(getenv("MPASB_SPLIT")) != 0;
+            if (group && h->halo.active && h->overlap && !h->profile && split) {
                 // boundary columns first; their exchange travels while the interior columns are solved
                 if (!h->ac_lists_ok) build_acoustic_lists(h);
                 AC6_RUN(h->d_ac_bnd, h->n_ac_bnd);
@@ -959,14 +964,38 @@ static int advance_acoustic_step(H* h, real dts, int small_step, const char* gro
 }
 // defer: the next kernel that reads ru_p (the edge update of the next small step, or -- single block -- the edge part of
 // recover_large_step_variables) applies the damping in registers; same arithmetic, one kernel and one ru_p round trip less
-static void divergence_damping_3d(H* h, real dts, bool defer = false) {           // TI:2987-3075
+// Owned edges on a send list of the edge kind (any layer) and their flags: see k2_recover_edge
+static void build_dd_lists(H* h) {
+    const HaloKind& K = h->halo.kind[1];
+    const int nE = h->D.nEdges;
+    std::vector<unsigned char> done(nE + 1, 0);
+    for (int e : K.h_send) if (e >= 0 && e < nE) done[e] = 1;
+    std::vector<int> list;
+    for (int e = 0; e < nE; e++) if (done[e]) list.push_back(e);
+    if (h->d_dd_edges) { cudaFree(h->d_dd_edges); cudaFree(h->d_dd_done); }
+    cudaMalloc(&h->d_dd_edges, std::max<size_t>(1, list.size()) * sizeof(int)); cudaMalloc(&h->d_dd_done, done.size());
+    cudaMemcpyAsync(h->d_dd_edges, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_dd_done, done.data(), done.size(), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    h->n_dd_edges = (int)list.size(); h->dd_lists_ok = true;
+}
+// partial: decomposed block, the exchange of ru_p follows (TI:1322)
+static void divergence_damping_3d(H* h, real dts, bool defer = false, bool partial = false) {           // TI:2987-3075
     Scope sc(h, "atm_divergence_damping_3d");
     const real rdts = 1.0 / dts;
     const real coef_divdamp = 2.0 * h->cfg.config_smdiv * h->cfg.config_len_disp * rdts;
     if (h->colwarp && defer && h->fuse_dd) { h->dd_deferred = true; h->dd_coef = coef_divdamp; h->dd_dts = dts; return; }
     comm_wait(h);                      // the rtheta_pp halos of an exchange started inside advance_acoustic_step
+    if (h->colwarp && partial && h->fuse_dd) {
+        // decomposed block, last small step of a stage: damp (and, on a first small step, materialise) only the edges a neighbour
+        // is about to receive (TI:1322); k2_recover_edge applies the same arithmetic to every other edge in registers
+        if (!h->dd_lists_ok) build_dd_lists(h);
+        if (h->n_dd_edges) LAUNCHW(k2_divergence_damping, h->n_dd_edges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts, (const int*)h->d_dd_edges, h->n_dd_edges);
+        h->dd_deferred = true; h->dd_partial = true; h->dd_coef = coef_divdamp; h->dd_dts = dts;      // ru_p_pending stays as it is: mode 2 for the folded edges
+        return;
+    }
     if (h->colwarp) {
-        LAUNCHW(k2_divergence_damping, h->D.nEdges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts);
+        LAUNCHW(k2_divergence_damping, h->D.nEdges, h->D, coef_divdamp, h->ru_p_pending ? 1 : 0, dts, (const int*)nullptr, 0);
         h->ru_p_pending = false;
         return;
     }
@@ -984,8 +1013,8 @@ static int recover_large_step_variables(H* h, real dt, int ns, int rk_step, bool
         LAUNCHW(k2_recover_cell1, h->D.nCells + 1, h->D, dt, invNs, rk_step, rcv, rgas / p0);
         {
             const int dd_mode = h->dd_deferred ? (h->ru_p_pending ? 2 : 1) : 0;
-            LAUNCHW(k2_recover_edge, h->D.nEdges, h->D, invNs, dd_mode, h->dd_coef, h->dd_dts);
-            h->dd_deferred = false; h->ru_p_pending = false;
+            LAUNCHW(k2_recover_edge, h->D.nEdges, h->D, invNs, dd_mode, h->dd_coef, h->dd_dts, (const unsigned char*)(h->dd_partial ? h->d_dd_done : nullptr));
+            h->dd_deferred = false; h->ru_p_pending = false; h->dd_partial = false;
         }
     } else {
         LAUNCH(k_recover_cell1, h->D.nCells + 1, 0, h->D, dt, invNs, rk_step, rcv, rgas / p0);
@@ -1221,7 +1250,8 @@ static int srk3(H* h, real dt) {
                 const bool more = small_step < number_sub_steps[rk_step];
                 if (advance_acoustic_step(h, rk_sub_timestep[rk_step], small_step, more ? "dynamics:rtheta_pp,rho_pp" : "dynamics:rtheta_pp")) return 1;
                 // (more small steps follow, or nothing exchanges ru_p: the damping is folded into the next edge kernel)
-                divergence_damping_3d(h, rk_sub_timestep[rk_step], more || !h->halo.active);
+                static const bool dd_partial_ok = !getenv("MPASB_NO_DD_PARTIAL");
+                divergence_damping_3d(h, rk_sub_timestep[rk_step], more || !h->halo.active, !more && h->halo.active && dd_partial_ok);
             }
             if (exchange(h, "dynamics:rw_p,ru_p,rho_pp,rtheta_pp")) return 1;
             if (recover_large_step_variables(h, rk_timestep[rk_step], number_sub_steps[rk_step], rk_step, !lbcs)) return 1;   // starts u_3 (TI:1371)

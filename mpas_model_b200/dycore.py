@@ -272,6 +272,10 @@ class Dycore(Backend):
     def exchange_halo_group(self, name):
         self._check(self.lib.mpasb_exchange_halo_group(self._h, name.encode()), f"exchange {name}")
 
+    def exchange_halo_group_async(self, name):
+        """the same without waiting for it on the host"""
+        self._check(self.lib.mpasb_exchange_halo_group_async(self._h, name.encode()), f"exchange {name}")
+
     def set_halo_lists(self, kind, lists):
         """kind: 0 cells, 1 edges, 2 vertices; lists: decomp.exchange_lists()[rank][kind name]."""
         nbrs, nl, n_send, ss, n_recv, rr = self._flatten_halo_lists(lists)
