@@ -206,8 +206,8 @@ def reference_arm(args, rank, world):
         for r in ranks:
             rec = mg.load_block(prefix, r)
             ob = OracleDycore(rec["block"], rec["cfg"], rank=r)
-            for kind, k in mg.KINDS:
-                ob.set_halo_lists(k, rec["ex"][kind])
+            for halo_kind, k in mg.KINDS:
+                ob.set_halo_lists(k, rec["ex"][halo_kind])
             blocks.append(ob)
             cfg = rec["cfg"]
         frac = 1.0 if whole else 1.0 / args.gpus

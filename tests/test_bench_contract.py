@@ -31,6 +31,17 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and abs(d["value"] - 642 * 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
 
 
+def test_reference_arm_decomposed(tmp_path):
+    """N > 1: rank 0 steps all N blocks of the decomposition in lock step (nothing extrapolated) with the C++ restatement."""
+    r = _run("--impl", "reference", "--gpus", "2", "--cells", "642", "--levels", "10", "--steps", "2", "--warmup", "3",
+             env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "MPASB_CACHE": str(tmp_path)})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    cb = d["cpu_baseline"]
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and cb["kind"] == "port" and cb["extrapolated"] is False
+    assert "all 2 blocks" in cb["sample"] and d["value"] > 0
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run("--impl", "reference", "--gpus", "2", "--cells", "642", "--levels", "10", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
