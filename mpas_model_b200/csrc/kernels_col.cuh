@@ -118,13 +118,27 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
 #define CW_SETUP(ncols) PDL_ENTER CW_SETUP_NW(ncols)
 // the hot kernels: CW_ENTER, loads of static mesh data (connectivity, metric weights), then pdl_wait() before the first field access
 #define CW_ENTER(ncols) pdl_trigger(); CW_SETUP_NW(ncols)
+// Sweep direction.  Consecutive kernels of a step walk their columns in OPPOSITE directions, so a kernel starts where its
+// predecessor just finished and finds the tail of that kernel's inputs and outputs still in the 126 MB L2.  The direction is a
+// compile-time property of each kernel (the order of the kernels in a stage is fixed and alternates: see srk3): the _R forms
+// start at the last column.  (A run-time direction flag cost every kernel a register -- a reversed index cannot be
+// rematerialised from blockIdx for free -- and pushed three kernels over an occupancy step: measured)
+#define CW_SETUP_R(ncols) PDL_ENTER CW_SETUP_NW_R(ncols)
+#define CW_ENTER_R(ncols) pdl_trigger(); CW_SETUP_NW_R(ncols)
+#define CW_SETUP_NW_R(ncols)                                                                  \
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
+    const int i = (ncols) - 1 - (int)(blockIdx.x * CW_WARPS + wib);                           \
+    const int LDK = D.LDK, nl = D.nl;                                                         \
+    if (i < 0) return;                                                                        \
+    CW_SETUP_REST
 // ... without the wait: the kernel places pdl_wait() itself, below its loads of static mesh data
 #define CW_SETUP_NW(ncols)                                                                    \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
-    const int i_fwd_ = blockIdx.x * CW_WARPS + wib;                                           \
+    const int i = blockIdx.x * CW_WARPS + wib;                                                \
     const int LDK = D.LDK, nl = D.nl;                                                         \
-    if (i_fwd_ >= (ncols)) return;                                                            \
-    const int i = D.rev ? (ncols) - 1 - i_fwd_ : i_fwd_;                                      \
+    if (i >= (ncols)) return;                                                                 \
+    CW_SETUP_REST
+#define CW_SETUP_REST                                                                         \
     Lv lv; lv.k0 = 2 * lane;                                                                  \
     const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;                             \
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
     const int LDK = D.LDK, nl = D.nl;
     real* s_w = reinterpret_cast<real*>(ef_raw);
     real* s_t = s_w + EF_MAXT * LDK;
-    const int tile = D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int tile = blockIdx.x;
     const int4 hdr = tile_hdr[tile];                        // (runs, staged columns, active-edge mask); runs < 0: gather from global memory
     const int nt = hdr.x;
     Lv lv; lv.k0 = 2 * lane;
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
     const int G = gridDim.x * FX_WARPS;
     const int le = min(lane, 5), lr = min(lane, FX_RING - 1);
     const int nSolve = D.nCellsSolve;
-#define FX_COL(j) (D.rev ? nSolve - 1 - (j) : (j))            /* sweep direction of this launch (Dev::rev) */
+#define FX_COL(j) (j)                                         /* forward sweep (see CW_SETUP_R) */
     int j = blockIdx.x * FX_WARPS + wib;
     int my_ring = 0, my_e = 0; real my_sgn = 0.0;
     if (j < nSolve) {
@@ -445,7 +459,7 @@ __global__ void __launch_bounds__(CW_THREADS, FX1_MINB) k5s_flux_cell(const Dev 
     const int field = g & 1;
     const int LDK = D.LDK, nl = D.nl;
     if ((g >> 1) >= D.nCellsSolve) return;
-    const int i = D.rev ? D.nCellsSolve - 1 - (g >> 1) : (g >> 1);
+    const int i = g >> 1;
     Lv lv; lv.k0 = 2 * lane;
     const int k0 = lv.k0; const bool act = k0 < D.LDKA;
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
@@ -530,7 +544,7 @@ __global__ void __launch_bounds__(CW_THREADS, FX1_MINB) k5s_flux_cell(const Dev 
 // here from the per-edge fluxes of k2_dt_edge_flux
 template <bool HDIV>
 __global__ void __launch_bounds__(CW_THREADS, CELLF_MINB) k2_dt_cell_f(const Dev D, const DynTendArgs A) {
-    CW_SETUP(D.nCellsSolve)
+    CW_SETUP_R(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     // one edge of the cell per lane (lanes >= ne repeat the last edge): id, sign, mixing metadata
     const int le = min(lane, ne - 1);
@@ -681,7 +695,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
     const int G = gridDim.x * WARPS;
     const int nSolve = D.nCellsSolve;
-#define CF7_COL(j) (D.rev ? nSolve - 1 - (j) : (j))           /* sweep direction of this launch (Dev::rev) */
+#define CF7_COL(j) (nSolve - 1 - (j))                         /* backward sweep (see CW_SETUP_R) */
     int jcol = blockIdx.x * WARPS + wib;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
     if (jcol < nSolve) cn = cf_conn(D, CF7_COL(jcol), lane, rk1);
@@ -832,7 +846,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k8_coriolis_cell(const Dev D) {
 // arithmetic), instead of being gathered here over edgesOnEdge
 template <bool COR>
 __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
-    CW_ENTER(D.nEdges)
+    CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
     const real invDc = D.invDcEdge[i];
@@ -903,6 +917,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
     CW_ENTER(D.nCellsSolve)
+    if (D.bdyMaskCell[i] > 5) return;                  // regional run: no conversion in the specified zone, TI:2482 (static mask)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -934,6 +949,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
 __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     CW_ENTER(D.nCells)
+    if (D.bdyMaskCell[i] > 5) return;                  // regional run: no update in the specified zone, TI:3385 (static mask)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -967,7 +983,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
 // (1) vertex-all: vorticity (6452-6472), ke_vertex (6548-6561, ke_edge recomputed inline), pv_vertex (6647-6659)
 __global__ void __launch_bounds__(CW_THREADS) k2_diag_vertex(const Dev D, const real* u) {
-    CW_ENTER(D.nVertices)
+    CW_ENTER_R(D.nVertices)
     int my_e = 0; real my_s = 0.0, my_efac = 0.0;
     {
         const int l3 = min(lane, 2);
@@ -1039,7 +1055,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_C) k2_diag_cell(const Dev 
 // (3) edge-all: h_edge (6428-6435), tangential velocity v (6618-6632, rk 3 only), pv_edge with APVM upwinding (6673-6745)
 __global__ void __launch_bounds__(CW_THREADS, MB_DIAG_E) k2_diag_edge(const Dev D, const real* u, const real* h,
                                                            int reconstruct_v, int apvm, real apvm_dt) {
-    CW_ENTER(D.nEdges)
+    CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const int vertex1 = D.verticesOnEdge[2 * i], vertex2 = D.verticesOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
@@ -1123,7 +1139,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_A) k2_dt_cell_a(const Dev 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (e)
 // rk 1, cell-all: first del^2 of w (5795-5829) and of theta_m (6027-6057) with their 2nd-order mixing tendencies
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_E) k2_dt_cell_e(const Dev D, const DynTendArgs A) {
-    CW_ENTER(D.nCells)
+    CW_ENTER_R(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1211,7 +1227,7 @@ __global__ void __launch_bounds__(AC3_WARPS * 32, AC3_MINB) k3_acoustic_cell(con
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const bool first = small_step == 1;
     const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
-    const int base = (D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * AC3_COLS;      // sweep direction of this launch
+    const int base = (gridDim.x - 1 - blockIdx.x) * AC3_COLS;      // backward sweep (see CW_SETUP_R)
     const r2 rdzw = LD(D.rdzw, 0), cofrz = LD(D.cofrz, 0);
     // connectivity of ALL columns of this warp in one pass: lane = (column slot << 3) | edge slot, so the two
     // dependent index loads (edgesOnCell -> cellsOnEdge/dvEdge) are exposed once per warp, not once per column
@@ -1386,10 +1402,11 @@ __device__ __forceinline__ Ac6Conn ac6_conn(const Dev& D, int i, int lane, real 
     c.invArea = D.invAreaCell[i];
     return c;
 }
-template <int WARPS, int MINB>
-// list != nullptr: the kernel works through the nlist columns of `list` instead of all cells -- a decomposed block runs it
-// twice per small step, first over the columns a neighbour rank needs (and its own halo columns), then, while their
-// exchange is on its way, over the rest (srk3: TI:1279/1302 exchanges hidden behind interior columns)
+// LISTED: the kernel works through the nlist columns of `list` instead of all cells -- a decomposed block may run it twice per
+// small step, first over the columns a neighbour rank needs (and its own halo columns), then, while their exchange is on its
+// way, over the rest (MPASB_SPLIT=1).  REGIONAL: with the specified-zone branch of TI:2862.  Both are template parameters
+// because either costs the plain kernel its last free registers (168, 24 bytes of spills otherwise).
+template <int WARPS, int MINB, bool LISTED, bool REGIONAL>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm,
                                                                      const int* list, int nlist) {
     pdl_trigger();
@@ -1405,9 +1422,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
     // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
     const int G = gridDim.x * WARPS;
-    const int nAll = list ? nlist : D.nCells;
-#define AC6_POS(j) (D.rev ? nAll - 1 - (j) : (j))             /* sweep direction of this launch (Dev::rev) */
-#define AC6_COL(j) (list ? list[AC6_POS(j)] : AC6_POS(j))
+    const int nAll = LISTED ? nlist : D.nCells;
+#define AC6_POS(j) (nAll - 1 - (j))                           /* backward sweep (see CW_SETUP_R) */
+#define AC6_COL(j) (LISTED ? list[AC6_POS(j)] : AC6_POS(j))
     int jcol = blockIdx.x * WARPS + wib;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
     if (jcol < nAll && AC6_COL(jcol) < D.nCellsSolve) cn = ac6_conn(D, AC6_COL(jcol), lane, dts);
@@ -1433,6 +1450,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
         wwAvg = sel(k_le_nl, LD(D.wwAvg, i), 0.0);
     }
     const r2 tend_rho = LD(D.tend_rho, i), tend_theta = LD(D.tend_theta, i), tend_w = LD(D.tend_w, i);
+    if (REGIONAL && D.specZoneMaskCell[i] != 0.0) {
+        // specified zone of a regional run (TI:2862, 2962-2971): no implicit solve, the perturbation variables follow their
+        // (driving) tendencies; row nl is zeroed on the first small step and left alone afterwards
+        const r2 rw_new = rw_p + dts * tend_w;
+        ST(D.rtheta_pp_old, i, rtheta_pp);
+        ST(D.rho_pp, i, sel(k_lt_nl, rho_pp + dts * tend_rho, 0.0));
+        ST(D.rtheta_pp, i, sel(k_lt_nl, rtheta_pp + dts * tend_theta, 0.0));
+        ST(D.rw_p, i, sel(k_lt_nl, rw_new, sel(k_le_nl, rw_p, 0.0)));
+        ST(D.wwAvg, i, sel(k_lt_nl, wwAvg + 0.5 * (1.0 + epssm) * rw_new, sel(k_le_nl, wwAvg, 0.0)));
+        if (inext < D.nCellsSolve) cn = ac6_conn(D, inext, lane, dts);
+        continue;
+    }
     const r2 coftz = LD(D.coftz, i), cofwz = LD(D.cofwz, i), cofwr = LD(D.cofwr, i), cofwt = LD(D.cofwt, i);
     const r2 zz = LD(D.zz, i);
     const r2 a_tri = LD(D.a_tri, i), al_tri = LD(D.alpha_tri, i), ga_tri = LD(D.gamma_tri, i);
@@ -1545,7 +1574,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_divergence_damping(const Dev D,
     const int i_fwd = blockIdx.x * CW_WARPS + wib;
     const int LDK = D.LDK, nl = D.nl;
     if (i_fwd >= ncols) return;
-    const int i_pos = D.rev ? ncols - 1 - i_fwd : i_fwd;
+    const int i_pos = i_fwd;
     const int i = list ? list[i_pos] : i_pos;
     Lv lv; lv.k0 = 2 * lane;
     const int k0 = lv.k0; const bool act = k0 < D.LDKA; (void)nl;
@@ -1616,7 +1645,7 @@ __device__ __forceinline__ r2 dd_term(const Dev& D, int cell1, int cell2, int i,
 }
 __global__ void __launch_bounds__(CW_THREADS) k2_recover_edge(const Dev D, real invNs, int dd_mode_in, real coef_divdamp, real dts,
                                                               const unsigned char* dd_done) {
-    CW_ENTER(D.nEdges)
+    CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const b2 k_lt_nl = lv.lt(nl);
     const int dd_mode = (dd_done && (dd_done[i] || !(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve))) ? 0 : dd_mode_in;   // warp-uniform
@@ -1658,8 +1687,8 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
 // ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855
 // edge value of every scalar ("horiz_flux_arr"), TI:3670-3751: one warp per edge, the stencil indices and the two
 // possible weights per entry live one per lane and are broadcast; scalars are separate level-contiguous planes
-__global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
-    CW_SETUP(D.nEdges)
+__global__ void __launch_bounds__(CW_THREADS, 6) k2_scalars_edge(const Dev D) {
+    CW_SETUP_R(D.nEdges)
     const int nadv = D.nAdvCellsForEdge[i];
     int my_c = 0; real my_wp = 0.0, my_wm = 0.0;
     if (lane < nadv) {
@@ -1667,8 +1696,22 @@ __global__ void __launch_bounds__(CW_THREADS) k2_scalars_edge(const Dev D) {
         const real a = D.adv_coefs[(unsigned)i * 15 + lane], b = D.adv_coefs_3rd[(unsigned)i * 15 + lane];
         my_wp = a + b; my_wm = a - b;
     }
-    const b2 pos = nonneg_sign(LD(D.ruAvg, i));
+    const r2 ruavg = LD(D.ruAvg, i);
+    const b2 pos = nonneg_sign(ruavg);
     const b2 k_lt_nl = lv.lt(nl);
+    if (D.apply_lbcs && D.bdyMaskEdge[i] >= 4) {           // regional run, TI:3732-3750 (warp-uniform)
+        if (D.bdyMaskEdge[i] > 5) return;                   // edges of the specified zone: nothing
+        // the two outermost rings of the relaxation zone take the upwind cell value
+        const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+        const real dv = D.dvEdge[i];
+        const r2 u_direction = mk2(copysign((real)0.5, ruavg.x), copysign((real)0.5, ruavg.y));
+        const r2 u_positive = dv * abs2(u_direction + 0.5), u_negative = dv * abs2(u_direction - 0.5);
+        for (int s = 0; s < D.num_scalars; s++) {
+            const real* q = D.scalars_2 + (size_t)s * D.cellPlane;
+            ST(D.horiz_flux_arr + (size_t)s * D.edgePlane, i, sel(k_lt_nl, u_positive * LD(q, cell1) + u_negative * LD(q, cell2), 0.0));
+        }
+        return;
+    }
     for (int s = 0; s < D.num_scalars; s++) {
         const real* __restrict__ q = D.scalars_2 + (size_t)s * D.cellPlane;
         r2 acc = mk2(0.0, 0.0);
@@ -1697,6 +1740,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SC_CELL) k2_scalars_cell(const 
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const real invArea = D.invAreaCell[i];
+    if (D.bdyMaskCell[i] > 5) return;                  // regional run: the specified zone is not updated here, TI:3775
     const r2 rho_old = LD(D.rho_zz, i), rho_new = LD(D.rho_zz_2, i);
     const r2 rho_zz_new_inv = 1.0 / (weight_time_old * rho_old + weight_time_new * rho_new);
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0);
@@ -1759,7 +1803,7 @@ __global__ void __launch_bounds__(VIC_WARPS * 32, MB_VIC) k3_vert_imp_coefs(cons
     const int k0 = lv.k0; const bool act = k0 < D.LDKA;
     const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
     const b2 k_lt_nl = lv.lt(nl), k_mid = lv.ge(1) && lv.lt(nl);
-    const int base = (D.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * VIC_COLS;      // sweep direction of this launch
+    const int base = (gridDim.x - 1 - blockIdx.x) * VIC_COLS;      // backward sweep (see CW_SETUP_R)
     const r2 fzm = LD(D.fzm, 0), fzp = LD(D.fzp, 0), rdzw = LD(D.rdzw, 0), rdzu = LD(D.rdzu, 0);
     const r2 cofrz = dtseps * rdzw;
     if (blockIdx.x == 0 && wib == 0) ST(D.cofrz, 0, sel(k_lt_nl, cofrz, 0.0));
@@ -1833,7 +1877,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_vertex(const Dev D) {
     ST(D.delsq_vorticity, i, sel(lv.lt(nl), acc, 0.0));
 }
 __global__ void __launch_bounds__(CW_THREADS) k2_dt_delsq_cell(const Dev D) {
-    CW_SETUP(D.nCells)
+    CW_SETUP_R(D.nCells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1873,7 +1917,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const Dy
 __device__ __forceinline__ r2 max0(r2 a) { return mk2(rmax(0.0, a.x), rmax(0.0, a.y)); }
 __device__ __forceinline__ r2 min0(r2 a) { return mk2(rmin(0.0, a.x), rmin(0.0, a.y)); }
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, real dt) {
-    CW_SETUP(D.nEdges)
+    CW_SETUP_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
@@ -1902,8 +1946,11 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, 
     const r2 flux = ten ? uh * acc : acc;
     const r2 fup = D.dvEdge[i] * dt * (max0(uh) * so1 + min0(uh) * so2);
     const b2 k_lt_nl = lv.lt(nl);
+    // TI:4479 (and :4592), as written there: `config_apply_lbcs .and. (m == nRelaxZone) .or. (m == nRelaxZone-1)`
+    const int m_bdy = D.bdyMaskEdge[i];
+    const bool upwind_only = (D.apply_lbcs && m_bdy == 5) || m_bdy == 4;
     ST(D.flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
-    ST(D.flux_tmp, i, sel(k_lt_nl, dt * flux - fup, 0.0));
+    ST(D.flux_tmp, i, upwind_only ? mk2(0.0, 0.0) : sel(k_lt_nl, dt * flux - fup, 0.0));
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, the other parts
@@ -1911,7 +1958,7 @@ __device__ __forceinline__ r2 max2(r2 a, r2 b) { return mk2(rmax(a.x, b.x), rmax
 __device__ __forceinline__ r2 min2(r2 a, r2 b) { return mk2(rmin(a.x, b.x), rmin(a.y, b.y)); }
 // (B) owned cells: re-integrated density, TI:4177-4204
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real dt) {
-    CW_SETUP(D.nCellsSolve)
+    CW_SETUP_R(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -1993,7 +2040,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const r
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
 __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
-    CW_ENTER(D.nEdges)
+    CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
@@ -2008,6 +2055,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
     CW_SETUP(D.nCells)
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
     const b2 k_lt_nl = lv.lt(nl);
+    if (D.bdyMaskCell[i] > 2) return;                  // TI:4709 `bdyMaskCell <= nSpecZone`: these cells are set after the transport
     if (i >= D.nCellsSolve) { ST(out, i, sel(k_lt_nl, max0(LD(out, i)), 0.0)); return; }       // warp-uniform
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
@@ -2038,7 +2086,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
 #define MB_CELL_FT 4
 #endif
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FW) k2_dt_cell_fw(const Dev D, const DynTendArgs A) {     // tend_w, TI:5713-5757, 5838-5945
-    CW_SETUP(D.nCellsSolve)
+    CW_SETUP_R(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -2088,7 +2136,7 @@ __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FW) k2_dt_cell_fw(const De
     ST(D.tend_w, i, sel(k_ge1 && k_lt_nl, tw + twe, 0.0));
 }
 __global__ void __launch_bounds__(CW_THREADS, MB_CELL_FT) k2_dt_cell_ft(const Dev D, const DynTendArgs A) {     // tend_theta, TI:5956-6016, 6066-6126, 6134-6197
-    CW_SETUP(D.nCellsSolve)
+    CW_SETUP_R(D.nCellsSolve)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];

@@ -158,7 +158,7 @@ __global__ void k_zb_flags(const Dev D) {
 // 16-byte element pairs.  op 0: d = s;  1: d = s + d;  2: d = s, then s = d * scale;  3: d = s + d, then s = d * scale.
 #define SEG_MAX 16
 struct Seg { real* d; real* s; unsigned n2; int op; };        // n2 = number of 16-byte pairs (LDK is even)
-struct SegList { Seg seg[SEG_MAX]; real scale; int rev; };      // rev: sweep each segment from its end (Dev::rev)
+struct SegList { Seg seg[SEG_MAX]; real scale; };
 #define SEG_BLOCKS 296                                        // blocks per segment: 2 per SM
 __global__ void __launch_bounds__(256) k_segments(const SegList L) {
     PDL_ENTER
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_segments(const SegList L) {
     v2* __restrict__ d = reinterpret_cast<v2*>(g.d);
     v2* __restrict__ s = reinterpret_cast<v2*>(g.s);
     const unsigned stride = gridDim.x * blockDim.x;
-#define SEG_AT(t) (L.rev ? g.n2 - 1u - (t) : (t))
+#define SEG_AT(t) (t)
     if (g.op == 0) {
         for (unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < g.n2; t0 += stride) { const unsigned t = SEG_AT(t0); d[t] = s[t]; }
     } else if (g.op == 1) {

@@ -12,7 +12,7 @@
 
 // column-warp version: one warp per cell, lane l owns the level pair (2l, 2l+1)
 __global__ void __launch_bounds__(CW_THREADS) k2_reconstruct(const Dev D, const real* u, int ncells, int on_a_sphere) {
-    CW_SETUP(ncells)
+    CW_SETUP_R(ncells)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const unsigned slot = (unsigned)i * D.maxEdges + le;

@@ -61,7 +61,6 @@ struct mpasb_handle_s {
     real lbc_dt_end = 0.0;         // regional runs: seconds from the start of the next step to the end of the LBC interval
     bool fuse_dd = true;           // MPASB_NO_DD_FUSE=1: always run the damping as its own kernel
     bool pdl = true;               // MPASB_PDL=0: no programmatic dependent launch
-    bool snake = true;             // MPASB_SNAKE=0: every kernel sweeps its columns forward (Dev::rev)
     int* d_dd_edges = nullptr; unsigned char* d_dd_done = nullptr; int n_dd_edges = 0; bool dd_lists_ok = false, dd_partial = false;   // build_dd_lists
     int* d_ac_bnd = nullptr; int* d_ac_int = nullptr; int n_ac_bnd = 0, n_ac_int = 0; bool ac_lists_ok = false;   // build_acoustic_lists
     bool profile = false;
@@ -151,7 +150,6 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     h->relaxed = !mpasb_strict_arithmetic();
     h->fuse_dd = !getenv("MPASB_NO_DD_FUSE");
     if (const char* e = getenv("MPASB_PDL")) h->pdl = atoi(e) != 0;
-    if (const char* e = getenv("MPASB_SNAKE")) h->snake = atoi(e) != 0;
     memset(&h->D, 0, sizeof(Dev));
     h->D.pf_next = 1;
     if (const char* pf = getenv("MPASB_PF_NEXT")) h->D.pf_next = atoi(pf);
@@ -458,8 +456,10 @@ extern "C" int mpasb_set_field_int(mpasb_handle h, const char* name, const int* 
     if (!strcmp(name, "nEdgesOnCell")) {
         h->max_ne = 0;
         for (long n = 0; n < count; n++) h->max_ne = std::max(h->max_ne, src[n]);
-        h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS") &&
-                     !h->cfg.config_apply_lbcs;       // the bdyMask / specZoneMask branches of a regional run live in the generic family
+        // regional runs: the column-warp kernels carry the bdyMask / specZoneMask branches except the block-tiled column solve of
+        // the strict path, so a strict regional handle (the bit-exact cross-check) stays on the generic family
+        const bool regional_ok = !h->cfg.config_apply_lbcs || (h->relaxed && !getenv("MPASB_NO_SCAN"));
+        h->colwarp = h->D.LDK <= 64 && h->max_ne <= CW_MAXNE && h->dims.maxEdges >= CW_NE && !getenv("MPASB_GENERIC_KERNELS") && regional_ok;
     }
     if (!strcmp(name, "advCellsForEdge")) { h->hc_advCells.assign(src, src + count); h->tiles_dirty = true; }
     if (!strcmp(name, "nAdvCellsForEdge")) { h->hc_nAdv.assign(src, src + count); h->tiles_dirty = true; }
@@ -517,7 +517,6 @@ struct KScope {
 // blocks may become resident while the previous kernel of the stream drains (mpasb_dev.cuh); MPASB_PDL=0 launches them plainly.
 template <typename... P, typename... A>
 static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
-    if (h->snake) h->D.rev ^= 1;          // alternate the sweep direction (the Dev argument is a reference to h->D: copied below)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute at;
@@ -542,7 +541,6 @@ struct SegBuilder {       // collects the column ranges of one routine into one 
     void flush() {
         if (!n) return;
         KScope ks_(h, "k:k_segments");
-        L.rev = h->snake ? !h->D.rev : 0;          // the direction klaunch is about to switch to
         klaunch(h, k_segments, dim3(SEG_BLOCKS, n), dim3(256), 0, L);
         h->launches++; n = 0;
     }
@@ -926,12 +924,18 @@ static int advance_acoustic_step(H* h, real dts, int small_step, const char* gro
             if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
             static const int variant = getenv("MPASB_AC6") ? atoi(getenv("MPASB_AC6")) : 1;
             KScope ks_(h, "k:k6_acoustic_cell");
-#define AC6_LAUNCH(W, MB, LIST, N) do { const unsigned need = (unsigned)(((N) + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
-                klaunch(h, k6_acoustic_cell<W, MB>, dim3(std::max(1u, std::min(need, resident))), dim3((W) * 32), 0, h->D, dts, small_step, epssm, resm, (const int*)(LIST), (int)(N)); \
+#define AC6_LAUNCH(W, MB, LISTED, REG, LIST, N) do { const unsigned need = (unsigned)(((N) + (W) - 1) / (W)), resident = (unsigned)(sm_count * (MB)); \
+                klaunch(h, k6_acoustic_cell<W, MB, LISTED, REG>, dim3(std::max(1u, std::min(need, resident))), dim3((W) * 32), 0, h->D, dts, small_step, epssm, resm, (const int*)(LIST), (int)(N)); \
                 h->launches++; } while (0)
-#define AC6_RUN(LIST, N) do { if (variant == 0) AC6_LAUNCH(8, 2, LIST, N);      /* 128 registers, 16 warps per SM */ \
-                              else if (variant == 2) AC6_LAUNCH(4, 4, LIST, N); /* 128 registers, 16 warps per SM in smaller blocks */ \
-                              else AC6_LAUNCH(4, 3, LIST, N); } while (0)       /* 168 registers, 12 warps per SM */
+            const bool regional = h->D.apply_lbcs != 0;
+            // the plain kernel in three register / occupancy variants; the listed and the regional forms as (4, 3) only
+#define AC6_RUN(LIST, N) do { const bool listed = (LIST) != nullptr; \
+                              if (listed && regional) AC6_LAUNCH(4, 3, true, true, LIST, N); \
+                              else if (listed) AC6_LAUNCH(4, 3, true, false, LIST, N); \
+                              else if (regional) AC6_LAUNCH(4, 3, false, true, LIST, N); \
+                              else if (variant == 0) AC6_LAUNCH(8, 2, false, false, LIST, N);      /* 128 registers, 16 warps per SM */ \
+                              else if (variant == 2) AC6_LAUNCH(4, 4, false, false, LIST, N); /* 128 registers, 16 warps per SM in smaller blocks */ \
+                              else AC6_LAUNCH(4, 3, false, false, LIST, N); } while (0)       /* 168 registers, 12 warps per SM */
             // opt-in (MPASB_SPLIT=1): measured on 4 B200 it does not pay -- 13.73 / 13.85 ms per step against 13.60 ms with the
             // exchange simply following the kernel: the two launches lose more (a scattered boundary launch, two tails) than
             // the ~20 us of exchange they hide (profiles/r2_bench_t_4gpu_*)
@@ -944,7 +948,7 @@ static int advance_acoustic_step(H* h, real dts, int small_step, const char* gro
                 AC6_RUN(h->d_ac_int, h->n_ac_int);
                 return 0;
             }
-            AC6_RUN(nullptr, h->D.nCells);
+            AC6_RUN((const int*)nullptr, h->D.nCells);
 #undef AC6_RUN
 #undef AC6_LAUNCH
             return group ? exchange(h, group) : 0;

@@ -23,8 +23,13 @@ typedef double real;
 // do that (its blocks take the SM slots this kernel's last wave vacates); pdl_wait() returns once the predecessor grid has
 // completed and its writes are visible.  Everything before pdl_wait() may only touch data no kernel of the step writes (mesh
 // connectivity, weights); launched without the attribute both are no-ops.
+#ifdef MPASB_EXPERIMENT_NOPDL
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 #define PDL_ENTER pdl_trigger(); pdl_wait();
 
 enum { LOC_CELL = 0, LOC_EDGE = 1, LOC_VERTEX = 2, LOC_LEVS = 3 };
@@ -48,9 +53,6 @@ struct Dev {
     // derived, library-internal: 1 where any zb_cell/zb3_cell entry of the cell is non-zero (terrain slope);
     // cells with 0 skip the 2 x maxEdges x nVertLevels metric reads of TI:2480-2500 and TI:3379-3414
     int* zb_any;
-    int rev;           // sweep direction of this launch: 1 = columns from the last to the first.  The host alternates it from launch
-                       // to launch, so a kernel starts where its predecessor just finished and finds that part of the
-                       // predecessor's inputs and outputs still in the 126 MB L2 (MPASB_SNAKE=0: always forward)
     int pf_next;       // the persistent kernels (k6_acoustic_cell, k7_dt_cell_f) ask L2 for the own-column operands of their next cell (MPASB_PF_NEXT=0: off)
     // per-edge 3rd/4th-order advective fluxes of w and theta_m (kernels_col.cuh: k2_dt_edge_flux -> k2_dt_cell_f)
     real* adv_flux_w; real* adv_flux_theta;

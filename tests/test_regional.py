@@ -78,16 +78,21 @@ def _differing(a, b):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["strict", "relaxed"])
 @pytest.mark.parametrize("variant", ["default", "coupled_transport_order3"])
-def test_every_regional_routine_bit_identical_to_the_reference_source(regional_case, variant):
-    """GPU library against oracle/_ref routine by routine on identical inputs, every field, bit for bit -- except the
-    stage-3 pow() of recover_large_step_variables (<= 1e-13, as in the global case)."""
+def test_every_regional_routine_against_the_reference_source(regional_case, variant, mode, monkeypatch):
+    """GPU library against oracle/_ref routine by routine on identical inputs, every field.  MPASB_STRICT=1 (a regional handle
+    then runs the generic kernel family): bit for bit, except the stage-3 pow() of recover_large_step_variables (<= 1e-13, as
+    in the global case).  Default mode (column-warp kernels with the mask branches, relaxed arithmetic): the per-routine bars of
+    tests/test_parity_gpu.py, and every atm_bdy_* routine still bit for bit."""
     from mpas_model_b200.dycore import Dycore
     d, cfg, t_end = regional_case
     if variant != "default":
         cfg = dict(cfg, config_split_dynamics_transport=False, config_time_integration_order=3, config_number_of_sub_steps=4)
     dt = cfg["config_dt"]
+    monkeypatch.setenv("MPASB_STRICT", "1" if mode == "strict" else "0")
     g, r = Dycore(d, cfg), ref.RefDycore(d, cfg)
+    assert g.strict_arithmetic() == (mode == "strict")
     for b in (g, r):
         b.set_lbc_time(t_end)
         b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
@@ -96,13 +101,15 @@ def test_every_regional_routine_bit_identical_to_the_reference_source(regional_c
 
     def after(label):
         bad = _differing(r, g)
-        if label.startswith("recover_large_step_variables") and label.endswith("3)"):
+        uses_pow = label.startswith("recover_large_step_variables") and label.endswith("3)")
+        if mode == "strict" and not uses_pow or label.startswith("lbc_"):
+            assert bad == [], (label, bad)
+        else:
             for f in bad:
                 n, lev = f.split("@")
                 a, b = g.get_array(n, int(lev)), r.get_array(n, int(lev))
-                assert np.linalg.norm((a - b).ravel()) <= 1e-13 * np.linalg.norm(b.ravel()), (label, f)
-        else:
-            assert bad == [], (label, bad)
+                tol = 1e-13 if mode == "strict" else (5e-10 if n == "rthdynten" else 2e-11)
+                assert np.linalg.norm((a - b).ravel()) <= tol * np.linalg.norm(b.ravel()), (label, f)
         labels.append(label)
         sync_all(r, g)
 
