@@ -917,7 +917,6 @@ __global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev 
 #define LDZ(p, E) ld2((p), ((unsigned)i * (unsigned)D.maxEdges + (unsigned)(E)) * uLDK + kc)
 __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev D) {
     CW_ENTER(D.nCellsSolve)
-    if (D.bdyMaskCell[i] > 5) return;                  // regional run: no conversion in the specified zone, TI:2482 (static mask)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -943,13 +942,15 @@ __global__ void __launch_bounds__(CW_THREADS, MB_SML) k2_smlstep_pert(const Dev 
         for (int e = CW_NE; e < ne; e++) SML_EDGE(e)
 #undef SML_EDGE
     }
-    ST(D.tend_w, i, sel(lv.ge(1) && lv.lt(nl), (fm * zz + fp * up1(zz)) * wt, wt_in));
+    // regional run: no conversion in the specified zone, TI:2482.  Only the store is predicated, with the (static, cache-resident)
+    // mask read last: an early exit puts the mask load in front of every other load of the kernel (one more exposed memory
+    // round trip, measured +5 %), a flag read first and kept costs the register-capped kernel another spill
+    st2(D.tend_w, (unsigned)i * uLDK + kc, act && D.bdyMaskCell[i] <= 5, sel(lv.ge(1) && lv.lt(nl), (fm * zz + fp * up1(zz)) * wt, wt_in));
 }
 
 // ------------------------------------------------------------------ atm_recover_large_step_variables_work, part 3  TI:3379-3416
 __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const Dev D, real cf1, real cf2, real cf3) {
     CW_ENTER(D.nCells)
-    if (D.bdyMaskCell[i] > 5) return;                  // regional run: no update in the specified zone, TI:3385 (static mask)
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
@@ -977,7 +978,8 @@ __global__ void __launch_bounds__(CW_THREADS, MB_REC2) k2_recover_cell2(const De
 #undef REC_EDGE
     }
     const r2 den = sel(k_eq0, cf1 * rho + cf2 * dn1(rho) + cf3 * dn2(rho), fm * rho + fp * up1(rho));
-    ST(D.w_2, i, sel(lv.lt(nl), w / den, w_in));
+    // regional run: no update in the specified zone, TI:3385 (store predicated, mask read last: see k2_smlstep_pert)
+    st2(D.w_2, (unsigned)i * uLDK + kc, act && D.bdyMaskCell[i] <= 5, sel(lv.lt(nl), w / den, w_in));
 }
 
 // ------------------------------------------------------------------ atm_compute_solve_diagnostics_work  TI:6337-6773
