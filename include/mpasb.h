@@ -123,6 +123,26 @@ int  mpasb_init_coupled_diagnostics(mpasb_handle h);
 int  mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt);
 int  mpasb_init_solve_diagnostics_async(mpasb_handle h, mpasb_real dt);   /* enqueued only: no host synchronisation */
 
+/* The mesh part of atm_mpas_init_block (mpas_atm_core.F:368-602): atm_compute_signs (:1151-1238), the inverses (:456-470),
+ * atm_adv_coef_compression (:1285-1430), atm_couple_coef_3rd_order (:1433-1452), atm_compute_mesh_scaling (:1091-1148) and
+ * atm_compute_damping_coefs (:1241-1282), computed by the library (C++, host) from the raw mesh fields of an init file, so
+ * that a run can start with nothing derived on the caller's side.
+ * Inputs, by name, in the layout a Fortran caller holds (dense, 1-based connectivity, garbage slot n+1):
+ *   int : nEdgesOnCell, edgesOnCell, cellsOnCell, verticesOnCell, cellsOnEdge, verticesOnEdge, edgesOnVertex, cellsOnVertex
+ *   real: zb, zb3 (nVertLevels+1, 2, nEdges+1), deriv_two (15, 2, nEdges+1), dcEdge, dvEdge, areaCell, areaTriangle,
+ *         meshDensity, zgrid
+ * Derived: edgesOnVertex_sign, edgesOnCell_sign, zb_cell, zb3_cell, kiteForCell, invAreaCell, invDvEdge, invDcEdge,
+ * invAreaTriangle, nAdvCellsForEdge, advCellsForEdge, adv_coefs, adv_coefs_3rd, meshScalingDel2, meshScalingDel4,
+ * meshScalingRegionalCell, meshScalingRegionalEdge, dss (shapes: include/mpasb_fields.def).
+ * mpasb_init_block stores them in the handle (as mpasb_set_field / mpasb_set_field_int would); mpasb_init_block_host is the
+ * same computation without a handle or a device, written to the caller's arrays.  The three namelist values are the ones
+ * only this routine reads (Registry.xml:177, 261, 266).  Returns 1 when a named input / output is missing or unknown. */
+int  mpasb_init_block(mpasb_handle h, int config_h_ScaleWithMesh, double config_zd, double config_xnutr,
+                      int n_in, const char* const* in_names, const void* const* in_arrays);
+int  mpasb_init_block_host(const mpasb_dims* dims, const mpasb_config* cfg, int config_h_ScaleWithMesh, double config_zd, double config_xnutr,
+                           int n_in, const char* const* in_names, const void* const* in_arrays,
+                           int n_out, const char* const* out_names, void* const* out_arrays);
+
 /* mpas_reconstruct (src/operators/mpas_vector_reconstruction.F:205-330): uReconstructX/Y/Z/Zonal/Meridional from u of
  * the given time level through the init-time field coeffs_reconstruct; mpasb_step already ends with the call of
  * TI:1606 (time level 2, owned cells), mpas_atm_core.F:543 is (1, 0) at start-up.

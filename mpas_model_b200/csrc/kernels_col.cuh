@@ -24,8 +24,13 @@
 #include "kernels_dyn.cuh"
 
 #define CW_FULL 0xffffffffu
+#ifndef CW_WARPS
 #define CW_WARPS 8                      // warps (= columns) per block
+#endif
 #define CW_THREADS (CW_WARPS * 32)
+#ifndef EB_WARPS
+#define EB_WARPS CW_WARPS               // ... of the edge tendency kernel
+#endif
 
 // resident blocks per SM each kernel's register allocation aims for (1 = no constraint); tuned on B200, DESIGN.md §4
 #ifndef MB_EDGE_B
@@ -127,14 +132,14 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
 #define CW_ENTER_R(ncols) pdl_trigger(); CW_SETUP_NW_R(ncols)
 #define CW_SETUP_NW_R(ncols)                                                                  \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
-    const int i = (ncols) - 1 - (int)(blockIdx.x * CW_WARPS + wib);                           \
+    const int i = (ncols) - 1 - (int)(blockIdx.x * (blockDim.x >> 5) + wib);                           \
     const int LDK = D.LDK, nl = D.nl;                                                         \
     if (i < 0) return;                                                                        \
     CW_SETUP_REST
 // ... without the wait: the kernel places pdl_wait() itself, below its loads of static mesh data
 #define CW_SETUP_NW(ncols)                                                                    \
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                                \
-    const int i = blockIdx.x * CW_WARPS + wib;                                                \
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;                                       \
     const int LDK = D.LDK, nl = D.nl;                                                         \
     if (i >= (ncols)) return;                                                                 \
     CW_SETUP_REST
@@ -148,6 +153,30 @@ __device__ __forceinline__ r2 flux3_2(r2 q_im2, r2 q_im1, r2 q_i, r2 q_ip1, r2 u
 // request a column pair into L2 without holding registers: used for operands of a later, dependent phase
 __device__ __forceinline__ void pf2(const real* p, unsigned off) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p + off)); }
 #define PF(p, col) pf2((p), (unsigned)(col) * uLDK + kc)
+
+
+// Persistent-warp schedules.  Default: warp g walks columns g, g + G, ... (the whole grid sweeps one window of G columns).
+// MPASB_PERS_CHUNK: the R blocks b, b + NS, b + 2 NS, ... (NS = gridDim / R; the block scheduler deals consecutive blocks round
+// robin over the SMs, so these R are the ones resident together on one SM) share ONE contiguous range of columns and walk it
+// side by side, R*W consecutive columns per trip: the columns a SM gathers at any time are neighbours on the mesh (Morton
+// order), so what one warp pulled into L1 the next ones find there.  Results do not depend on the schedule.
+struct Pers { int j, end, stride; };
+template <int W, int R>
+__device__ __forceinline__ Pers pers_init(int n, int wib) {
+    Pers p;
+#ifdef MPASB_PERS_CHUNK
+    const int nb = (int)gridDim.x;
+    const bool grp = R > 1 && nb % R == 0;
+    const int NS = grp ? nb / R : nb, r = grp ? (int)blockIdx.x / NS : 0, s = grp ? (int)blockIdx.x % NS : (int)blockIdx.x;
+    const int L = (n + NS - 1) / NS;
+    p.stride = (grp ? R : 1) * W;
+    p.end = min(n, (s + 1) * L);
+    p.j = s * L + r * W + wib;
+#else
+    p.j = (int)blockIdx.x * W + wib; p.end = n; p.stride = (int)gridDim.x * W;
+#endif
+    return p;
+}
 
 // ------------------------------------------------------------------ atm_compute_dyn_tend_work, part (f)
 // The reference computes the 3rd/4th-order horizontal flux of w and theta_m inside the cell loop, i.e. every
@@ -329,8 +358,19 @@ __global__ void __launch_bounds__(CW_THREADS, EF_MINB) k4_dt_edge_flux(const Dev
 #define FX_MINB 2
 #endif
 __device__ __forceinline__ r2 fma2(real a, r2 q, r2 acc) { return mk2(fma(a, q.x, acc.x), fma(a, q.y, acc.y)); }
+#ifndef FX_TMA
+#define FX_TMA 1                        // 0: the weight row travels through registers (measured the same: 0.977 vs 0.966-0.982 ms/step)
+#endif
+// FX_TMA: the cell's weight row (FX_WTS reals, one contiguous 1 KB slab of D.fx_w) is not carried through registers but fetched
+// by one bulk-asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier; SASS UBLKCP / SYNCS) issued by lane 0
+// one cell AHEAD into the other half of a double buffer, so it costs the warp neither registers nor LSU issue slots.
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev D) {
+#if FX_TMA
+    __shared__ __align__(128) real s_wts2[FX_WARPS][2][FX_WTS];
+    __shared__ __align__(8) unsigned long long s_bar[FX_WARPS][2];
+#else
     __shared__ __align__(16) real s_wts[FX_WARPS][FX_WTS];
+#endif
     pdl_trigger();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int LDK = D.LDK, nl = D.nl;
@@ -342,28 +382,49 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
     // Persistent warps: warp g handles cells g, g + G, g + 2G, ...  The kernel is latency bound (two dependent memory round
     // trips per cell: neighbourhood table -> columns), so the table row, the edge ids and the signs of the NEXT cell are
     // fetched while the current cell's columns are in flight: one exposed round trip per cell instead of two.
-    const int G = gridDim.x * FX_WARPS;
     const int le = min(lane, 5), lr = min(lane, FX_RING - 1);
-    const int nSolve = D.nCellsSolve;
+    const Pers ps = pers_init<FX_WARPS, FX_MINB>(D.nCellsSolve, wib);
+    const int G = ps.stride, nSolve = ps.end;
 #define FX_COL(j) (j)                                         /* forward sweep (see CW_SETUP_R) */
-    int j = blockIdx.x * FX_WARPS + wib;
+    int j = ps.j;
     int my_ring = 0, my_e = 0; real my_sgn = 0.0;
+#if FX_TMA
+    const unsigned bar0 = smem_u32(&s_bar[wib][0]), buf0 = smem_u32(&s_wts2[wib][0][0]);
+    unsigned trip = 0;                                   // buffer = trip & 1, mbarrier phase = (trip >> 1) & 1
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    __syncwarp();
+#endif
     if (j < nSolve) {
         const int i = FX_COL(j);
         my_ring = D.fx_ring[(unsigned)i * FX_RING + lr];
         my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
         my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
+#if FX_TMA
+        if (lane == 0) { mbar_expect_tx(bar0, FX_WTS * sizeof(real)); bulk_g2s(buf0, D.fx_w + (size_t)i * FX_WTS, FX_WTS * sizeof(real), bar0); }
+#endif
     }
     pdl_wait();                                          // everything above is static mesh data
     for (; j < nSolve; j += G) {
     const int i = FX_COL(j);
     const int regular = BC(my_ring, 18);
     r2 tw = mk2(0.0, 0.0), tt = mk2(0.0, 0.0);
-    const int inext = j + G < nSolve ? FX_COL(j + G) : nSolve;
+    const int inext = j + G < nSolve ? FX_COL(j + G) : D.nCellsSolve;
     int nx_ring = 0, nx_e = 0; real nx_sgn = 0.0;
+#if FX_TMA
+    const unsigned cur = trip & 1u, ph = (trip >> 1) & 1u;
+    trip++;
+    __syncwarp();                                        // every lane is done with the other buffer (read two trips ago ... one trip ago)
+    if (inext < D.nCellsSolve && lane == 0) {            // next cell's weights into the other buffer
+        const unsigned nb = bar0 + 8u * (cur ^ 1u);
+        mbar_expect_tx(nb, FX_WTS * sizeof(real));
+        bulk_g2s(buf0 + (cur ^ 1u) * (unsigned)(FX_WTS * sizeof(real)), D.fx_w + (size_t)inext * FX_WTS, FX_WTS * sizeof(real), nb);
+    }
+#endif
     if (regular) {
+#if !FX_TMA
         const real* __restrict__ wsrc = D.fx_w + (size_t)i * FX_WTS + 4 * lane;
         const r2 wts_a = *reinterpret_cast<const r2*>(wsrc), wts_b = *reinterpret_cast<const r2*>(wsrc + 2);
+#endif
         // all 19 columns of both fields and the 6 edge columns are requested before any of them is used
         const r2 wc = LD(D.w_2, i), tc = LD(D.theta_m_2, i);
         r2 wn[6], tn[6], wm[12], tm[12], ru6[6];
@@ -378,10 +439,15 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
             nx_e = D.edgesOnCell[(unsigned)inext * D.maxEdges + le];
             nx_sgn = D.edgesOnCell_sign[(unsigned)inext * D.maxEdges + le];
         }
+#if FX_TMA
+        mbar_wait(bar0 + 8u * cur, ph);                  // this cell's weights have landed (requested one trip ago)
+        const real* __restrict__ W = s_wts2[wib][cur];
+#else
         __syncwarp();                                    // the previous cell's reads of s_wts are done
         *reinterpret_cast<r2*>(&s_wts[wib][4 * lane]) = wts_a; *reinterpret_cast<r2*>(&s_wts[wib][4 * lane + 2]) = wts_b;
         __syncwarp();
         const real* __restrict__ W = s_wts[wib];
+#endif
 #pragma unroll
         for (int e = 0; e < 6; e++) {
             const r2 wa = wm[(2 * e + 11) % 12], ta = tm[(2 * e + 11) % 12], wb = wm[2 * e], tb = tm[2 * e],
@@ -408,6 +474,9 @@ __global__ void __launch_bounds__(FX_WARPS * 32, FX_MINB) k5_flux_cell(const Dev
             tt = tt - sg * fxt;
         }
     } else {
+#if FX_TMA
+        mbar_wait(bar0 + 8u * cur, ph);                  // (unused here, but every fill is waited for before its barrier is re-armed)
+#endif
         if (inext < D.nCellsSolve) {
             nx_ring = D.fx_ring[(unsigned)inext * FX_RING + lr];
             nx_e = D.edgesOnCell[(unsigned)inext * D.maxEdges + le];
@@ -693,10 +762,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k7_dt_cell_f(const Dev D, co
     const b2 k_ge1 = lv.ge(1), k_lt_nl = lv.lt(nl);
     const b2 kk_edge = lv.eq(1) || lv.eq(nl - 1);            // 2nd-order interfaces
     const b2 kk_zero = lv.lt(1) || lv.ge(nl);                // no flux through the boundaries
-    const int G = gridDim.x * WARPS;
-    const int nSolve = D.nCellsSolve;
-#define CF7_COL(j) (nSolve - 1 - (j))                         /* backward sweep (see CW_SETUP_R) */
-    int jcol = blockIdx.x * WARPS + wib;
+    const Pers ps = pers_init<WARPS, MINB>(D.nCellsSolve, wib);
+    const int G = ps.stride, nSolve = ps.end;
+#define CF7_COL(j) (D.nCellsSolve - 1 - (j))                  /* backward sweep (see CW_SETUP_R) */
+    int jcol = ps.j;
     CfConn cn; cn.ne = 1; cn.e = 0; cn.c1 = 0; cn.c2 = 0; cn.sgn = 0.0; cn.dv = 0.0; cn.d4 = 0.0; cn.idc = 0.0; cn.invArea = 0.0;
     if (jcol < nSolve) cn = cf_conn(D, CF7_COL(jcol), lane, rk1);
     pdl_wait();                                          // everything above is static mesh data
@@ -845,7 +914,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) k8_coriolis_cell(const Dev D) {
 // COR: the nonlinear Coriolis sum arrives as two partial sums, one from each adjacent cell (k8_coriolis_cell, relaxed
 // arithmetic), instead of being gathered here over edgesOnEdge
 template <bool COR>
-__global__ void __launch_bounds__(CW_THREADS, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
+__global__ void __launch_bounds__(EB_WARPS * 32, MB_EDGE_B) k2_dt_edge_b(const Dev D, const DynTendArgs A) {
     CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const bool solve = i < D.nEdgesSolve;
@@ -1423,11 +1492,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
     const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
     // persistent warps (warp g: cells g, g + G, ...): the connectivity of the NEXT cell -- a chain of two dependent index
     // loads -- is fetched while this cell's columns are in flight, so each cell exposes one memory round trip, not three
-    const int G = gridDim.x * WARPS;
-    const int nAll = LISTED ? nlist : D.nCells;
-#define AC6_POS(j) (nAll - 1 - (j))                           /* backward sweep (see CW_SETUP_R) */
+    const int nTot = LISTED ? nlist : D.nCells;
+    const Pers ps = pers_init<WARPS, MINB>(nTot, wib);
+    const int G = ps.stride, nAll = ps.end;
+#define AC6_POS(j) (nTot - 1 - (j))                           /* backward sweep (see CW_SETUP_R) */
 #define AC6_COL(j) (LISTED ? list[AC6_POS(j)] : AC6_POS(j))
-    int jcol = blockIdx.x * WARPS + wib;
+    int jcol = ps.j;
     Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
     if (jcol < nAll && AC6_COL(jcol) < D.nCellsSolve) cn = ac6_conn(D, AC6_COL(jcol), lane, dts);
     pdl_wait();                                          // everything above is static mesh data
@@ -1563,6 +1633,208 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k6_acoustic_cell(const Dev D
 #undef AC6_POS
 }
 
+// ---- the same column solve with its OWN-COLUMN operands staged by bulk-asynchronous copies (TMA) ----
+// k6_acoustic_cell reads 21 of its 33 columns from the cell's own column; a block of W warps that takes W consecutive cells per
+// trip therefore needs, per field, ONE contiguous slab of W columns (W * LDK reals).  Here warp 0 requests the slabs of the NEXT
+// trip -- one cp.async.bulk (SASS UBLKCP) per field, each issued by its own lane, all completing on one mbarrier -- into the
+// other half of a double buffer while the block works on the current trip, and the warps read their operands from shared
+// memory at the point of use: a whole trip of prefetch distance (the kernel is bound by memory latency at 12 warps per SM, not
+// by bytes), no registers held by loads in flight, no LSU issue slots for 20 of the 33 columns.  Gathers of neighbour columns
+// (theta_m of the <= 6 neighbours, ru_p of the <= 6 edges) and the cell's own theta_m stay LDG.128.
+// Protocol: full[s] (1 arrival + transaction bytes) is waited for by every warp before its first read of stage s; empty[s]
+// (W arrivals, one per warp after its last read) is waited for by warp 0 before it refills stage s.  Trips are block-uniform.
+// Arithmetic and results are those of k6_acoustic_cell.  Not for listed or regional runs (k6 serves those).
+#ifndef AC9_MINB
+#define AC9_MINB 3
+#endif
+#ifndef AC9_WARPS
+#define AC9_WARPS 4
+#endif
+#ifndef AC9_DEFAULT
+#define AC9_DEFAULT 0                   // MPASB_AC9=1 selects it at run time
+#endif
+enum { A9_rtheta_pp, A9_rw_p, A9_rho_pp, A9_wwAvg,        // the first four are not read on the first small step
+       A9_tend_rho, A9_tend_theta, A9_tend_w, A9_coftz, A9_cofwz, A9_cofwr, A9_cofwt, A9_zz, A9_a_tri, A9_alpha_tri, A9_gamma_tri,
+       A9_dss, A9_rw_save, A9_rw, A9_rho_zz_2, A9_w_2, AC9_NF };
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k9_acoustic_cell(const Dev D, real dts, int small_step, real epssm, real resm) {
+    extern __shared__ __align__(128) unsigned char a9_raw[];          // [2 stages][AC9_NF fields][WARPS columns][LDK]
+    __shared__ __align__(8) unsigned long long a9_bar[4];             // full[0], full[1], empty[0], empty[1]
+    __shared__ const real* a9_src[AC9_NF];
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int LDK = D.LDK, nl = D.nl;
+    Lv lv; lv.k0 = 2 * lane;
+    const int k0 = lv.k0; const bool act = k0 < D.LDKA;
+    const unsigned uLDK = (unsigned)LDK, kc = (unsigned)min(k0, D.LDKA - 2);
+    const bool first = small_step == 1;
+    const b2 k_lt_nl = lv.lt(nl), k_le_nl = lv.lt(nl + 1), k_mid = lv.ge(1) && lv.lt(nl);
+    const r2 rdzw = LD(D.rdzw, 0);
+    const r2 fm = LD(D.fzm, 0), fp = LD(D.fzp, 0);
+    const unsigned colB = uLDK * (unsigned)sizeof(real), fieldB = WARPS * colB, stageB = AC9_NF * fieldB;
+    const unsigned bar = smem_u32(a9_bar), raw = smem_u32(a9_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1); mbar_init(bar + 8, 1); mbar_init(bar + 16, WARPS); mbar_init(bar + 24, WARPS);
+        a9_src[A9_rtheta_pp] = D.rtheta_pp; a9_src[A9_rw_p] = D.rw_p; a9_src[A9_rho_pp] = D.rho_pp; a9_src[A9_wwAvg] = D.wwAvg;
+        a9_src[A9_tend_rho] = D.tend_rho; a9_src[A9_tend_theta] = D.tend_theta; a9_src[A9_tend_w] = D.tend_w;
+        a9_src[A9_coftz] = D.coftz; a9_src[A9_cofwz] = D.cofwz; a9_src[A9_cofwr] = D.cofwr; a9_src[A9_cofwt] = D.cofwt;
+        a9_src[A9_zz] = D.zz; a9_src[A9_a_tri] = D.a_tri; a9_src[A9_alpha_tri] = D.alpha_tri; a9_src[A9_gamma_tri] = D.gamma_tri;
+        a9_src[A9_dss] = D.dss; a9_src[A9_rw_save] = D.rw_save; a9_src[A9_rw] = D.rw; a9_src[A9_rho_zz_2] = D.rho_zz_2; a9_src[A9_w_2] = D.w_2;
+    }
+    __syncthreads();
+    // trip t of this block: group g = blockIdx + t * gridDim of W consecutive columns [lo, hi), walked from the last column down
+    // (backward sweep, see CW_SETUP_R); warp wib takes column hi - 1 - wib
+    const int nAll = D.nCells, nG = (nAll + WARPS - 1) / WARPS, NB = (int)gridDim.x;
+    const int f0 = first ? 4 : 0;
+    // request the slabs of group g into stage s (warp 0 only; lane f copies field f)
+#define AC9_FILL(g, s)                                                                                           \
+    {                                                                                                             \
+        const int hi_ = nAll - (g) * WARPS, lo_ = max(0, hi_ - WARPS);                                            \
+        const unsigned bytes_ = (unsigned)(hi_ - lo_) * colB;                                                     \
+        if (lane == 0) mbar_expect_tx(bar + 8u * (s), (unsigned)(AC9_NF - f0) * bytes_);                          \
+        __syncwarp();                                                                                             \
+        if (lane >= f0 && lane < AC9_NF)                                                                          \
+            bulk_g2s(raw + (s) * stageB + (unsigned)lane * fieldB, a9_src[lane] + (size_t)lo_ * uLDK, bytes_, bar + 8u * (s)); \
+    }
+    int g = (int)blockIdx.x;
+    Ac6Conn cn; cn.ne = 1; cn.e = 0; cn.oth = 0; cn.is12 = 0; cn.f = 0.0; cn.invArea = 0.0;
+    {
+        const int i0 = nAll - g * WARPS - 1 - wib;
+        if (g < nG && i0 >= 0 && i0 < D.nCellsSolve) cn = ac6_conn(D, i0, lane, dts);
+    }
+    pdl_wait();                                          // everything above is static mesh data
+    const r2 cofrz = LD(D.cofrz, 0);                     // (written by the vertical-coefficient kernel)
+    if (wib == 0 && g < nG) AC9_FILL(g, 0u)
+    for (unsigned t = 0; g < nG; g += NB, t++) {
+        const unsigned s = t & 1u, ph = (t >> 1) & 1u;
+        const int hi = nAll - g * WARPS, lo = max(0, hi - WARPS);
+        const int i = hi - 1 - wib;                       // this warp's column (i < lo: none, in the last group)
+        const int gn = g + NB;
+        const int inext = gn < nG ? nAll - gn * WARPS - 1 - wib : -1;
+        if (wib == 0 && gn < nG) {                       // next trip's slabs into the other stage, once every warp has left it
+            if (t >= 1) { if (lane == 0) mbar_wait(bar + 16 + 8u * (s ^ 1u), ((t - 1) >> 1) & 1u); __syncwarp(); }
+            AC9_FILL(gn, s ^ 1u)
+        }
+        mbar_wait(bar + 8u * s, ph);
+        const unsigned char* st = a9_raw + s * stageB + (unsigned)max(i - lo, 0) * colB + kc * (unsigned)sizeof(real);
+#define S9(F) (*reinterpret_cast<const r2*>(st + (unsigned)(F) * fieldB))
+#define AC9_RELEASE { __syncwarp(); if (lane == 0) mbar_arrive(bar + 16 + 8u * s); }
+        if (i < lo) { AC9_RELEASE continue; }
+        r2 rtheta_pp = mk2(0.0, 0.0), rho_pp = mk2(0.0, 0.0), rw_p = mk2(0.0, 0.0), wwAvg = mk2(0.0, 0.0);
+        if (!first) rtheta_pp = sel(k_lt_nl, S9(A9_rtheta_pp), 0.0);
+        if (i >= D.nCellsSolve) {                                                          // halo cells: TI:2827-2842 only
+            AC9_RELEASE
+            ST(D.rtheta_pp_old, i, rtheta_pp);
+            if (inext >= 0 && inext < D.nCellsSolve) cn = ac6_conn(D, inext, lane, dts);
+            continue;
+        }
+        const int ne = cn.ne;
+        const int my_e = cn.e, my_oth = cn.oth;
+        const bool my_is1 = (cn.is12 & 1) != 0, my_is2 = (cn.is12 & 2) != 0;
+        const real my_f = cn.f, invArea = cn.invArea;
+        const r2 th_own = LD(D.theta_m, i);
+        r2 rs = mk2(0.0, 0.0), ts = mk2(0.0, 0.0);
+#define AC9_EDGE(E)                                                                                         \
+        {                                                                                                   \
+            const int iEdge = BC(my_e, (E));                                                                \
+            const bool is1 = BC(my_is1, (E)), is2 = BC(my_is2, (E));                                        \
+            const r2 th_o = LD(D.theta_m, BC(my_oth, (E)));                                                 \
+            const r2 ru_p = first ? dts * LD(D.tend_u, iEdge) : LD(D.ru_p, iEdge);   /* TI:2798-2806 */     \
+            const r2 flux = BC(my_f, (E)) * ru_p * invArea;                                                 \
+            const r2 th = selb(is2, th_own, th_o) + selb(is1, th_own, th_o);                                \
+            rs = selb((E) < ne, rs - flux, rs);                                                             \
+            ts = selb((E) < ne, ts - flux * 0.5 * th, ts);                                                  \
+        }
+#pragma unroll
+        for (int e = 0; e < CW_NE; e++) AC9_EDGE(e)
+        for (int e = CW_NE; e < ne; e++) AC9_EDGE(e)
+#undef AC9_EDGE
+        if (inext >= 0 && inext < D.nCellsSolve) cn = ac6_conn(D, inext, lane, dts);   // next cell's connectivity, in flight with the gathers
+        if (!first) {
+            rw_p = sel(k_le_nl, S9(A9_rw_p), 0.0);
+            rho_pp = sel(k_lt_nl, S9(A9_rho_pp), 0.0);
+            wwAvg = sel(k_le_nl, S9(A9_wwAvg), 0.0);
+        }
+        const r2 coftz = S9(A9_coftz), zz = S9(A9_zz);
+        const r2 rw_p1 = dn1(rw_p);
+        const r2 coftz1 = dn1(coftz);
+        rs = rho_pp + dts * S9(A9_tend_rho) + rs - cofrz * resm * (rw_p1 - rw_p);
+        ts = rtheta_pp + dts * S9(A9_tend_theta) + ts - resm * rdzw * (coftz1 * rw_p1 - coftz * rw_p);
+        rs = sel(k_lt_nl, rs, 0.0); ts = sel(k_lt_nl, ts, 0.0);
+        const r2 zzm = up1(zz);
+        r2 rhs;
+        {
+            const r2 cofwt = S9(A9_cofwt);
+            const r2 tsm = up1(ts), rsm = up1(rs), rtm = up1(rtheta_pp), rhm = up1(rho_pp), cofwtm = up1(cofwt);
+            const r2 rr = rw_p + dts * S9(A9_tend_w)
+                          - S9(A9_cofwz) * ((zz * ts - zzm * tsm) + resm * (zz * rtheta_pp - zzm * rtm))
+                          - S9(A9_cofwr) * ((rs + rsm) + resm * (rho_pp + rhm))
+                          + cofwt * (ts + resm * rtheta_pp)
+                          + cofwtm * (tsm + resm * rtm);
+            rhs = sel(k_le_nl, sel(k_mid, rr, rw_p), 0.0);
+        }
+        // ---- forward sweep: x_k = alpha_k (rhs_k - a_k x_{k-1}), k = 1 .. nl-1; x_0 = rhs_0, x_nl = rhs_nl
+        r2 x;
+        {
+            const r2 a_tri = S9(A9_a_tri), al_tri = S9(A9_alpha_tri);
+            aff m0, m1;
+            m0.a = k_mid.x ? -(a_tri.x * al_tri.x) : (real)0.0; m0.b = k_mid.x ? rhs.x * al_tri.x : rhs.x;
+            m1.a = k_mid.y ? -(a_tri.y * al_tri.y) : (real)0.0; m1.b = k_mid.y ? rhs.y * al_tri.y : rhs.y;
+            aff m = aff_after(m1, m0);                              // x_{k0-1} -> x_{k0+1}
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                aff p; p.a = __shfl_up_sync(CW_FULL, m.a, d); p.b = __shfl_up_sync(CW_FULL, m.b, d);
+                if (lane >= d) m = aff_after(m, p);
+            }
+            real xprev = __shfl_up_sync(CW_FULL, m.b, 1);           // x_{k0-1}: the previous lane's upper level (lane 0: m0.a == 0)
+            if (lane == 0) xprev = 0.0;
+            x.x = fma(m0.a, xprev, m0.b);
+            x.y = m.b;
+        }
+        // ---- backward sweep: y_k = x_k - gamma_k y_{k+1}, k = nl-1 .. 0; y_nl = x_nl
+        r2 r;
+        {
+            const r2 ga_tri = S9(A9_gamma_tri);
+            aff m0, m1;
+            m0.a = k_lt_nl.x ? -ga_tri.x : (real)0.0; m0.b = x.x;
+            m1.a = k_lt_nl.y ? -ga_tri.y : (real)0.0; m1.b = x.y;
+            aff m = aff_after(m0, m1);                              // y_{k0+2} -> y_{k0}
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                aff p; p.a = __shfl_down_sync(CW_FULL, m.a, d); p.b = __shfl_down_sync(CW_FULL, m.b, d);
+                if (lane + d < 32) m = aff_after(m, p);
+            }
+            real ynext = __shfl_down_sync(CW_FULL, m.b, 1);         // y_{k0+2}
+            if (lane == 31) ynext = 0.0;
+            r.x = m.b;
+            r.y = fma(m1.a, ynext, m1.b);
+        }
+        // ---- damping, averages, back-substitution of rho_pp and rtheta_pp (TI:2936-2959)
+        wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 - epssm) * rw_p, wwAvg);
+        {
+            const r2 dss = S9(A9_dss), rho = S9(A9_rho_zz_2);
+            const r2 dw = S9(A9_rw_save) - S9(A9_rw);
+            const r2 rd = (r + dw - dts * dss * (fm * zz + fp * zzm) * (fm * rho + fp * up1(rho)) * S9(A9_w_2)) / (1.0 + dts * dss) - dw;
+            r = sel(k_mid, rd, r);
+            wwAvg = sel(k_mid, wwAvg + 0.5 * (1.0 + epssm) * r, wwAvg);
+        }
+        AC9_RELEASE                                      // last read of this stage
+        r = sel(k_le_nl, r, 0.0);
+        const r2 r1 = dn1(r);
+        ST(D.rtheta_pp_old, i, rtheta_pp);
+        ST(D.rw_p, i, r);
+        ST(D.wwAvg, i, sel(k_le_nl, wwAvg, 0.0));
+        ST(D.rho_pp, i, sel(k_lt_nl, rs - cofrz * (r1 - r), 0.0));
+        ST(D.rtheta_pp, i, sel(k_lt_nl, ts - rdzw * (coftz1 * r1 - coftz * r), 0.0));
+    }
+#undef S9
+#undef AC9_RELEASE
+#undef AC9_FILL
+}
+
 // ------------------------------------------------------------------ atm_divergence_damping_3d  TI:2987-3075
 // first != 0: also performs the first-small-step edge update of atm_advance_acoustic_step_work (TI:2798-2806:
 // ru_p = dts * tend_u, ruAvg = ru_p), which k3_acoustic_cell only evaluated on the fly.
@@ -1689,7 +1961,7 @@ __global__ void __launch_bounds__(CW_THREADS) k2_acoustic_edge(const Dev D, real
 // ------------------------------------------------------------------ atm_advance_scalars_work  TI:3575-3855
 // edge value of every scalar ("horiz_flux_arr"), TI:3670-3751: one warp per edge, the stencil indices and the two
 // possible weights per entry live one per lane and are broadcast; scalars are separate level-contiguous planes
-__global__ void __launch_bounds__(CW_THREADS, 6) k2_scalars_edge(const Dev D) {
+__global__ void __launch_bounds__(CW_THREADS, 6 * 8 / CW_WARPS) k2_scalars_edge(const Dev D) {
     CW_SETUP_R(D.nEdges)
     const int nadv = D.nAdvCellsForEdge[i];
     int my_c = 0; real my_wp = 0.0, my_wm = 0.0;

@@ -64,7 +64,7 @@ struct mpasb_handle_s {
     int* d_dd_edges = nullptr; unsigned char* d_dd_done = nullptr; int n_dd_edges = 0; bool dd_lists_ok = false, dd_partial = false;   // build_dd_lists
     int* d_ac_bnd = nullptr; int* d_ac_int = nullptr; int n_ac_bnd = 0, n_ac_int = 0; bool ac_lists_ok = false;   // build_acoustic_lists
     bool profile = false;
-    bool smem_attr_vic = false, smem_attr_ac = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
+    bool smem_attr_vic = false, smem_attr_ac = false, smem_attr_ac9 = false;   // opt-in to > 48 KB of dynamic shared memory, per handle because it is per device
     std::map<std::string, ProfRec> prof;
     // stencil-union tiles of the TMA-staged advective flux kernel (k4_dt_edge_flux): host copies of the lists they
     // are derived from, and the derived device tables
@@ -525,6 +525,7 @@ static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size
     cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 #define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + CW_WARPS - 1) / CW_WARPS)), dim3(CW_THREADS), 0, __VA_ARGS__); h->launches++; } while (0)
+#define LAUNCHWB(kern, W, n, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + (W) - 1) / (W))), dim3((W) * 32), 0, __VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -806,8 +807,8 @@ static int compute_dyn_tend(H* h, int rk_step, real dt, bool in_step = false) { 
     comm_wait(h);
     if (h->colwarp && !A.rayleigh_damp_u) {
         if (h->cor_dirty) build_coriolis_tables(h);
-        if (h->cor_ok) { LAUNCHW(k8_coriolis_cell, D.nCells, D); LAUNCHW(k2_dt_edge_b<true>, D.nEdges, D, A); }
-        else LAUNCHW(k2_dt_edge_b<false>, D.nEdges, D, A);
+        if (h->cor_ok) { LAUNCHW(k8_coriolis_cell, D.nCells, D); LAUNCHWB(k2_dt_edge_b<true>, EB_WARPS, D.nEdges, D, A); }
+        else LAUNCHWB(k2_dt_edge_b<false>, EB_WARPS, D.nEdges, D, A);
     }
     else LAUNCH(k_dt_edge_b, D.nEdges, 0, D, A);
     if (rk_step == 1) {
@@ -947,6 +948,24 @@ static int advance_acoustic_step(H* h, real dts, int small_step, const char* gro
                 if (exchange_async(h, group)) return 1;
                 AC6_RUN(h->d_ac_int, h->n_ac_int);
                 return 0;
+            }
+            // TMA-pipelined form (own-column operands by cp.async.bulk, one trip ahead): plain runs only
+            static const int tma = getenv("MPASB_AC9") ? atoi(getenv("MPASB_AC9")) : AC9_DEFAULT;
+            if (tma && !regional) {
+                const size_t smem9 = (size_t)2 * AC9_NF * AC9_WARPS * h->D.LDK * sizeof(real);
+                if (!h->smem_attr_ac9) {
+                    cudaFuncSetAttribute(k9_acoustic_cell<AC9_WARPS, AC9_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem9, 220 * 1024 / AC9_MINB));
+                    cudaFuncSetAttribute(k9_acoustic_cell<AC9_WARPS, AC9_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                    h->smem_attr_ac9 = true;
+                }
+                if (smem9 <= (size_t)220 * 1024 / AC9_MINB) {
+                    const unsigned need = (unsigned)((h->D.nCells + AC9_WARPS - 1) / AC9_WARPS), resident = (unsigned)(sm_count * AC9_MINB);
+                    KScope ks9_(h, "k:k9_acoustic_cell");
+                    klaunch(h, k9_acoustic_cell<AC9_WARPS, AC9_MINB>, dim3(std::max(1u, std::min(need, resident))), dim3(AC9_WARPS * 32), smem9,
+                            h->D, dts, small_step, epssm, resm);
+                    h->launches++;
+                    return group ? exchange(h, group) : 0;
+                }
             }
             AC6_RUN((const int*)nullptr, h->D.nCells);
 #undef AC6_RUN
@@ -1394,6 +1413,53 @@ extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
 }
 
 // ------------------------------------------------------------------ init-time and per-routine entry points
+// ------------------------------------------------------------------ atm_mpas_init_block, mesh part (CORE:456-470, 1091-1452)
+#include "init_block_host.inl"
+static const char* const INITBLK_REAL_OUT[] = {"edgesOnVertex_sign", "edgesOnCell_sign", "zb_cell", "zb3_cell", "invAreaCell", "invDvEdge", "invDcEdge",
+    "invAreaTriangle", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4", "meshScalingRegionalCell", "meshScalingRegionalEdge", "dss"};
+static const char* const INITBLK_INT_OUT[] = {"kiteForCell", "nAdvCellsForEdge", "advCellsForEdge"};
+static std::vector<real>* initblk_real(initblk::Out& o, const char* name) {
+    std::vector<real>* v[] = {&o.edgesOnVertex_sign, &o.edgesOnCell_sign, &o.zb_cell, &o.zb3_cell, &o.invAreaCell, &o.invDvEdge, &o.invDcEdge,
+        &o.invAreaTriangle, &o.adv_coefs, &o.adv_coefs_3rd, &o.meshScalingDel2, &o.meshScalingDel4, &o.meshScalingRegionalCell, &o.meshScalingRegionalEdge, &o.dss};
+    for (size_t q = 0; q < sizeof(INITBLK_REAL_OUT) / sizeof(*INITBLK_REAL_OUT); q++) if (!strcmp(name, INITBLK_REAL_OUT[q])) return v[q];
+    return nullptr;
+}
+static std::vector<int>* initblk_int(initblk::Out& o, const char* name) {
+    std::vector<int>* v[] = {&o.kiteForCell, &o.nAdvCellsForEdge, &o.advCellsForEdge};
+    for (size_t q = 0; q < sizeof(INITBLK_INT_OUT) / sizeof(*INITBLK_INT_OUT); q++) if (!strcmp(name, INITBLK_INT_OUT[q])) return v[q];
+    return nullptr;
+}
+static bool initblk_dims_ok(const mpasb_dims* d) {
+    return d && d->nCells > 0 && d->nEdges > 0 && d->nVertices > 0 && d->nVertLevels > 0 && d->maxEdges > 0 && d->maxEdges <= 14 && d->vertexDegree > 0;
+}
+extern "C" int mpasb_init_block_host(const mpasb_dims* dims, const mpasb_config* cfg, int config_h_ScaleWithMesh, double config_zd, double config_xnutr,
+                                     int n_in, const char* const* in_names, const void* const* in_arrays,
+                                     int n_out, const char* const* out_names, void* const* out_arrays) {
+    if (!initblk_dims_ok(dims) || !cfg || n_in < 0 || n_out < 0 || (n_in && (!in_names || !in_arrays)) || (n_out && (!out_names || !out_arrays))) return 2;
+    initblk::In in;
+    if (initblk::bind(in, n_in, in_names, in_arrays)) return 1;                 // an input is missing
+    initblk::Out o;
+    initblk::compute(*dims, *cfg, config_h_ScaleWithMesh, config_zd, config_xnutr, in, o);
+    for (int k = 0; k < n_out; k++) {
+        if (!out_names[k] || !out_arrays[k]) return 2;
+        if (std::vector<real>* v = initblk_real(o, out_names[k])) memcpy(out_arrays[k], v->data(), v->size() * sizeof(real));
+        else if (std::vector<int>* w = initblk_int(o, out_names[k])) memcpy(out_arrays[k], w->data(), w->size() * sizeof(int));
+        else return 1;                                                            // not a field this routine derives
+    }
+    return 0;
+}
+extern "C" int mpasb_init_block(mpasb_handle h, int config_h_ScaleWithMesh, double config_zd, double config_xnutr,
+                                int n_in, const char* const* in_names, const void* const* in_arrays) {
+    if (!h || n_in < 0 || (n_in && (!in_names || !in_arrays))) return 2;
+    initblk::In in;
+    if (const char* missing = initblk::bind(in, n_in, in_names, in_arrays)) { h->err = std::string("mpasb_init_block: input missing: ") + missing; return 1; }
+    initblk::Out o;
+    initblk::compute(h->dims, h->cfg, config_h_ScaleWithMesh, config_zd, config_xnutr, in, o);
+    for (const char* name : INITBLK_REAL_OUT) { std::vector<real>* v = initblk_real(o, name); if (int rc = mpasb_set_field(h, name, 1, v->data(), (long)v->size())) return rc; }
+    for (const char* name : INITBLK_INT_OUT) { std::vector<int>* v = initblk_int(o, name); if (int rc = mpasb_set_field_int(h, name, v->data(), (long)v->size())) return rc; }
+    return 0;
+}
+
 #define ENTRY(body) { cudaSetDevice(h->device); body; CUDA_OK(cudaStreamSynchronize(h->stream)); CUDA_OK(cudaGetLastError()); return 0; }
 extern "C" int mpasb_init_coupled_diagnostics(mpasb_handle h) ENTRY(init_coupled_diagnostics(h))
 extern "C" int mpasb_init_solve_diagnostics(mpasb_handle h, mpasb_real dt) ENTRY(compute_solve_diagnostics(h, dt, 1, 0))

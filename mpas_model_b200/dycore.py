@@ -150,6 +150,60 @@ def _load_lib(path=None):
     return lib
 
 
+# ---- atm_mpas_init_block, mesh part, in the library (mpasb_init_block / mpasb_init_block_host) ----
+INIT_BLOCK_IN_INT = ("nEdgesOnCell", "edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsOnEdge", "verticesOnEdge",
+                     "edgesOnVertex", "cellsOnVertex")
+INIT_BLOCK_IN_REAL = ("zb", "zb3", "deriv_two", "dcEdge", "dvEdge", "areaCell", "areaTriangle", "meshDensity", "zgrid")
+INIT_BLOCK_OUT_REAL = ("edgesOnVertex_sign", "edgesOnCell_sign", "zb_cell", "zb3_cell", "invAreaCell", "invDvEdge", "invDcEdge",
+                       "invAreaTriangle", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4",
+                       "meshScalingRegionalCell", "meshScalingRegionalEdge", "dss")
+INIT_BLOCK_OUT_INT = ("kiteForCell", "nAdvCellsForEdge", "advCellsForEdge")
+_INIT_BLOCK_ONE_BASED = {"edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsOnEdge", "verticesOnEdge", "edgesOnVertex",
+                         "cellsOnVertex", "kiteForCell", "advCellsForEdge"}
+
+
+def _init_block_inputs(d, rdtype):
+    """The raw mesh fields of a block dict in the layout of the ABI: dense, 1-based connectivity (the dict is 0-based)."""
+    keep, names, ptrs = [], [], []
+    for n in INIT_BLOCK_IN_INT + INIT_BLOCK_IN_REAL:
+        if n in INIT_BLOCK_IN_INT:
+            a = np.ascontiguousarray(d[n], dtype=np.int32)
+            if n in _INIT_BLOCK_ONE_BASED:
+                a = np.ascontiguousarray(a + 1)
+        else:
+            a = np.ascontiguousarray(d[n], dtype=rdtype)
+        keep.append(a); names.append(n.encode()); ptrs.append(a.ctypes.data)
+    k = len(names)
+    return keep, k, (C.c_char_p * k)(*names), (C.c_void_p * k)(*ptrs)
+
+
+def init_block_host(d: dict, cfg: dict, precision: str = "double") -> dict:
+    """mpasb_init_block_host: the derived mesh fields of ``init_block.init_block`` computed by the library's C++ host code (no
+    device, no handle); returns them 0-based, shaped like the block dict's."""
+    lib = _load_lib(LIB_PATH_SINGLE if precision == "single" else None)
+    rdtype = np.float32 if lib.mpasb_real_bytes() == 4 else np.float64
+    dims, config = make_dims(d), make_config(cfg, d)
+    keep, k, names, ptrs = _init_block_inputs(d, rdtype)
+    nC, nE, nV, mx, vd, nz = d["nCells"], d["nEdges"], d["nVertices"], d["maxEdges"], d["vertexDegree"], d["nVertLevels"]
+    shapes = dict(edgesOnVertex_sign=(nV + 1, vd), edgesOnCell_sign=(nC + 1, mx), zb_cell=(nC + 1, mx, nz + 1), zb3_cell=(nC + 1, mx, nz + 1),
+                  invAreaCell=(nC + 1,), invDvEdge=(nE + 1,), invDcEdge=(nE + 1,), invAreaTriangle=(nV + 1,), adv_coefs=(nE + 1, 15),
+                  adv_coefs_3rd=(nE + 1, 15), meshScalingDel2=(nE + 1,), meshScalingDel4=(nE + 1,), meshScalingRegionalCell=(nC + 1,),
+                  meshScalingRegionalEdge=(nE + 1,), dss=(nC + 1, nz), kiteForCell=(nC + 1, mx), nAdvCellsForEdge=(nE + 1,),
+                  advCellsForEdge=(nE + 1, 15))
+    out = {n: np.zeros(shapes[n], dtype=rdtype if n in INIT_BLOCK_OUT_REAL else np.int32) for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT}
+    m = len(out)
+    onames = (C.c_char_p * m)(*[n.encode() for n in out])
+    optrs = (C.c_void_p * m)(*[a.ctypes.data for a in out.values()])
+    rc = lib.mpasb_init_block_host(C.byref(dims), C.byref(config), C.c_int(int(cfg["config_h_ScaleWithMesh"])), C.c_double(cfg["config_zd"]),
+                                   C.c_double(cfg["config_xnutr"]), C.c_int(k), names, ptrs, C.c_int(m), onames, optrs)
+    if rc != 0:
+        raise RuntimeError(f"mpasb_init_block_host failed ({rc})")
+    for n in out:
+        if n in _INIT_BLOCK_ONE_BASED:
+            out[n] = out[n] - 1
+    return out
+
+
 class Dycore(Backend):
     """One mesh block resident on one GPU."""
 
@@ -227,6 +281,13 @@ class Dycore(Backend):
             pass
 
     # -- reference entry points
+    def atm_mpas_init_block(self, d: dict, cfg: dict):
+        """mpas_atm_core.F:368-602, mesh part: the library derives the row-M fields from the raw mesh fields of ``d`` and keeps
+        them in the handle (mpasb_init_block)."""
+        keep, k, names, ptrs = _init_block_inputs(d, self.rdtype)
+        self._check(self.lib.mpasb_init_block(self._h, C.c_int(int(cfg["config_h_ScaleWithMesh"])), C.c_double(cfg["config_zd"]),
+                                              C.c_double(cfg["config_xnutr"]), C.c_int(k), names, ptrs), "mpasb_init_block")
+
     def atm_init_coupled_diagnostics(self):
         self._check(self.lib.mpasb_init_coupled_diagnostics(self._h), "init_coupled_diagnostics")
 

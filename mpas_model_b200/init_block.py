@@ -94,7 +94,9 @@ def adv_coef_compression(d: dict) -> None:
     dt2 = d["deriv_two"][:nE]
 
     def pos(target):
-        return np.argmax(lst[:, :15] == target[:, None], axis=1)
+        # the LAST match, as the reference's `do j=1,n; if (cell_list(j) == ...) j_in = j` (it differs from the first only where
+        # several neighbours of a block's outer halo cell point at the garbage cell)
+        return 14 - np.argmax((lst[:, :15] == target[:, None])[:, ::-1], axis=1)
 
     for side, cc, sg3 in ((0, c1, 1.0), (1, c2, -1.0)):
         j = pos(cc)

@@ -135,16 +135,20 @@ def test_gpu_step_started_from_an_init_file(tmp_path):
     p = str(tmp_path / "x1.642.init.nc")
     initfile.write_init_file(d, p)
     d2, cfg2 = initfile.read_init_file(p, dt=cfg["config_dt"])
+    d3, cfg3 = initfile.read_init_file(p, dt=cfg["config_dt"], derive="library")   # raw mesh fields only: the library derives the rest
+    assert "adv_coefs" not in d3 and "zb_cell" not in d3
     dt = cfg["config_dt"]
-    o, g_file, g_case = OracleDycore(d, cfg), Dycore(d2, cfg2), Dycore(d, cfg)
-    for b in (o, g_file, g_case):
+    o, g_file, g_case, g_lib = OracleDycore(d, cfg), Dycore(d2, cfg2), Dycore(d, cfg), Dycore(d3, cfg3)
+    g_lib.atm_mpas_init_block(d3, cfg3)                              # mpasb_init_block (C++ in the library)
+    for b in (o, g_file, g_case, g_lib):
         b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
         for _ in range(2):
             b.atm_srk3(dt); b.mpas_pool_shift_time_levels()
     for name in ("u", "w", "rho_zz", "theta_m", "scalars"):
         a, r = g_file.get_array(name, 1), o.get_array(name, 1)
         assert np.array_equal(a, g_case.get_array(name, 1)), name
+        assert np.array_equal(a, g_lib.get_array(name, 1)), name
         assert np.linalg.norm((a - r).ravel()) <= 2e-11 * np.linalg.norm(r.ravel()), name
     assert g_file.kernel_launch_count() > 0
-    for b in (o, g_file, g_case):
+    for b in (o, g_file, g_case, g_lib):
         b.close()

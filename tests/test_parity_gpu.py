@@ -136,6 +136,27 @@ def test_every_routine_in_sequence(pair):
 
 
 @pytest.mark.parametrize("mode", ["relaxed", "strict"])
+def test_one_block_of_a_decomposition_every_routine(small_case, mode, monkeypatch):
+    """One block of a 4-way decomposition (owned cells + two halo layers: nCellsSolve < nCells, nEdgesSolve < nEdges) as a
+    stand-alone handle, no exchanges: every routine of a step on identical inputs, halo columns included -- the halo-cell and
+    non-owned-edge branches of every kernel on ONE GPU (the N-GPU tests of test_multigpu.py need N devices)."""
+    from mpas_model_b200 import decomp
+    from mpas_model_b200.dycore import Dycore
+    from oracle.oracle import OracleDycore
+    monkeypatch.setenv("MPASB_STRICT", "1" if mode == "strict" else "0")
+    d, cfg = small_case
+    blocks, ex = decomp.decompose_case(d, cfg, decomp.partition_rcb(d, 4))
+    b = blocks[1]
+    assert b["nCellsSolve"] < b["nCells"] and b["nEdgesSolve"] < b["nEdges"]
+    o = OracleDycore(b, cfg, rank=1); g = Dycore(b, cfg)
+    try:
+        report = _walk_routines(b, cfg, o, g)
+        print(f"block 1 of 4, {mode}: worst {max(report, key=lambda r: r[1][1])}")
+    finally:
+        g.close(); o.close()
+
+
+@pytest.mark.parametrize("mode", ["relaxed", "strict"])
 def test_irregular_mesh_with_heptagons(mode, monkeypatch):
     """A jittered Voronoi mesh (maxEdges = 7: pentagons, hexagons and heptagons, stencils of up to 12 cells, 12 edges on
     edge) like the reference's variable-resolution meshes: the column-warp kernels leave their unrolled 6-edge loops

@@ -76,7 +76,7 @@ def f_arg(ctype, name):
         return name, f"character(kind=c_char), intent(out) :: {name}(*)"
     if ctype == "const char* const*":
         return name, f"type(c_ptr), intent(in) :: {name}(*)        ! C strings: c_loc of null-terminated character arrays"
-    if ctype in ("const mpasb_real* const*", "mpasb_real* const*"):
+    if ctype in ("const mpasb_real* const*", "mpasb_real* const*", "const void* const*", "void* const*"):
         return name, f"type(c_ptr), intent(in) :: {name}(*)        ! c_loc of the host arrays"
     if ctype in ("const void*", "void*"):
         return name, f"character(kind=c_char) :: {name}(*)"
