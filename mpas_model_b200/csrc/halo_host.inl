@@ -28,6 +28,9 @@ static const std::vector<GroupDef>& group_table() {
         {"dynamics:scalars_old", {{"scalars", 1, 0, 3}}},
         {"dynamics:w", {{"w", 2, 0, 3}}},
         {"dynamics:scale", {{"scale_arr", 1, 0, 3}}},
+        // not a reference group: "dynamics:scale" of every scalar in one message (the batched monotonic transport, where the
+        // scalar loop of TI:4220 runs inside each kernel; lev 0 = all Dev::mb_planes pairs of the work array)
+        {"dynamics:scale_all", {{"scale_arr", 0, 0, 3}}},
         {"initialization:u", {{"u", 1, 1, 7}}},
         {"initialization:pv_edge,ru,rw", {{"pv_edge", 1, 1, 7}, {"ru", 1, 1, 7}, {"rw", 1, 0, 3}}},
     };
@@ -145,7 +148,11 @@ static int halo_build_plan(H* h, const GroupDef& gd, HaloGroupPlan& P) {
             else if (f->inner == IN_S_NL) { nplanes = h->dims.num_scalars; plane = outer_of(h, f->loc) * LDK; }
             else if (f->inner == IN_NL_TWO) { nplanes = 2; plane = outer_of(h, f->loc) * LDK; }
             else if (f->inner != IN_NL) { h->err = std::string("halo: unsupported field shape ") + gf.name; return 1; }
-            real* base = (real*)f->d[gf.lev - 1];
+            real* base = gf.lev >= 1 ? (real*)f->d[gf.lev - 1] : nullptr;
+            if (gf.lev == 0) {                             // every per-scalar pair of scale_arr
+                if (strcmp(gf.name, "scale_arr")) { h->err = "halo: level 0 is scale_arr only"; return 1; }
+                base = h->D.mb_scale; nplanes = 2 * h->D.mb_planes;
+            }
             for (int p = 0; p < nplanes; p++)
                 for (int l = 0; l < K.n_layers; l++) {
                     if (!(gf.layers & (1 << l))) continue;

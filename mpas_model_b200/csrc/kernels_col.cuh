@@ -2190,8 +2190,15 @@ __global__ void __launch_bounds__(CW_THREADS) k2_dt_edge_d(const Dev D, const Dy
 // upwind flux and their difference (TI:4467-4487); same arithmetic as k_mono_edge2
 __device__ __forceinline__ r2 max0(r2 a) { return mk2(rmax(0.0, a.x), rmax(0.0, a.y)); }
 __device__ __forceinline__ r2 min0(r2 a) { return mk2(rmin(0.0, a.x), rmin(0.0, a.y)); }
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, real dt) {
+// The five kernels of the scalar loop take the scalar s = s0 + blockIdx.y and the plane pl of the per-scalar work arrays
+// (pl0 < 0: plane s, the batched launch with gridDim.y = num_scalars; otherwise plane pl0 for every scalar -- the arrays of
+// the field table are the last plane, Dev::mb_planes)
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s0, int pl0, real dt) {
     CW_SETUP_R(D.nEdges)
+    const int s = s0 + (int)blockIdx.y;
+    const size_t pl = (size_t)(pl0 < 0 ? s : pl0);
+    real* const flux_tmp = D.mb_flux_tmp + pl * D.edgePlane;
+    real* const flux_upwind_tmp = D.mb_flux_upwind_tmp + pl * D.edgePlane;
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
@@ -2223,8 +2230,8 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_edge2(const Dev D, int s, 
     // TI:4479 (and :4592), as written there: `config_apply_lbcs .and. (m == nRelaxZone) .or. (m == nRelaxZone-1)`
     const int m_bdy = D.bdyMaskEdge[i];
     const bool upwind_only = (D.apply_lbcs && m_bdy == 5) || m_bdy == 4;
-    ST(D.flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
-    ST(D.flux_tmp, i, upwind_only ? mk2(0.0, 0.0) : sel(k_lt_nl, dt * flux - fup, 0.0));
+    ST(flux_upwind_tmp, i, sel(k_lt_nl, fup, 0.0));
+    ST(flux_tmp, i, upwind_only ? mk2(0.0, 0.0) : sel(k_lt_nl, dt * flux - fup, 0.0));
 }
 
 // ------------------------------------------------------------------ atm_advance_scalars_mono_work, the other parts
@@ -2248,8 +2255,11 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_rho_int(const Dev D, real 
     ST(D.rho_zz_int, i, sel(lv.lt(nl), LD(D.rho_zz, i) + dt * (r - LD(D.rdzw, 0) * (dn1(ww) - ww)), 0.0));
 }
 // (C1) owned cells: vertical fluxes, bounds, vertical part of the upwind update and of scale_arr  TI:4277-4344, 4426-4459
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, real dt, real coef3) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s0, int pl0, real dt, real coef3) {
     CW_SETUP(D.nCellsSolve)
+    const int s = s0 + (int)blockIdx.y;
+    const size_t pl = (size_t)(pl0 < 0 ? s : pl0);
+    real* const scale_in = D.mb_scale + 2 * pl * D.cellPlane;
     const real* __restrict__ so = D.scalars + (size_t)s * D.cellPlane;
     const real* __restrict__ sn = D.scalars_2 + (size_t)s * D.cellPlane;
     const int ne = D.nEdgesOnCell[i];
@@ -2275,26 +2285,31 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell1(const Dev D, int s, 
     r2 snew = q * rho;
     snew = sel(lv.lt(nl - 1), snew - dn1(fu) * rdnw, snew);
     snew = sel(lv.ge(1), snew + fu * rdnw, snew);
-    ST(D.wdtn, i, wd0);
-    ST(D.s_max, i, sel(k_lt_nl, smax, 0.0));
-    ST(D.s_min, i, sel(k_lt_nl, smin, 0.0));
-    ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
-    ST(D.scale_arr, i, sel(k_lt_nl, -rdnw * (min0(wd1) - max0(wd0)), 0.0));                     // SCALE_IN
-    ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));       // SCALE_OUT
+    ST(D.mb_wdtn + pl * D.cellPlane, i, wd0);
+    ST(D.mb_s_max + pl * D.cellPlane, i, sel(k_lt_nl, smax, 0.0));
+    ST(D.mb_s_min + pl * D.cellPlane, i, sel(k_lt_nl, smin, 0.0));
+    ST(D.mb_scalar_new + pl * D.cellPlane, i, sel(k_lt_nl, snew, 0.0));
+    ST(scale_in, i, sel(k_lt_nl, -rdnw * (min0(wd1) - max0(wd0)), 0.0));                        // SCALE_IN
+    ST(scale_in + D.cellPlane, i, sel(k_lt_nl, -rdnw * (max0(wd1) - min0(wd0)), 0.0));          // SCALE_OUT
 }
 // (C3) owned cells: horizontal part of the upwind update and of scale_arr (4496-4513) and the limiter (4523-4553)
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const real* rho_lim) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, int pl0, const real* rho_lim) {
     CW_SETUP(D.nCellsSolve)
+    const size_t pl = (size_t)(pl0 < 0 ? (int)blockIdx.y : pl0);
+    real* const scale_in = D.mb_scale + 2 * pl * D.cellPlane;
+    real* const scalar_new = D.mb_scalar_new + pl * D.cellPlane;
+    const real* const flux_tmp = D.mb_flux_tmp + pl * D.edgePlane;
+    const real* const flux_upwind_tmp = D.mb_flux_upwind_tmp + pl * D.edgePlane;
     const int ne = D.nEdgesOnCell[i];
     const int le = min(lane, ne - 1);
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const real invArea = D.invAreaCell[i];
-    r2 snew = LD(D.scalar_new, i), sin_ = LD(D.scale_arr, i), sout = LD(D.scale_arr + D.cellPlane, i);
+    r2 snew = LD(scalar_new, i), sin_ = LD(scale_in, i), sout = LD(scale_in + D.cellPlane, i);
 #define MONO3_EDGE(E)                                                                                       \
     {                                                                                                       \
         const int iEdge = BC(my_e, (E)); const real sg = BC(my_sgn, (E));                                   \
-        const r2 ft = LD(D.flux_tmp, iEdge), fup = LD(D.flux_upwind_tmp, iEdge);                            \
+        const r2 ft = LD(flux_tmp, iEdge), fup = LD(flux_upwind_tmp, iEdge);                                \
         snew = selb((E) < ne, snew - sg * fup * invArea, snew);                                             \
         sout = selb((E) < ne, sout - max0(sg * ft) * invArea, sout);                                        \
         sin_ = selb((E) < ne, sin_ - min0(sg * ft) * invArea, sin_);                                        \
@@ -2305,28 +2320,32 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell3(const Dev D, const r
 #undef MONO3_EDGE
     const real eps = 1.e-20;
     const r2 rl = LD(rho_lim, i);
-    const r2 f_in = (LD(D.s_max, i) * rl - snew) / (sin_ + eps);
-    const r2 f_out = (LD(D.s_min, i) * rl - snew) / (sout - eps);
+    const r2 f_in = (LD(D.mb_s_max + pl * D.cellPlane, i) * rl - snew) / (sin_ + eps);
+    const r2 f_out = (LD(D.mb_s_min + pl * D.cellPlane, i) * rl - snew) / (sout - eps);
     const b2 k_lt_nl = lv.lt(nl);
-    ST(D.scalar_new, i, sel(k_lt_nl, snew, 0.0));
-    ST(D.scale_arr, i, sel(k_lt_nl, min2(splat(1.0), max0(f_in)), 0.0));
-    ST(D.scale_arr + D.cellPlane, i, sel(k_lt_nl, min2(splat(1.0), max0(f_out)), 0.0));
+    ST(scalar_new, i, sel(k_lt_nl, snew, 0.0));
+    ST(scale_in, i, sel(k_lt_nl, min2(splat(1.0), max0(f_in)), 0.0));
+    ST(scale_in + D.cellPlane, i, sel(k_lt_nl, min2(splat(1.0), max0(f_out)), 0.0));
 }
 // (D1) edges of owned cells: rescale the anti-diffusive flux (4579-4623)
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_edge4(const Dev D, int pl0) {
     CW_ENTER_R(D.nEdges)
     const int cell1 = D.cellsOnEdge[2 * i], cell2 = D.cellsOnEdge[2 * i + 1];
+    const size_t pl = (size_t)(pl0 < 0 ? (int)blockIdx.y : pl0);
     pdl_wait();
     if (!(cell1 < D.nCellsSolve || cell2 < D.nCellsSolve)) return;
-    const real* __restrict__ s_in = D.scale_arr; const real* __restrict__ s_out = D.scale_arr + D.cellPlane;
-    const r2 flux = LD(D.flux_tmp, i);
+    const real* s_in = D.mb_scale + 2 * pl * D.cellPlane; const real* s_out = s_in + D.cellPlane;
+    const r2 flux = LD(D.mb_flux_tmp + pl * D.edgePlane, i);
     const r2 f = max0(flux) * min2(LD(s_out, cell1), LD(s_in, cell2))
                + min0(flux) * min2(LD(s_in, cell1), LD(s_out, cell2));
-    ST(D.flux_arr, i, sel(lv.lt(nl), f, 0.0));
+    ST(D.mb_flux_arr + pl * D.edgePlane, i, sel(lv.lt(nl), f, 0.0));
 }
 // (D2) all cells: rescaled vertical flux (4636-4645), final update (4651-4674), positive-definite copy-out (4708-4715)
-__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, const real* rho_div) {
+__global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s0, int pl0, const real* rho_div) {
     CW_SETUP(D.nCells)
+    const int s = s0 + (int)blockIdx.y;
+    const size_t pl = (size_t)(pl0 < 0 ? s : pl0);
+    const real* const flux_arr = D.mb_flux_arr + pl * D.edgePlane;
     real* out = D.scalars_2 + (size_t)s * D.cellPlane;
     const b2 k_lt_nl = lv.lt(nl);
     if (D.bdyMaskCell[i] > 2) return;                  // TI:4709 `bdyMaskCell <= nSpecZone`: these cells are set after the transport
@@ -2336,11 +2355,11 @@ __global__ void __launch_bounds__(CW_THREADS) k2_mono_cell5(const Dev D, int s, 
     const int my_e = D.edgesOnCell[(unsigned)i * D.maxEdges + le];
     const real my_sgn = D.edgesOnCell_sign[(unsigned)i * D.maxEdges + le];
     const real invArea = D.invAreaCell[i];
-    const r2 s_in = LD(D.scale_arr, i), s_out = LD(D.scale_arr + D.cellPlane, i), wd = LD(D.wdtn, i);
+    const r2 s_in = LD(D.mb_scale + 2 * pl * D.cellPlane, i), s_out = LD(D.mb_scale + (2 * pl + 1) * D.cellPlane, i), wd = LD(D.mb_wdtn + pl * D.cellPlane, i);
     const r2 w0 = sel(lv.ge(1) && k_lt_nl, max0(wd) * min2(up1(s_out), s_in) + min0(wd) * min2(s_out, up1(s_in)), 0.0);
     const r2 w1 = dn1(w0);
-    r2 snew = LD(D.scalar_new, i);
-#define MONO5_EDGE(E) { const r2 fa = LD(D.flux_arr, BC(my_e, (E))); snew = selb((E) < ne, snew - BC(my_sgn, (E)) * fa * invArea, snew); }
+    r2 snew = LD(D.mb_scalar_new + pl * D.cellPlane, i);
+#define MONO5_EDGE(E) { const r2 fa = LD(flux_arr, BC(my_e, (E))); snew = selb((E) < ne, snew - BC(my_sgn, (E)) * fa * invArea, snew); }
 #pragma unroll
     for (int e = 0; e < CW_NE; e++) MONO5_EDGE(e)
     for (int e = CW_NE; e < ne; e++) MONO5_EDGE(e)

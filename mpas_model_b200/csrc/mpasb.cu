@@ -30,6 +30,7 @@ enum { TG_NONE = 0, TG_LOCAL, TG_CELL, TG_EDGE, TG_VERTEX };
 struct FieldRec {
     const char* name; int loc, inner, levels, type, target;
     void* d[2];            // device buffers per time level
+    void* alloc = nullptr; // start of the allocation when d[0] is not (work arrays of the batched monotonic transport: d[0] is the last plane)
     size_t dev_count;      // elements per buffer
     long host_count;       // dense host elements
 };
@@ -162,6 +163,11 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
     D.apply_lbcs = cfg->config_apply_lbcs != 0;
     D.index_qv = dims->index_qv - 1; D.moist_start = dims->moist_start - 1; D.moist_end = dims->moist_end - 1;
     D.cellPlane = (size_t)(dims->nCells + 1) * D.LDK; D.edgePlane = (size_t)(dims->nEdges + 1) * D.LDK;
+    {   // batched monotonic transport (MPASB_MONO_BATCH=0: one scalar at a time, as the reference's loop TI:4220)
+        const char* e = getenv("MPASB_MONO_BATCH");
+        const bool on = (!e || atoi(e) != 0) && dims->num_scalars > 1 && cfg->config_scalar_advection && (cfg->config_monotonic || cfg->config_positive_definite);
+        D.mb_planes = on ? dims->num_scalars : 1;
+    }
     h->cpb = std::max(1, 256 / D.LDK);
 #define F(name_, loc_, inner_, lev_, type_, tgt_) { FieldRec f; f.name = #name_; f.loc = LOC_##loc_; f.inner = IN_##inner_; \
         f.levels = lev_; f.type = T_##type_; f.target = TG_##tgt_; f.d[0] = f.d[1] = nullptr; h->fields.push_back(f); }
@@ -174,10 +180,17 @@ extern "C" int mpasb_create(const mpasb_dims* dims, const mpasb_config* cfg, int
         f.dev_count = dev_count_of(h, f.loc, f.inner);
         f.host_count = (long)(outer_of(h, f.loc) * inner_dense1(h, f.inner) * inner_dense2(h, f.inner));
         const size_t esz = f.type == T_REAL ? sizeof(real) : sizeof(int);
+        // work arrays of the monotonic transport: one plane per scalar when the transport is batched (Dev::mb_planes)
+        real** mb = nullptr;
+        for (const auto& kv : std::initializer_list<std::pair<const char*, real**>>{{"wdtn", &D.mb_wdtn}, {"s_max", &D.mb_s_max}, {"s_min", &D.mb_s_min},
+                 {"scalar_new", &D.mb_scalar_new}, {"scale_arr", &D.mb_scale}, {"flux_tmp", &D.mb_flux_tmp}, {"flux_upwind_tmp", &D.mb_flux_upwind_tmp},
+                 {"flux_arr", &D.mb_flux_arr}}) if (!strcmp(f.name, kv.first)) mb = kv.second;
+        const size_t planes = mb ? (size_t)D.mb_planes : 1;
         for (int l = 0; l < f.levels; l++) {
-            if (cudaMalloc(&f.d[l], f.dev_count * esz) != cudaSuccess) { h->err = "cudaMalloc failed"; mpasb_destroy(h); return 7; }
-            cudaMemsetAsync(f.d[l], 0, f.dev_count * esz, h->stream);
+            if (cudaMalloc(&f.d[l], planes * f.dev_count * esz) != cudaSuccess) { h->err = "cudaMalloc failed"; mpasb_destroy(h); return 7; }
+            cudaMemsetAsync(f.d[l], 0, planes * f.dev_count * esz, h->stream);
         }
+        if (mb) { *mb = (real*)f.d[0]; if (planes > 1) { f.alloc = f.d[0]; f.d[0] = (real*)f.d[0] + (planes - 1) * f.dev_count; } }
         max_bytes = std::max(max_bytes, (size_t)f.host_count * esz);
         set_dev_ptr(h, f);
     }
@@ -209,7 +222,7 @@ extern "C" int mpasb_destroy(mpasb_handle h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     halo_destroy(h->halo);
-    for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(f.d[l]);
+    for (FieldRec& f : h->fields) for (int l = 0; l < 2; l++) if (f.d[l]) cudaFree(l == 0 && f.alloc ? f.alloc : f.d[l]);
     if (h->staging) cudaFree(h->staging);
     if (h->stage_in) cudaFree(h->stage_in);
     if (h->stage_out) cudaFree(h->stage_out);
@@ -526,6 +539,7 @@ static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size
 }
 #define LAUNCHW(kern, n, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + CW_WARPS - 1) / CW_WARPS)), dim3(CW_THREADS), 0, __VA_ARGS__); h->launches++; } while (0)
 #define LAUNCHWB(kern, W, n, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + (W) - 1) / (W))), dim3((W) * 32), 0, __VA_ARGS__); h->launches++; } while (0)
+#define LAUNCHWY(kern, n, ny, ...) do { KScope ks_(h, "k:" #kern); klaunch(h, kern, dim3((unsigned)(((n) + CW_WARPS - 1) / CW_WARPS), (unsigned)(ny)), dim3(CW_THREADS), 0, __VA_ARGS__); h->launches++; } while (0)
 #define LAUNCH1D(kern, n, ...) do { KScope ks_(h, "k:" #kern); kern<<<nblk(n), 256, 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 
 static const real rgas = RGAS, cp = CP_, rv = RV_;
@@ -1106,36 +1120,51 @@ static int advance_scalars_mono(H* h, real dt) {              // TI:4012-4734
     Scope sc(h, "atm_advance_scalars_mono");
     const Dev& D = h->D;
     const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
+    const int S = D.num_scalars, last = D.mb_planes - 1;
     LAUNCH(k_mono_pre, D.nCellsSolve, 0, D, dt);
     if (exchange(h, "dynamics:scalars_old")) return 1;
     if (adv_density) { if (h->colwarp) LAUNCHW(k2_mono_rho_int, D.nCellsSolve, D, dt); else LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt); }
     const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
-    for (int s = 0; s < D.num_scalars; s++) {
-        if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
-        if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
-        if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+    if (h->colwarp && D.mb_planes == S && S > 1) {
+        // batched over scalars: the scalar loop of TI:4220 runs INSIDE each kernel launch (gridDim.y = scalar, work arrays
+        // one plane per scalar), and the scale factors of all scalars travel in one exchange instead of S (TI:4568)
+        LAUNCHWY(k2_mono_cell1, D.nCellsSolve, S, D, 0, -1, dt, h->cfg.config_coef_3rd_order);
+        LAUNCHWY(k2_mono_edge2, D.nEdges, S, D, 0, -1, dt);
+        LAUNCHWY(k2_mono_cell3, D.nCellsSolve, S, D, -1, rho);
+        if (exchange(h, "dynamics:scale_all")) return 1;
+        LAUNCHWY(k2_mono_edge4, D.nEdges, S, D, -1);
+        LAUNCHWY(k2_mono_cell5, D.nCells, S, D, 0, -1, rho);
+        return 0;
+    }
+    for (int s = 0; s < S; s++) {
+        if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, last, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+        if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, last, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+        if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, last, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
         if (exchange(h, "dynamics:scale")) return 1;
-        if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
-        if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+        if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D, last); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+        if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, last, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
     }
     return 0;
 }
-// the same routine split at its two exchange points, for hosts that exchange halos themselves
+// the same routine split at its two exchange points, for hosts that exchange halos themselves (one scalar at a time; the
+// work arrays are the ones of the field table, i.e. the last plane)
 static void mono_pre(H* h, real dt) { LAUNCH(k_mono_pre, h->D.nCellsSolve, 0, h->D, dt); }
 static void mono_a(H* h, real dt, int s) {
     const Dev& D = h->D;
     const bool adv_density = h->cfg.config_split_dynamics_transport != 0;
+    const int last = D.mb_planes - 1;
     if (s == 0 && adv_density) { if (h->colwarp) LAUNCHW(k2_mono_rho_int, D.nCellsSolve, D, dt); else LAUNCH(k_mono_rho_int, D.nCellsSolve, 0, D, dt); }
     const real* rho = adv_density ? D.rho_zz_int : D.rho_zz_2;
-    if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
-    if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
-    if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
+    if (h->colwarp) LAUNCHW(k2_mono_cell1, D.nCellsSolve, D, s, last, dt, h->cfg.config_coef_3rd_order); else LAUNCH(k_mono_cell1, D.nCellsSolve, 0, D, s, dt, h->cfg.config_coef_3rd_order);
+    if (h->colwarp) LAUNCHW(k2_mono_edge2, D.nEdges, D, s, last, dt); else LAUNCH(k_mono_edge2, D.nEdges, 0, D, s, dt);
+    if (h->colwarp) LAUNCHW(k2_mono_cell3, D.nCellsSolve, D, last, rho); else LAUNCH(k_mono_cell3, D.nCellsSolve, 0, D, rho);
 }
 static void mono_b(H* h, int s) {
     const Dev& D = h->D;
     const real* rho = h->cfg.config_split_dynamics_transport ? D.rho_zz_int : D.rho_zz_2;
-    if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
-    if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
+    const int last = D.mb_planes - 1;
+    if (h->colwarp) LAUNCHW(k2_mono_edge4, D.nEdges, D, last); else LAUNCH(k_mono_edge4, D.nEdges, 0, D);
+    if (h->colwarp) LAUNCHW(k2_mono_cell5, D.nCells, D, s, last, rho); else LAUNCH(k_mono_cell5, D.nCells, 0, D, s, rho);
 }
 static void init_coupled_diagnostics(H* h) {                  // TI:6776-7010
     const real rcv = rgas / (cp - rgas);

@@ -64,6 +64,12 @@ struct Dev {
     // W[i][j] of edge j of the cell in the edgesOnEdge list of its edge i (8 x 8 reals), per edge its slot in its two cells,
     // and the partial sums [cell][slot][LDK]
     real* cor_w; int* cor_slot; real* cor_part;
+    // monotonic transport batched over scalars (advance_scalars_mono): the per-scalar work arrays of TI:4220-4719 exist in
+    // mb_planes copies, one per scalar, so that each of its five kernels runs ONCE for all scalars (gridDim.y = scalar) and
+    // `scale_arr` of every scalar travels in ONE exchange; the arrays of the field table are the LAST plane of each (what the
+    // reference's arrays hold when the routine returns).  mb_planes == 1: not batched, the bases are the table arrays.
+    int mb_planes;
+    real *mb_wdtn, *mb_s_max, *mb_s_min, *mb_scalar_new, *mb_scale, *mb_flux_tmp, *mb_flux_upwind_tmp, *mb_flux_arr;
 };
 #undef F
 #undef FIELD_REAL

@@ -53,6 +53,7 @@ GROUPS = {
     "dynamics:scalars_old": (("scalars", 1, "cells", (1, 2)),),
     "dynamics:w": (("w", 2, "cells", (1, 2)),),
     "dynamics:scale": (("scale_arr", 1, "cells", (1, 2)),),
+    "dynamics:scale_all": (("scale_arr", 0, "cells", (1, 2)),),   # library only: the pairs of all scalars in one message (level 0)
     "initialization:u": (("u", 1, "edges", (1, 2, 3)),),
     "initialization:pv_edge,ru,rw": (("pv_edge", 1, "edges", (1, 2, 3)), ("ru", 1, "edges", (1, 2, 3)), ("rw", 1, "cells", (1, 2))),
 }
