@@ -530,6 +530,13 @@ struct KScope {
 // blocks may become resident while the previous kernel of the stream drains (mpasb_dev.cuh); MPASB_PDL=0 launches them plainly.
 template <typename... P, typename... A>
 static inline void klaunch(H* h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+    // MPASB_CARVEOUT=<percent>: one shared-memory carve-out preference for every kernel launched through here (experiment: do
+    // carve-out changes between consecutive kernels cost anything?  the k9 arguments keep their own 100 %)
+    static const int carve = getenv("MPASB_CARVEOUT") ? atoi(getenv("MPASB_CARVEOUT")) : -1;
+    if (carve >= 0) {
+        static std::map<const void*, bool> seen;
+        if (!seen.count((const void*)kern)) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve); seen[(const void*)kern] = true; }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute at;
