@@ -963,7 +963,11 @@ __global__ void __launch_bounds__(EB_WARPS * 32, MB_EDGE_B) k2_dt_edge_b(const D
         int my_eoe = 0; real my_woe = 0.0;
         if (lane < neoe) { my_eoe = D.edgesOnEdge[(unsigned)i * D.maxEdges2 + lane]; my_woe = D.weightsOnEdge[(unsigned)i * D.maxEdges2 + lane]; }
         const r2 pv_e = LD(D.pv_edge, i);
-#pragma unroll 5
+#ifndef EB_UNROLL
+#define EB_UNROLL 5
+#endif
+        constexpr int eb_unroll = EB_UNROLL;
+#pragma unroll eb_unroll
         for (int j = 0; j < neoe; j++) {
             const int eoe = BC(my_eoe, j);
             const real woe = BC(my_woe, j);

@@ -295,9 +295,10 @@ struct HaloSeg { real* field; int idx_off; int count; int width; int peer; size_
 __global__ void k_halo_pack(const HaloSeg* __restrict__ seg, const int* __restrict__ idx, real* __restrict__ buf, int nseg) {
     for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
         const HaloSeg g = seg[s];
-        const size_t total = (size_t)g.count * g.width;
-        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-            const int j = (int)(t / g.width), k = (int)(t % g.width);
+        // 32-bit index arithmetic: a segment holds count * width < 2^31 reals, and a 64-bit division per element costs more than the copy
+        const unsigned total = (unsigned)g.count * (unsigned)g.width, w = (unsigned)g.width;
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+            const unsigned j = t / w, k = t - j * w;
             buf[g.buf_off + t] = g.field[(size_t)idx[g.idx_off + j] * g.stride + k];
         }
     }
@@ -338,9 +339,10 @@ __global__ void k_halo_put(const HaloSeg* __restrict__ seg, const int* __restric
             while (ld_acquire_sys(pp.local_consumed[p]) < pp.seq_send[p] - 2) { }
         __syncthreads();
         real* dst = pp.remote[p] + (g.buf_off - pp.send_off[p]);
-        const size_t total = (size_t)g.count * g.width;
-        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-            const int j = (int)(t / g.width), k = (int)(t % g.width);
+        // 32-bit index arithmetic: a segment holds count * width < 2^31 reals, and a 64-bit division per element costs more than the copy
+        const unsigned total = (unsigned)g.count * (unsigned)g.width, w = (unsigned)g.width;
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+            const unsigned j = t / w, k = t - j * w;
             dst[t] = g.field[(size_t)idx[g.idx_off + j] * g.stride + k];
         }
     }
@@ -362,9 +364,10 @@ __global__ void k_halo_get(const HaloSeg* __restrict__ seg, const int* __restric
         if (threadIdx.x == 0) while (ld_acquire_sys(pp.local_arrived[p]) < pp.seq_recv[p]) { }
         __syncthreads();
         const real* src = pp.local[p] + (g.buf_off - pp.recv_off[p]);
-        const size_t total = (size_t)g.count * g.width;
-        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-            const int j = (int)(t / g.width), k = (int)(t % g.width);
+        // 32-bit index arithmetic: a segment holds count * width < 2^31 reals, and a 64-bit division per element costs more than the copy
+        const unsigned total = (unsigned)g.count * (unsigned)g.width, w = (unsigned)g.width;
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+            const unsigned j = t / w, k = t - j * w;
             g.field[(size_t)idx[g.idx_off + j] * g.stride + k] = __ldcg(src + t);
         }
     }
@@ -381,9 +384,10 @@ __global__ void k_halo_get(const HaloSeg* __restrict__ seg, const int* __restric
 __global__ void k_halo_unpack(const HaloSeg* __restrict__ seg, const int* __restrict__ idx, const real* __restrict__ buf, int nseg) {
     for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
         const HaloSeg g = seg[s];
-        const size_t total = (size_t)g.count * g.width;
-        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-            const int j = (int)(t / g.width), k = (int)(t % g.width);
+        // 32-bit index arithmetic: a segment holds count * width < 2^31 reals, and a 64-bit division per element costs more than the copy
+        const unsigned total = (unsigned)g.count * (unsigned)g.width, w = (unsigned)g.width;
+        for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+            const unsigned j = t / w, k = t - j * w;
             g.field[(size_t)idx[g.idx_off + j] * g.stride + k] = buf[g.buf_off + t];
         }
     }
