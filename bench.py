@@ -126,7 +126,7 @@ KERNEL_MODEL_C = {
 }
 
 
-NCU_STEP_CSV = os.path.join("profiles", "r2_ncu_step_metrics_y.csv")
+NCU_STEP_CSV = os.path.join("profiles", "r2_ncu_step_metrics_ae.csv")
 
 
 def kernel_traffic(kernel, n_cells, n_lev, rb):
