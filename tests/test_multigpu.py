@@ -25,10 +25,13 @@ def _free_port():
 def _launch(mode, world, n_cells, n_lev, n_scal, n_steps, out, tmp_path, overrides=None):
     import json
     env = dict(os.environ, MPASB_CACHE=str(tmp_path), OMP_NUM_THREADS="2", MPASB_TEST_CFG=json.dumps(overrides or {}))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "mp_worker.py"), mode, str(n_cells), str(n_lev), str(n_scal), str(n_steps), out]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for attempt in range(3):         # the port found free can be taken again before torchrun binds it (seen once on a GPU box): retry
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+               os.path.join(ROOT, "tests", "mp_worker.py"), mode, str(n_cells), str(n_lev), str(n_scal), str(n_steps), out]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
 
