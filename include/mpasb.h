@@ -134,6 +134,10 @@ int  mpasb_init_solve_diagnostics_async(mpasb_handle h, mpasb_real dt);   /* enq
  * Derived: edgesOnVertex_sign, edgesOnCell_sign, zb_cell, zb3_cell, kiteForCell, invAreaCell, invDvEdge, invDcEdge,
  * invAreaTriangle, nAdvCellsForEdge, advCellsForEdge, adv_coefs, adv_coefs_3rd, meshScalingDel2, meshScalingDel4,
  * meshScalingRegionalCell, meshScalingRegionalEdge, dss (shapes: include/mpasb_fields.def).
+ * Optional inputs xCell, yCell, zCell, xEdge, yEdge, zEdge (all six, mesh on a sphere): coeffs_reconstruct is derived as well --
+ * mpas_initialize_vectors (src/operators/mpas_vector_operations.F:652-771) and mpas_init_reconstruct
+ * (src/operators/mpas_vector_reconstruction.F:60-177; radial-basis-function fit of mpas_rbf_interpolation.F:1079-1145 solved by
+ * elgs / mpas_legs :1670-1846), which mpas_atm_core.F:534-535 call at start-up.
  * mpasb_init_block stores them in the handle (as mpasb_set_field / mpasb_set_field_int would); mpasb_init_block_host is the
  * same computation without a handle or a device, written to the caller's arrays.  The three namelist values are the ones
  * only this routine reads (Registry.xml:177, 261, 266).  Returns 1 when a named input / output is missing or unknown. */

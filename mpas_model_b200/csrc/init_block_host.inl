@@ -25,10 +25,14 @@ struct In {
               *verticesOnEdge = nullptr, *edgesOnVertex = nullptr, *cellsOnVertex = nullptr;
     const real *zb = nullptr, *zb3 = nullptr, *deriv_two = nullptr, *dcEdge = nullptr, *dvEdge = nullptr, *areaCell = nullptr,
                *areaTriangle = nullptr, *meshDensity = nullptr, *zgrid = nullptr;
+    // optional (all six or none): with them, coeffs_reconstruct is derived as well (mpas_init_reconstruct)
+    const real *xCell = nullptr, *yCell = nullptr, *zCell = nullptr, *xEdge = nullptr, *yEdge = nullptr, *zEdge = nullptr;
+    bool coords() const { return xCell && yCell && zCell && xEdge && yEdge && zEdge; }
 };
 struct Out {
     std::vector<real> edgesOnVertex_sign, edgesOnCell_sign, zb_cell, zb3_cell, invAreaCell, invDvEdge, invDcEdge, invAreaTriangle,
-                      adv_coefs, adv_coefs_3rd, meshScalingDel2, meshScalingDel4, meshScalingRegionalCell, meshScalingRegionalEdge, dss;
+                      adv_coefs, adv_coefs_3rd, meshScalingDel2, meshScalingDel4, meshScalingRegionalCell, meshScalingRegionalEdge, dss,
+                      coeffs_reconstruct;
     std::vector<int> kiteForCell, nAdvCellsForEdge, advCellsForEdge;
 };
 
@@ -46,6 +50,10 @@ static const char* bind(In& in, int n, const char* const* names, const void* con
         for (size_t q = 0; q < sizeof(IN_INT) / sizeof(*IN_INT); q++) if (!strcmp(names[k], IN_INT[q])) *ip[q] = (const int*)arrays[k];
         for (size_t q = 0; q < sizeof(IN_REAL) / sizeof(*IN_REAL); q++) if (!strcmp(names[k], IN_REAL[q])) *rp[q] = (const real*)arrays[k];
     }
+    static const char* const opt[] = {"xCell", "yCell", "zCell", "xEdge", "yEdge", "zEdge"};
+    const real** op[] = {&in.xCell, &in.yCell, &in.zCell, &in.xEdge, &in.yEdge, &in.zEdge};
+    for (int k = 0; k < n; k++)
+        if (names[k] && arrays[k]) for (int q = 0; q < 6; q++) if (!strcmp(names[k], opt[q])) *op[q] = (const real*)arrays[k];
     for (size_t q = 0; q < sizeof(IN_INT) / sizeof(*IN_INT); q++) if (!*ip[q]) return IN_INT[q];
     for (size_t q = 0; q < sizeof(IN_REAL) / sizeof(*IN_REAL); q++) if (!*rp[q]) return IN_REAL[q];
     return nullptr;
@@ -161,6 +169,101 @@ static void compute(const mpasb_dims& dm, const mpasb_config& cf, int h_ScaleWit
                 const real s = std::sin((real)0.5 * pii * (z - zd) / (zt - zd));
                 o.dss[(size_t)(c - 1) * nz + k] = xnutr * (s * s) / std::pow(in.meshDensity[c - 1], (real)0.25);
             }
+        }
+    }
+}
+
+// ---- mpas_initialize_vectors (src/operators/mpas_vector_operations.F:652-771, spherical non-periodic branch) and
+// mpas_init_reconstruct (src/operators/mpas_vector_reconstruction.F:60-177) with the radial-basis-function fit of
+// mpas_rbf_interp_func_3D_plane_vec_const_dir_comp_coeffs (src/operators/mpas_rbf_interpolation.F:1079-1145, matrix and right-hand
+// sides :1527-1559, inverse multiquadric :1369-1376) solved by elgs / mpas_legs (:1782-1846, 1670-1698: Gaussian elimination
+// with scaled partial pivoting): coeffs_reconstruct(3, maxEdges, nCells+1) of the owned cells.  Operation order as in
+// mpas_model_b200/reconstruct.py, which the GPU tests of mpas_reconstruct are built on.
+struct V3 { real x, y, z; };
+static inline real dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline V3 unit3(V3 v) { const real n = std::sqrt((v.x * v.x + v.y * v.y) + v.z * v.z); return V3{v.x / n, v.y / n, v.z / n}; }
+static void reconstruct_coeffs(const mpasb_dims& dm, const In& in, Out& o) {
+    const int nC = dm.nCells, nE = dm.nEdges, nS = dm.nCellsSolve, mx = dm.maxEdges;
+    o.coeffs_reconstruct.assign((size_t)(nC + 1) * mx * 3, (real)0);
+    auto xc = [&](int c) { return V3{in.xCell[c], in.yCell[c], in.zCell[c]}; };          // 0-based; the garbage cell is index nC
+    auto xe = [&](int e) { return V3{in.xEdge[e], in.yEdge[e], in.zEdge[e]}; };
+    auto edge_normal = [&](int e) {                                                          // e 0-based, < nE
+        const int c1 = in.cellsOnEdge[(size_t)e * 2] - 1, c2 = in.cellsOnEdge[(size_t)e * 2 + 1] - 1;
+        V3 v;
+        if (c1 == nC && c2 == nC) v = V3{(real)1, (real)0, (real)0};
+        else if (c1 == nC) { const V3 a = xc(c2), b = xe(e); v = V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+        else if (c2 == nC) { const V3 a = xe(e), b = xc(c1); v = V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+        else { const V3 a = xc(c2), b = xc(c1); v = V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+        return unit3(v);
+    };
+    const int NMAX = 16 + 2;
+    if (mx + 2 > NMAX) return;
+    for (int c = 0; c < nS; c++) {
+        const int n = in.nEdgesOnCell[c], N = n + 2;
+        if (n < 1 || n > mx) continue;
+        V3 src[16], uv[16];
+        for (int i = 0; i < n; i++) { const int e = in.edgesOnCell[(size_t)c * mx + i] - 1; src[i] = xe(e); uv[i] = e < nE ? edge_normal(e) : V3{0, 0, 0}; }
+        const V3 dest = xc(c), rhat = unit3(dest);
+        const real ndr = dot3(uv[0], rhat);
+        const V3 xhat = unit3(V3{uv[0].x - ndr * rhat.x, uv[0].y - ndr * rhat.y, uv[0].z - ndr * rhat.z});
+        const V3 yhat = unit3(V3{rhat.y * xhat.z - rhat.z * xhat.y, rhat.z * xhat.x - rhat.x * xhat.z, rhat.x * xhat.y - rhat.y * xhat.x});
+        real alpha = 0;
+        for (int i = 0; i < n; i++) {
+            const V3 d{dest.x - src[i].x, dest.y - src[i].y, dest.z - src[i].z};
+            alpha = alpha + std::sqrt((d.x * d.x + d.y * d.y) + d.z * d.z);
+        }
+        alpha = alpha / (real)n;
+        const real a2 = alpha * alpha;
+        real ps[16][2], pu[16][2];
+        for (int i = 0; i < n; i++) { ps[i][0] = dot3(src[i], xhat); ps[i][1] = dot3(src[i], yhat); pu[i][0] = dot3(uv[i], xhat); pu[i][1] = dot3(uv[i], yhat); }
+        const real pd[2] = {dot3(dest, xhat), dot3(dest, yhat)};
+        real M[NMAX][NMAX], rhs[NMAX][2];
+        for (int i = 0; i < N; i++) { for (int j = 0; j < N; j++) M[i][j] = 0; rhs[i][0] = rhs[i][1] = 0; }
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j < n; j++) {
+                const real dx = ps[i][0] - ps[j][0], dy = ps[i][1] - ps[j][1];
+                const real rsq = (dx * dx + dy * dy) / a2;
+                M[i][j] = ((real)1.0 / std::sqrt((real)1.0 + rsq)) * (pu[i][0] * pu[j][0] + pu[i][1] * pu[j][1]);
+            }
+            const real dx = pd[0] - ps[i][0], dy = pd[1] - ps[i][1];
+            const real rb = (real)1.0 / std::sqrt((real)1.0 + (dx * dx + dy * dy) / a2);
+            rhs[i][0] = rb * pu[i][0]; rhs[i][1] = rb * pu[i][1];
+            M[i][n] = pu[i][0]; M[i][n + 1] = pu[i][1]; M[n][i] = pu[i][0]; M[n + 1][i] = pu[i][1];
+        }
+        rhs[n][0] = 1; rhs[n + 1][1] = 1;
+        // elgs: scaled partial pivoting, factors stored in place
+        int indx[NMAX]; real cs[NMAX];
+        for (int i = 0; i < N; i++) { indx[i] = i; real m = 0; for (int j = 0; j < N; j++) m = std::max(m, std::fabs(M[i][j])); cs[i] = m; }
+        for (int j = 0; j < N - 1; j++) {
+            real pi1 = 0; int k = j;
+            for (int i = j; i < N; i++) { const real pi = std::fabs(M[indx[i]][j]) / cs[indx[i]]; if (pi > pi1) { pi1 = pi; k = i; } }
+            std::swap(indx[j], indx[k]);
+            const int rj = indx[j];
+            for (int i = j + 1; i < N; i++) {
+                const int ri = indx[i];
+                const real pj = M[ri][j] / M[rj][j];
+                M[ri][j] = pj;
+                for (int q = j + 1; q < N; q++) M[ri][q] = M[ri][q] - pj * M[rj][q];
+            }
+        }
+        real co[2][NMAX];
+        for (int q = 0; q < 2; q++) {                           // mpas_legs: forward elimination of the right-hand side, back substitution
+            real b[NMAX];
+            for (int i = 0; i < N; i++) b[i] = rhs[i][q];
+            for (int i = 0; i < N - 1; i++) for (int j = i + 1; j < N; j++) b[indx[j]] = b[indx[j]] - M[indx[j]][i] * b[indx[i]];
+            real* x = co[q];
+            x[N - 1] = b[indx[N - 1]] / M[indx[N - 1]][N - 1];
+            for (int i = N - 2; i >= 0; i--) {
+                real xi = b[indx[i]];
+                for (int j = i + 1; j < N; j++) xi = xi - M[indx[i]][j] * x[j];
+                x[i] = xi / M[indx[i]][i];
+            }
+        }
+        for (int i = 0; i < n; i++) {
+            real* dst = &o.coeffs_reconstruct[((size_t)c * mx + i) * 3];
+            dst[0] = xhat.x * co[0][i] + yhat.x * co[1][i];
+            dst[1] = xhat.y * co[0][i] + yhat.y * co[1][i];
+            dst[2] = xhat.z * co[0][i] + yhat.z * co[1][i];
         }
     }
 }

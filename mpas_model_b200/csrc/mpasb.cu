@@ -1452,11 +1452,13 @@ extern "C" int mpasb_get_profile(mpasb_handle h, char* buf, long buflen) {
 // ------------------------------------------------------------------ atm_mpas_init_block, mesh part (CORE:456-470, 1091-1452)
 #include "init_block_host.inl"
 static const char* const INITBLK_REAL_OUT[] = {"edgesOnVertex_sign", "edgesOnCell_sign", "zb_cell", "zb3_cell", "invAreaCell", "invDvEdge", "invDcEdge",
-    "invAreaTriangle", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4", "meshScalingRegionalCell", "meshScalingRegionalEdge", "dss"};
+    "invAreaTriangle", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4", "meshScalingRegionalCell", "meshScalingRegionalEdge", "dss",
+    "coeffs_reconstruct"};          // the last one only when the six coordinate arrays were given (and the mesh is on a sphere)
 static const char* const INITBLK_INT_OUT[] = {"kiteForCell", "nAdvCellsForEdge", "advCellsForEdge"};
 static std::vector<real>* initblk_real(initblk::Out& o, const char* name) {
     std::vector<real>* v[] = {&o.edgesOnVertex_sign, &o.edgesOnCell_sign, &o.zb_cell, &o.zb3_cell, &o.invAreaCell, &o.invDvEdge, &o.invDcEdge,
-        &o.invAreaTriangle, &o.adv_coefs, &o.adv_coefs_3rd, &o.meshScalingDel2, &o.meshScalingDel4, &o.meshScalingRegionalCell, &o.meshScalingRegionalEdge, &o.dss};
+        &o.invAreaTriangle, &o.adv_coefs, &o.adv_coefs_3rd, &o.meshScalingDel2, &o.meshScalingDel4, &o.meshScalingRegionalCell, &o.meshScalingRegionalEdge, &o.dss,
+        &o.coeffs_reconstruct};
     for (size_t q = 0; q < sizeof(INITBLK_REAL_OUT) / sizeof(*INITBLK_REAL_OUT); q++) if (!strcmp(name, INITBLK_REAL_OUT[q])) return v[q];
     return nullptr;
 }
@@ -1476,9 +1478,10 @@ extern "C" int mpasb_init_block_host(const mpasb_dims* dims, const mpasb_config*
     if (initblk::bind(in, n_in, in_names, in_arrays)) return 1;                 // an input is missing
     initblk::Out o;
     initblk::compute(*dims, *cfg, config_h_ScaleWithMesh, config_zd, config_xnutr, in, o);
+    if (in.coords() && cfg->on_a_sphere) initblk::reconstruct_coeffs(*dims, in, o);
     for (int k = 0; k < n_out; k++) {
         if (!out_names[k] || !out_arrays[k]) return 2;
-        if (std::vector<real>* v = initblk_real(o, out_names[k])) memcpy(out_arrays[k], v->data(), v->size() * sizeof(real));
+        if (std::vector<real>* v = initblk_real(o, out_names[k])) { if (v->empty()) return 1; memcpy(out_arrays[k], v->data(), v->size() * sizeof(real)); }
         else if (std::vector<int>* w = initblk_int(o, out_names[k])) memcpy(out_arrays[k], w->data(), w->size() * sizeof(int));
         else return 1;                                                            // not a field this routine derives
     }
@@ -1491,7 +1494,12 @@ extern "C" int mpasb_init_block(mpasb_handle h, int config_h_ScaleWithMesh, doub
     if (const char* missing = initblk::bind(in, n_in, in_names, in_arrays)) { h->err = std::string("mpasb_init_block: input missing: ") + missing; return 1; }
     initblk::Out o;
     initblk::compute(h->dims, h->cfg, config_h_ScaleWithMesh, config_zd, config_xnutr, in, o);
-    for (const char* name : INITBLK_REAL_OUT) { std::vector<real>* v = initblk_real(o, name); if (int rc = mpasb_set_field(h, name, 1, v->data(), (long)v->size())) return rc; }
+    if (in.coords() && h->cfg.on_a_sphere) initblk::reconstruct_coeffs(h->dims, in, o);
+    for (const char* name : INITBLK_REAL_OUT) {
+        std::vector<real>* v = initblk_real(o, name);
+        if (v->empty()) continue;                              // coeffs_reconstruct without coordinates: stays what the host uploaded
+        if (int rc = mpasb_set_field(h, name, 1, v->data(), (long)v->size())) return rc;
+    }
     for (const char* name : INITBLK_INT_OUT) { std::vector<int>* v = initblk_int(o, name); if (int rc = mpasb_set_field_int(h, name, v->data(), (long)v->size())) return rc; }
     return 0;
 }

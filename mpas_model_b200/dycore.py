@@ -154,6 +154,7 @@ def _load_lib(path=None):
 INIT_BLOCK_IN_INT = ("nEdgesOnCell", "edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsOnEdge", "verticesOnEdge",
                      "edgesOnVertex", "cellsOnVertex")
 INIT_BLOCK_IN_REAL = ("zb", "zb3", "deriv_two", "dcEdge", "dvEdge", "areaCell", "areaTriangle", "meshDensity", "zgrid")
+INIT_BLOCK_IN_COORDS = ("xCell", "yCell", "zCell", "xEdge", "yEdge", "zEdge")     # optional: with them coeffs_reconstruct is derived too
 INIT_BLOCK_OUT_REAL = ("edgesOnVertex_sign", "edgesOnCell_sign", "zb_cell", "zb3_cell", "invAreaCell", "invDvEdge", "invDcEdge",
                        "invAreaTriangle", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4",
                        "meshScalingRegionalCell", "meshScalingRegionalEdge", "dss")
@@ -165,7 +166,8 @@ _INIT_BLOCK_ONE_BASED = {"edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsO
 def _init_block_inputs(d, rdtype):
     """The raw mesh fields of a block dict in the layout of the ABI: dense, 1-based connectivity (the dict is 0-based)."""
     keep, names, ptrs = [], [], []
-    for n in INIT_BLOCK_IN_INT + INIT_BLOCK_IN_REAL:
+    coords = INIT_BLOCK_IN_COORDS if all(n in d for n in INIT_BLOCK_IN_COORDS) else ()
+    for n in INIT_BLOCK_IN_INT + INIT_BLOCK_IN_REAL + coords:
         if n in INIT_BLOCK_IN_INT:
             a = np.ascontiguousarray(d[n], dtype=np.int32)
             if n in _INIT_BLOCK_ONE_BASED:
@@ -189,8 +191,11 @@ def init_block_host(d: dict, cfg: dict, precision: str = "double") -> dict:
                   invAreaCell=(nC + 1,), invDvEdge=(nE + 1,), invDcEdge=(nE + 1,), invAreaTriangle=(nV + 1,), adv_coefs=(nE + 1, 15),
                   adv_coefs_3rd=(nE + 1, 15), meshScalingDel2=(nE + 1,), meshScalingDel4=(nE + 1,), meshScalingRegionalCell=(nC + 1,),
                   meshScalingRegionalEdge=(nE + 1,), dss=(nC + 1, nz), kiteForCell=(nC + 1, mx), nAdvCellsForEdge=(nE + 1,),
-                  advCellsForEdge=(nE + 1, 15))
-    out = {n: np.zeros(shapes[n], dtype=rdtype if n in INIT_BLOCK_OUT_REAL else np.int32) for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT}
+                  advCellsForEdge=(nE + 1, 15), coeffs_reconstruct=(nC + 1, mx, 3))
+    want = INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT
+    if all(n in d for n in INIT_BLOCK_IN_COORDS) and cfg.get("on_a_sphere", True):
+        want = want + ("coeffs_reconstruct",)            # mpas_init_reconstruct (mpas_vector_reconstruction.F:60-177)
+    out = {n: np.zeros(shapes[n], dtype=np.int32 if n in INIT_BLOCK_OUT_INT else rdtype) for n in want}
     m = len(out)
     onames = (C.c_char_p * m)(*[n.encode() for n in out])
     optrs = (C.c_void_p * m)(*[a.ctypes.data for a in out.values()])

@@ -91,7 +91,7 @@ def read_init_file(path: str, dt: float | None = None, time_index: int = 0, deri
     """-> (block dict, cfg) ready for ``Dycore``/``OracleDycore``.  Scalars found in the file (``qv, qc, ...`` then
     ``tracerN``) become the planes of ``scalars`` in that order; ``qv`` is the only moist species assumed.
     ``derive``: who runs the mesh part of atm_mpas_init_block -- "numpy" (init_block.py, here) or "library" (nothing is derived
-    here except coeffs_reconstruct; the caller hands the raw fields to ``Dycore.atm_mpas_init_block``, i.e. mpasb_init_block)."""
+    here; the caller hands the raw fields to ``Dycore.atm_mpas_init_block``, i.e. mpasb_init_block)."""
     dims, attrs, v = ncio.read(path)
     nC, nE, nV, nz = dims["nCells"], dims["nEdges"], dims["nVertices"], dims["nVertLevels"]
     d = dict(nCells=nC, nEdges=nE, nVertices=nV, maxEdges=dims["maxEdges"], maxEdges2=dims["maxEdges2"],
@@ -131,12 +131,10 @@ def read_init_file(path: str, dt: float | None = None, time_index: int = 0, deri
     cfg = default_config(d["nominalMinDc"], dt)
     cfg.update(cfg_overrides)
     if derive == "library":
-        from .reconstruct import mpas_init_reconstruct
         for n in ("specZoneMaskCell", "specZoneMaskEdge"):           # a global mesh: no lateral boundary zones
             d[n] = np.zeros((nC if n.endswith("Cell") else nE) + 1)
         for n in ("bdyMaskCell", "bdyMaskEdge"):
             d[n] = np.zeros((nC if n.endswith("Cell") else nE) + 1, dtype=np.int32)
-        mpas_init_reconstruct(d)
     else:
         init_block(d, cfg)
     return d, cfg

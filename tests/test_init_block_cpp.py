@@ -25,6 +25,7 @@ def _same(name, got, want):
 
 @pytest.mark.parametrize("jitter", [0.0, 0.2], ids=["icosahedral", "irregular"])
 def test_library_init_block_equals_the_numpy_restatement(jitter):
+    """... and mpas_init_reconstruct's coeffs_reconstruct (reconstruct.py, which init_block.init_block ends with)."""
     from mpas_model_b200 import decomp, init_block
     from mpas_model_b200.case import make_case
     from mpas_model_b200.dycore import INIT_BLOCK_OUT_INT, INIT_BLOCK_OUT_REAL, init_block_host
@@ -32,14 +33,14 @@ def test_library_init_block_equals_the_numpy_restatement(jitter):
     _nonuniform(d)
     init_block.init_block(d, cfg)
     got = init_block_host(d, cfg)
-    for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT:
+    for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT + ("coeffs_reconstruct",):       # (the last: mpas_init_reconstruct, from the coordinates)
         assert _same(n, got[n], d[n]), n
-    assert float(np.abs(got["meshScalingDel2"] - 1.0).max()) > 0.05 and got["dss"].max() > 0.0
+    assert float(np.abs(got["meshScalingDel2"] - 1.0).max()) > 0.05 and got["dss"].max() > 0.0 and np.abs(got["coeffs_reconstruct"]).max() > 0.1
     # one block of a decomposition: connectivity pointing at the garbage slot, edges without an owned cell
     blocks, _ = decomp.decompose_case(d, cfg, decomp.partition_rcb(d, 4))
     for r in (0, 3):
         got = init_block_host(blocks[r], cfg)
-        for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT:
+        for n in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT + ("coeffs_reconstruct",):
             assert _same(n, got[n], blocks[r][n]), (r, n)
 
 
@@ -89,7 +90,12 @@ def test_single_precision_library_and_error_returns(tiny_case):
     dims, config = dycore.make_dims(d), dycore.make_config(cfg, d)
     keep, k, names, ptrs = dycore._init_block_inputs(d, np.float64)
     args = (C.byref(dims), C.byref(config), C.c_int(1), C.c_double(cfg["config_zd"]), C.c_double(cfg["config_xnutr"]))
-    assert lib.mpasb_init_block_host(*args, C.c_int(k - 1), names, ptrs, C.c_int(0), None, None) == 1
+    assert lib.mpasb_init_block_host(*args, C.c_int(5), names, ptrs, C.c_int(0), None, None) == 1             # only the first five inputs
+    raw = {n: v for n, v in d.items() if n not in dycore.INIT_BLOCK_IN_COORDS}                                  # without coordinates: no coeffs_reconstruct
+    keep2, k2, names2, ptrs2 = dycore._init_block_inputs(raw, np.float64)
+    co = np.zeros((d["nCells"] + 1, d["maxEdges"], 3))
+    assert lib.mpasb_init_block_host(*args, C.c_int(k2), names2, ptrs2, C.c_int(1), (C.c_char_p * 1)(b"coeffs_reconstruct"),
+                                     (C.c_void_p * 1)(co.ctypes.data)) == 1
     buf = np.zeros(4)
     onames, optrs = (C.c_char_p * 1)(b"theta_m"), (C.c_void_p * 1)(buf.ctypes.data)
     assert lib.mpasb_init_block_host(*args, C.c_int(k), names, ptrs, C.c_int(1), onames, optrs) == 1
@@ -102,16 +108,16 @@ def test_gpu_handle_derives_its_own_mesh_fields(small_case):
     ones, and two steps are bit-identical to a handle that was handed the numpy-derived fields."""
     from mpas_model_b200.dycore import INIT_BLOCK_OUT_INT, INIT_BLOCK_OUT_REAL, Dycore
     d, cfg = small_case
-    raw = {k: v for k, v in d.items() if k not in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT}
+    raw = {k: v for k, v in d.items() if k not in INIT_BLOCK_OUT_REAL + INIT_BLOCK_OUT_INT + ("coeffs_reconstruct",)}
     dt = cfg["config_dt"]
     g_lib, g_np = Dycore(raw, cfg), Dycore(d, cfg)
     g_lib.atm_mpas_init_block(d, cfg)
-    for n in INIT_BLOCK_OUT_REAL:
+    for n in INIT_BLOCK_OUT_REAL + ("coeffs_reconstruct",):
         assert _same(n, g_lib.get_array(n, 1), np.asarray(d[n])), n
     for b in (g_lib, g_np):
         b.atm_init_coupled_diagnostics(); b.atm_init_solve_diagnostics(dt)
         for _ in range(2):
             b.atm_srk3(dt); b.mpas_pool_shift_time_levels()
-    for name in ("u", "w", "rho_zz", "theta_m", "scalars"):
+    for name in ("u", "w", "rho_zz", "theta_m", "scalars", "uReconstructZonal", "uReconstructMeridional"):
         assert np.array_equal(g_lib.get_array(name, 1), g_np.get_array(name, 1)), name
     g_lib.close(); g_np.close()

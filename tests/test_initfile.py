@@ -136,7 +136,7 @@ def test_gpu_step_started_from_an_init_file(tmp_path):
     initfile.write_init_file(d, p)
     d2, cfg2 = initfile.read_init_file(p, dt=cfg["config_dt"])
     d3, cfg3 = initfile.read_init_file(p, dt=cfg["config_dt"], derive="library")   # raw mesh fields only: the library derives the rest
-    assert "adv_coefs" not in d3 and "zb_cell" not in d3
+    assert "adv_coefs" not in d3 and "zb_cell" not in d3 and "coeffs_reconstruct" not in d3
     dt = cfg["config_dt"]
     o, g_file, g_case, g_lib = OracleDycore(d, cfg), Dycore(d2, cfg2), Dycore(d, cfg), Dycore(d3, cfg3)
     g_lib.atm_mpas_init_block(d3, cfg3)                              # mpasb_init_block (C++ in the library)
