@@ -169,7 +169,10 @@ def line_common(args, n_cells, n_lev, dt, world):
                                    "`value` is the one BASELINE throughput figure that is comparable across N: cell-column "
                                    "updates/s = nCells x steps/s; steps_per_s and sdpd are reported beside it",
                    "l2": "no flush: every step streams the block's fields (>= 3.5 GB at 40962 cells x 55 levels), >> 126 MB L2",
-                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)",
+                   "namelist": "reference defaults (SRK3 order 2, 3 dynamics substeps, 2 acoustic substeps, monotonic split transport)"
+                               if getattr(args, "order", 2) == 2 else
+                               "reference defaults except config_time_integration_order = 3 (acoustic substeps 1, 1, 2 per stage, a second "
+                               "vertical-coefficient pass; the byte model of step_roofline is the order-2 one)",
                    "timed_region": "K x (atm_srk3 + mpas_pool_shift_time_levels), fields resident; excluded: mesh/state generation, "
                                    "upload, init-time diagnostics, the min/max summary (taken once after the loop), H2D/D2H (those are in e2e)"},
         # outside `config` so that both arms print the same config object
@@ -217,7 +220,7 @@ def reference_arm(args, rank, world):
     else:
         from mpas_model_b200.case import make_case
         from oracle import ref as oref
-        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
+        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars, **(dict(config_time_integration_order=3) if args.order == 3 else {}))
         frac = 1.0
         sample_what = "the whole mesh"
         if oref.build() and not os.environ.get("MPASB_REF_PORT"):
@@ -278,6 +281,7 @@ def main():
     ap.add_argument("--levels", type=int, default=0)
     ap.add_argument("--scalars", type=int, default=1)
     ap.add_argument("--precision", default="double", choices=("double", "single"), help="RKIND of the library build")
+    ap.add_argument("--order", type=int, default=2, choices=(2, 3), help="config_time_integration_order (SURVEY.md §8d: order 3 as a second line; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-members", type=int, default=3, help="independent host-resident instances alternating in the e2e leg (1..4)")
@@ -309,7 +313,8 @@ def main():
         dt = cfg["config_dt"]
     else:
         from mpas_model_b200.case import make_case
-        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars)
+        over = dict(config_time_integration_order=3) if args.order == 3 else {}
+        d, cfg = make_case(n_cells, n_lev, num_scalars=args.scalars, **over)
         dt = cfg["config_dt"]
         g = Dycore(d, cfg, device=0, precision=args.precision)
         g.atm_init_coupled_diagnostics(); g.atm_init_solve_diagnostics(dt)
