@@ -116,16 +116,18 @@ static void compute(const mpasb_dims& dm, const mpasb_config& cf, int h_ScaleWit
         if (!(cell1 <= nC || cell2 <= nC)) continue;              // only if this edge flux is needed to update owned cells
         int cell_list[20], n = 2;
         cell_list[0] = cell1; cell_list[1] = cell2;
-        for (int i = 1; i <= nec(cell1); i++) if (coc(i, cell1) != cell2) cell_list[n++] = coc(i, cell1);
+        // (cell_list(20) as in the reference; 2 + 7 + 8 entries at most with maxEdges = 8 -- a longer list is cut, not overrun)
+        for (int i = 1; i <= nec(cell1); i++) if (coc(i, cell1) != cell2 && n < 20) cell_list[n++] = coc(i, cell1);
         for (int ic = 1; ic <= nec(cell2); ic++) {
             bool add = true;
             for (int i = 0; i < n; i++) if (cell_list[i] == coc(ic, cell2)) add = false;
-            if (add) cell_list[n++] = coc(ic, cell2);
+            if (add && n < 20) cell_list[n++] = coc(ic, cell2);
         }
         o.nAdvCellsForEdge[e - 1] = n;
         real a[20], b[20];
         for (int j = 0; j < 20; j++) { a[j] = 0; b[j] = 0; }
-        auto pos = [&](int target) { int j_in = -1; for (int j = 0; j < n; j++) if (cell_list[j] == target) j_in = j; return j_in; };   // the LAST match, as the reference's loop
+        // the LAST match, as the reference's loop (a cell cut from an over-long list lands on slot 0 and is never stored wrong: n <= 20)
+        auto pos = [&](int target) { int j_in = 0; for (int j = 0; j < n; j++) if (cell_list[j] == target) j_in = j; return j_in; };
         auto d2 = [&](int i, int side) { return in.deriv_two[((size_t)(e - 1) * 2 + (side - 1)) * 15 + (i - 1)]; };
         int j = pos(cell1);
         a[j] = a[j] + d2(1, 1); b[j] = b[j] + d2(1, 1);
